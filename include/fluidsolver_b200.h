@@ -1,0 +1,183 @@
+/*
+ * fluidsolver_b200 — C ABI of the B200-native implicit-solver hot path
+ * (matrix-free variational viscosity CG, pressure Poisson CG, solid fractions).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * Every pointer named *_dev* is a DEVICE pointer on the current CUDA device; `stream`
+ * is a cudaStream_t passed as void* (NULL = legacy default stream).  Arrays "in
+ * reference layout" are dense C-order [x][y][z] (z contiguous) exactly as the reference
+ * passes them (CuPy ndarrays): MAC faces u (nx+1,ny,nz), v (nx,ny+1,nz), w (nx,ny,nz+1),
+ * fine grids (2nx+1,2ny+1,2nz+1), cells (nx,ny,nz).
+ *
+ * All functions return an int status: FS_OK (0), FS_NOT_CONVERGED (1) or a negative
+ * error (argument / CUDA error; text via fs_last_error()).  They never throw.
+ *
+ * Reference interfaces replaced (paths relative to the reference's solver/ directory):
+ *   fs_visc3d_*   ViscosityCGSolver3D.py:472-530 (extrapolate, initialize_solver, matvecmul,
+ *                 apply_viscosity) and :532-613 (class ViscosityCGSolver3D, solve)
+ *   fs_visc2d_*   ViscosityCGSolver2D.py:222-244, :246-318
+ *   fs_press*     PressureCGSolver3D.py:155-171, :173-226; PressureCGSolver2D.py:122-138, :140-179
+ *   fs_solidfrac* SolidFraction3D.py:28-32, SolidFraction2D.py:22-26 (+ SolidFractionCommon.py:4-60)
+ *   CG vector algebra: the CuPy expressions inside solve() (ViscosityCGSolver3D.py:577-610,
+ *                 PressureCGSolver3D.py:201-221), CGSolverBuffer.py:3-8 (caller-owned d,r,q,b)
+ */
+#ifndef FLUIDSOLVER_B200_H
+#define FLUIDSOLVER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_ABI_VERSION 1
+
+/* status codes */
+#define FS_OK 0
+#define FS_NOT_CONVERGED 1
+#define FS_ERR_ARG (-1)
+#define FS_ERR_CUDA (-2)
+#define FS_ERR_STATE (-3)
+
+/* element types of caller arrays and of the solver's internal vectors */
+#define FS_F32 0
+#define FS_F64 1
+
+/* solver vectors addressable through the API (internal lattice layout) */
+#define FS_VEC_X 0 /* solution            (reference: x_x,x_y,x_z) */
+#define FS_VEC_R 1 /* residual            (r_*) */
+#define FS_VEC_D 2 /* search direction    (d_*) */
+#define FS_VEC_Q 3 /* A*d                 (q_*) */
+#define FS_VEC_B 4 /* right-hand side     (b_*) */
+#define FS_NUM_VECS 5
+
+/* which entries fs_visc*_store writes into the caller's arrays */
+#define FS_STORE_ALL 0       /* every entry (debug / attribute views) */
+#define FS_STORE_INTERIOR 1  /* rows a stencil kernel writes: 1..shape-2 on every axis of each component
+                                (matvecmul / initialize_solver semantics, boundary layer untouched) */
+#define FS_STORE_FLUID 2     /* apply_viscosity semantics: indices 1..g-1 on all axes, fluid faces only */
+
+/* result of a CG run */
+typedef struct fs_cg_stats {
+    int64_t iterations; /* CG iterations executed (reference: number of loop passes) */
+    double delta;       /* final  sum r.r  (reference: self.delta) */
+    double alpha;       /* last alpha      (self.alpha) */
+    double beta;        /* last beta       (self.beta) */
+    double delta0;      /* initial sum r.r */
+    int32_t converged;  /* 1 if delta < tol^2 was reached */
+    int32_t reserved;
+} fs_cg_stats;
+
+int fs_abi_version(void);
+const char* fs_last_error(void);
+/* number of kernels this library has launched in the calling process (bench bookkeeping) */
+int64_t fs_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Viscosity, 3-D  (ViscosityCGSolver3D)
+ *
+ * The solver object works on an internal padded lattice (X=nx+1, Y=ny+1, Zp=roundup(nz+1,4)) that
+ * lives in a caller-provided device workspace; it never allocates device memory itself.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fs_visc3d fs_visc3d;
+
+size_t fs_visc3d_workspace_bytes(int nx, int ny, int nz, int dtype);
+int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* workspace_dev, size_t workspace_bytes);
+void fs_visc3d_destroy(fs_visc3d* h);
+/* lattice geometry: extents X,Y,Zp and elements per component plane-set NL = X*Y*Zp */
+int fs_visc3d_lattice(const fs_visc3d* h, int* X, int* Y, int* Zp, int64_t* NL);
+/* device pointer of component `comp` (0,1,2) of solver vector `vec` (FS_VEC_*) inside the workspace */
+void* fs_visc3d_vector_ptr(const fs_visc3d* h, int vec, int comp);
+
+/* De-interleave the reference's fine-grid inputs into SoA coefficient planes + face masks.
+ * vol = lvol / vol_norm (ViscosityCGSolver3D.py:568 uses vol_norm = cell_vol*0.125; pass 1.0 when
+ * `lvol_dev` already holds the normalised `vol`).  Fluid test: sphi >= 0 (:255). */
+int fs_visc3d_pack(fs_visc3d* h, const double* sphi_dev, const double* lvol_dev, double vol_norm, void* stream);
+/* caller MAC arrays (reference layout, FS_F32/FS_F64) -> solver vector; padding is zeroed */
+int fs_visc3d_load(fs_visc3d* h, int vec, const void* vx_dev, const void* vy_dev, const void* vz_dev, int src_dtype, void* stream);
+/* solver vector -> caller MAC arrays, entries selected by `mode` (FS_STORE_*) */
+int fs_visc3d_store(fs_visc3d* h, int vec, void* vx_dev, void* vy_dev, void* vz_dev, int dst_dtype, int mode, void* stream);
+/* extrapolate(gres, num_iter, ...) (:472-502) in place on solver vector `vec`; uses Q as scratch */
+int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream);
+/* initialize_solver (:504-513): dst = RHS built from src (solid-neighbour terms moved over) */
+int fs_visc3d_rhs(fs_visc3d* h, double scale, double mu, int src_vec, int dst_vec, void* stream);
+/* matvecmul (:515-524): dst = A*src with the reference's neighbour masks; arbitrary src */
+int fs_visc3d_apply(fs_visc3d* h, double scale, double mu, int src_vec, int dst_vec, void* stream);
+/* CG on the loaded problem: expects X (extrapolated start) and B; runs q=Ax, d=r=b-q, then the loop
+ * (:575-612).  Blocks until finished.  Returns FS_OK or FS_NOT_CONVERGED. */
+int fs_visc3d_cg(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, fs_cg_stats* stats, void* stream);
+/* Bench hook: enqueue exactly `n` CG iterations on the current state without any host sync or
+ * convergence stop (the timed window of BASELINE.json's "fixed 200 iterations" configs). */
+int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void* stream);
+/* Same window with the d-update folded into the apply (2 kernels/iteration); see DESIGN.md */
+int fs_visc3d_read_stats(fs_visc3d* h, fs_cg_stats* stats, void* stream);
+/* One call = ViscosityCGSolver3D.solve (:566-613): pack, load, 3-sweep extrapolation, RHS, CG,
+ * masked write-back into vx,vy,vz (caller dtype `vel_dtype`). */
+int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_vol,
+                    void* vx_dev, void* vy_dev, void* vz_dev, int vel_dtype,
+                    const double* sphi_dev, const double* lvol_dev,
+                    double tol, int64_t max_iter, fs_cg_stats* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Viscosity, 2-D  (ViscosityCGSolver2D) — fluid test is sphi > 0, no extrapolation, tol 1e-4
+ * lattice X=W+1, Y'=roundup(H+1,4); MAC faces u (W+1,H), v (W,H+1); fine grid (2W+1,2H+1)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fs_visc2d fs_visc2d;
+
+size_t fs_visc2d_workspace_bytes(int W, int H, int dtype);
+int fs_visc2d_create(fs_visc2d** out, int W, int H, int dtype, void* workspace_dev, size_t workspace_bytes);
+void fs_visc2d_destroy(fs_visc2d* h);
+int fs_visc2d_lattice(const fs_visc2d* h, int* X, int* Yp, int64_t* NL);
+void* fs_visc2d_vector_ptr(const fs_visc2d* h, int vec, int comp);
+int fs_visc2d_pack(fs_visc2d* h, const double* sphi_dev, const double* lvol_dev, double vol_norm, void* stream);
+int fs_visc2d_load(fs_visc2d* h, int vec, const void* vx_dev, const void* vy_dev, int src_dtype, void* stream);
+int fs_visc2d_store(fs_visc2d* h, int vec, void* vx_dev, void* vy_dev, int dst_dtype, int mode, void* stream);
+int fs_visc2d_rhs(fs_visc2d* h, double scale, double mu, int src_vec, int dst_vec, void* stream);
+int fs_visc2d_apply(fs_visc2d* h, double scale, double mu, int src_vec, int dst_vec, void* stream);
+int fs_visc2d_cg(fs_visc2d* h, double scale, double mu, double tol, int64_t max_iter, fs_cg_stats* stats, void* stream);
+int fs_visc2d_solve(fs_visc2d* h, double dt, double mu, double rho, double cell_vol,
+                    void* vx_dev, void* vy_dev, int vel_dtype,
+                    const double* sphi_dev, const double* lvol_dev,
+                    double tol, int64_t max_iter, fs_cg_stats* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Solid fractions  (SolidFraction3D / SolidFraction2D) — fp64 in, fp64 out, reference layout.
+ * Only the entries the reference writes are written (far planes keep their previous contents).
+ * ---------------------------------------------------------------------------------------- */
+int fs_solidfrac3d(int nx, int ny, int nz, const double* sphi_dev, double* wx_dev, double* wy_dev, double* wz_dev, void* stream);
+int fs_solidfrac2d(int W, int H, const double* sphi_dev, double* wx_dev, double* wy_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pressure  (PressureCGSolver3D / 2D) — fp64 state in reference layout, operating directly on the
+ * caller's CGSolverBuffer arrays (d,r,q,b) and the solver's x, all of `ncells` doubles.
+ * nz == 0 selects the 2-D solver (arrays (nx,ny); vz/wz ignored; sv has 2 components).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fs_press fs_press;
+
+size_t fs_press_workspace_bytes(int nx, int ny, int nz);
+int fs_press_create(fs_press** out, int nx, int ny, int nz, void* workspace_dev, size_t workspace_bytes);
+void fs_press_destroy(fs_press* h);
+/* initialize_solver (PressureCGSolver3D.py:155-159): weighted divergence RHS into b */
+int fs_press_rhs(fs_press* h, const double* cell_size3, const void* vx_dev, const void* vy_dev, const void* vz_dev, int vel_dtype,
+                 const double* sv_dev, const double* lphi_dev, double* b_dev,
+                 const double* wx_dev, const double* wy_dev, const double* wz_dev, void* stream);
+/* matvecmul (:161-165): out = A*v on interior fluid cells, 0 on interior non-fluid, boundary untouched */
+int fs_press_apply(fs_press* h, const double* v_dev, double* out_dev,
+                   const double* wx_dev, const double* wy_dev, const double* wz_dev, const double* lphi_dev, void* stream);
+/* apply_pressure (:167-171): velocity update + solid blend in place */
+int fs_press_update(fs_press* h, const double* cell_size3, void* vx_dev, void* vy_dev, void* vz_dev, int vel_dtype,
+                    const double* pv_dev, const double* wx_dev, const double* wy_dev, const double* wz_dev,
+                    const double* sv_dev, const double* lphi_dev, void* stream);
+/* CG loop (:198-223): x=0, q=Ax, d=r=b-q, iterate.  raise_on_fail semantics are the caller's. */
+int fs_press_cg(fs_press* h, double* x_dev, double* d_dev, double* r_dev, double* q_dev, const double* b_dev,
+                const double* wx_dev, const double* wy_dev, const double* wz_dev, const double* lphi_dev,
+                double tol, int64_t max_iter, fs_cg_stats* stats, void* stream);
+int fs_press_cg_enqueue(fs_press* h, double* x_dev, double* d_dev, double* r_dev, double* q_dev,
+                        const double* wx_dev, const double* wy_dev, const double* wz_dev, const double* lphi_dev,
+                        int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUIDSOLVER_B200_H */

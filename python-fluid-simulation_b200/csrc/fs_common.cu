@@ -1,0 +1,48 @@
+// Library-wide state and the small non-template pieces of the CG control.
+#include "fs_common.cuh"
+
+namespace fs {
+
+thread_local char g_err[512] = "";
+long long g_launches = 0;
+
+__global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_iter) {
+    st->delta = 0.0;
+    st->delta_old = 0.0;
+    st->dq = 0.0;
+    st->alpha = 0.0;
+    st->beta = 0.0;
+    st->tol2 = tol2;
+    st->delta0 = 0.0;
+    st->iter = 0;
+    st->max_iter = max_iter;
+    st->done = 0;
+    st->pad = 0;
+    for (int i = 0; i < 4; ++i) st->counter[i] = 0;
+}
+
+int CgHost::init() {
+    FS_CUDA(cudaHostAlloc((void**)&st_pinned, 2 * sizeof(CgState), cudaHostAllocDefault));
+    memset(st_pinned, 0, 2 * sizeof(CgState));
+    for (int i = 0; i < 2; ++i) FS_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    return FS_OK;
+}
+
+void CgHost::destroy() {
+    if (st_pinned) cudaFreeHost(st_pinned);
+    st_pinned = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        if (ev[i]) cudaEventDestroy(ev[i]);
+        ev[i] = nullptr;
+    }
+}
+
+}  // namespace fs
+
+extern "C" {
+
+int fs_abi_version(void) { return FS_ABI_VERSION; }
+const char* fs_last_error(void) { return fs::g_err; }
+int64_t fs_launch_count(void) { return fs::g_launches; }
+
+}  // extern "C"

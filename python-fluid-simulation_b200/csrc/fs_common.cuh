@@ -1,0 +1,282 @@
+// Shared device/host helpers for the B200 (sm_100a) implicit-solver kernels:
+// error plumbing for the C ABI, deterministic block/grid reductions, and the fused CG
+// vector kernels (K2: x,r update + r.r ; K3: d update) that replace the CuPy expression
+// chains of the reference's solve() loops (ViscosityCGSolver3D.py:592-610,
+// PressureCGSolver3D.py:211-221).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fluidsolver_b200.h"
+
+namespace fs {
+
+// ---------------------------------------------------------------------------------------------
+// error handling (C ABI never throws)
+// ---------------------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern long long g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define FS_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) return ::fs::fail(FS_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define FS_LAUNCH_CHECK()                                                                   \
+    do {                                                                                   \
+        ++::fs::g_launches;                                                                \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) return ::fs::fail(FS_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+#define FS_TRY(expr)                 \
+    do {                             \
+        int _s = (expr);             \
+        if (_s < 0) return _s;       \
+    } while (0)
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// device-resident CG control block: alpha/beta/convergence live on the GPU so the iteration
+// needs no host round trip (the reference does two blocking .item() reads per iteration).
+// ---------------------------------------------------------------------------------------------
+struct CgState {
+    double delta;      // current  r.r
+    double delta_old;  // previous r.r
+    double dq;         // d.q of the current iteration
+    double alpha, beta;
+    double tol2;       // tol*tol
+    double delta0;
+    long long iter;
+    long long max_iter;
+    int done;          // 0 running, 1 converged, 2 iteration budget exhausted
+    int pad;
+    unsigned int counter[4];  // last-block tickets (one per reducing kernel type)
+};
+
+// ---------------------------------------------------------------------------------------------
+// reductions: warp shuffle -> shared -> one partial per block -> last block sums the partials
+// in a fixed order (deterministic run to run; no floating-point atomics).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// all threads of the block must call; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* sm /*>=32 doubles*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect sm reuse
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < nwarps ? sm[lane] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+// Grid-wide sum with a "last block finishes" epilogue.  `fin(total)` runs in thread 0 of the last
+// block to arrive, after every block's partial is visible.  blockDim must be 1-D.
+template <class Fin>
+__device__ __forceinline__ void grid_sum_finish(double v, double* partials, unsigned int* counter, Fin fin) {
+    __shared__ double sm[32];
+    __shared__ bool is_last;
+    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) {
+        partials[bid] = v;
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == nblocks - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) s += __ldcg(partials + i);
+        s = block_sum(s, sm);
+        if (threadIdx.x == 0) {
+            *counter = 0;
+            fin(s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector types for 16-byte accesses
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int N = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
+
+__device__ __forceinline__ void v_get(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void v_get(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ float4 v_make(const float* o) { return make_float4(o[0], o[1], o[2], o[3]); }
+__device__ __forceinline__ double2 v_make(const double* o) { return make_double2(o[0], o[1]); }
+
+constexpr int kVecThreads = 256;
+constexpr int kVecBlocksPerSM = 8;
+constexpr int kVecGrid = kSMs * kVecBlocksPerSM;  // persistent-style grid for streaming kernels
+
+// K2:  alpha = delta/dq ; x += alpha d ; r -= alpha q ; delta' = r.r ; convergence bookkeeping.
+// (ViscosityCGSolver3D.py:594-606 / PressureCGSolver3D.py:211-219)   n must be a multiple of Vec16<T>::N.
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, T* __restrict__ x, T* __restrict__ r,
+                                                                   const T* __restrict__ d, const T* __restrict__ q,
+                                                                   CgState* st, double* partials) {
+    if (*(volatile int*)&st->done) return;
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    const double alpha_d = st->delta / st->dq;
+    const T alpha = (T)alpha_d;
+    double acc = 0.0;
+    const long long nv = n / N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        V xv = reinterpret_cast<V*>(x)[i], rv = reinterpret_cast<V*>(r)[i];
+        V dv = __ldg(reinterpret_cast<const V*>(d) + i), qv = __ldg(reinterpret_cast<const V*>(q) + i);
+        T xa[N], ra[N], da[N], qa[N];
+        v_get(xv, xa); v_get(rv, ra); v_get(dv, da); v_get(qv, qa);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            xa[k] = xa[k] + alpha * da[k];
+            ra[k] = ra[k] - alpha * qa[k];
+            acc += (double)ra[k] * (double)ra[k];
+        }
+        reinterpret_cast<V*>(x)[i] = v_make(xa);
+        reinterpret_cast<V*>(r)[i] = v_make(ra);
+    }
+    grid_sum_finish(acc, partials, &st->counter[1], [=](double s) {
+        st->alpha = alpha_d;
+        st->delta_old = st->delta;
+        st->delta = s;
+        st->iter += 1;
+        if (s < st->tol2) st->done = 1;
+        else if (st->iter >= st->max_iter || !(s == s)) st->done = 2;  // NaN: the reference would spin to max_iter
+    });
+}
+
+// K3:  beta = delta/delta_old ; d = r + beta d      (ViscosityCGSolver3D.py:607-610)
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) cg_update_d_kernel(long long n, T* __restrict__ d, const T* __restrict__ r, CgState* st) {
+    if (*(volatile int*)&st->done) return;
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    const double beta_d = st->delta / st->delta_old;
+    const T beta = (T)beta_d;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->beta = beta_d;
+    const long long nv = n / N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        V dv = reinterpret_cast<V*>(d)[i];
+        V rv = __ldg(reinterpret_cast<const V*>(r) + i);
+        T da[N], ra[N];
+        v_get(dv, da); v_get(rv, ra);
+#pragma unroll
+        for (int k = 0; k < N; ++k) da[k] = ra[k] + beta * da[k];
+        reinterpret_cast<V*>(d)[i] = v_make(da);
+    }
+}
+
+// start of a solve:  d = b - q ; r = d ; delta0 = r.r   (ViscosityCGSolver3D.py:577-587)
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) cg_residual_init_kernel(long long n, const T* __restrict__ b, const T* __restrict__ q,
+                                                                       T* __restrict__ d, T* __restrict__ r, CgState* st, double* partials) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    double acc = 0.0;
+    const long long nv = n / N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        V bv = __ldg(reinterpret_cast<const V*>(b) + i), qv = __ldg(reinterpret_cast<const V*>(q) + i);
+        T ba[N], qa[N], da[N];
+        v_get(bv, ba); v_get(qv, qa);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            da[k] = ba[k] - qa[k];
+            acc += (double)da[k] * (double)da[k];
+        }
+        reinterpret_cast<V*>(d)[i] = v_make(da);
+        reinterpret_cast<V*>(r)[i] = v_make(da);
+    }
+    grid_sum_finish(acc, partials, &st->counter[2], [=](double s) {
+        st->delta = s;
+        st->delta0 = s;
+        st->delta_old = s;
+        if (s < st->tol2) st->done = 1;           // `if not self.delta < tol ** 2:` skips the loop
+    });
+}
+
+__global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_iter);
+
+// host-side CG control shared by all solvers ------------------------------------------------
+struct CgHost {
+    CgState* st_dev = nullptr;      // in workspace
+    double* partials_dev = nullptr; // in workspace, >= max grid size of any reducing kernel
+    CgState* st_pinned = nullptr;   // cudaHostAlloc, 2 slots
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int init();
+    void destroy();
+};
+
+// Runs `iter_fn(stream)` (enqueue K1,K2,K3 once) in batches until the device flags completion.
+// Blocks the calling thread; fills stats.  Returns FS_OK / FS_NOT_CONVERGED / <0.
+template <class IterFn>
+int cg_drive(CgHost& c, IterFn iter_fn, long long max_iter, fs_cg_stats* stats, cudaStream_t s, int batch = 16) {
+    // state already initialised and residual_init enqueued by the caller
+    int slot = 0;
+    bool pending[2] = {false, false};
+    long long enq = 0;
+    int status = FS_OK;
+    for (;;) {
+        long long nb = batch;
+        if (enq + nb > max_iter) nb = max_iter - enq;
+        for (long long k = 0; k < nb; ++k) FS_TRY(iter_fn(s));
+        enq += nb;
+        FS_CUDA(cudaMemcpyAsync(&c.st_pinned[slot], c.st_dev, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+        FS_CUDA(cudaEventRecord(c.ev[slot], s));
+        pending[slot] = true;
+        // look at the previous batch while this one runs
+        int prev = slot ^ 1;
+        bool finished = false;
+        if (pending[prev]) {
+            FS_CUDA(cudaEventSynchronize(c.ev[prev]));
+            pending[prev] = false;
+            if (c.st_pinned[prev].done) finished = true;
+        }
+        if (finished || enq >= max_iter) {
+            FS_CUDA(cudaEventSynchronize(c.ev[slot]));
+            pending[slot] = false;
+            const CgState& h = c.st_pinned[slot];
+            if (stats) {
+                stats->iterations = h.iter;
+                stats->delta = h.delta;
+                stats->alpha = h.alpha;
+                stats->beta = h.beta;
+                stats->delta0 = h.delta0;
+                stats->converged = (h.done == 1);
+                stats->reserved = 0;
+            }
+            status = (h.done == 1) ? FS_OK : FS_NOT_CONVERGED;
+            break;
+        }
+        slot ^= 1;
+    }
+    return status;
+}
+
+}  // namespace fs

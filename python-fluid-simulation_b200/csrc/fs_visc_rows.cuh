@@ -1,0 +1,99 @@
+// Row evaluator of the variational viscosity operator on the packed MAC lattice, generic in the
+// dimension D (2 or 3) and in the component A of the row.
+//
+// Reference per-thread code: ViscosityCGSolver3D.py:248-456 (apply), :41-246 (RHS);
+// ViscosityCGSolver2D.py:105-206, :6-102.  Here the 3x(1+14) hand-unrolled terms collapse to one
+// rule, because every term of a row for component A has one of two shapes:
+//   same-component neighbour along axis ax :  coef(ax) * vol_{hi|lo}(ax) * vel_A(i +/- e_ax),
+//                                             coef = 2*scale*mu if ax == A else scale*mu
+//   cross-component B (own axis b)         :  scale*mu * vol_hi(b) * [ +vel_B(i+e_b) - vel_B(i+e_b-e_A) ]
+//                                             scale*mu * vol_lo(b) * [ -vel_B(i)     + vel_B(i-e_A)     ]
+// with  vol_hi(A)=Vc(i), vol_lo(A)=Vc(i-e_A)  and, for ax != A,  vol_hi(ax)=E_{A,ax}(i+e_ax), vol_lo(ax)=E_{A,ax}(i)
+// (E = edge-centred volume in 3-D, node volume in 2-D).  Term order and association follow the reference
+// (+x,-x,+y,-y,+z,-z for the own component, then the other components in ascending order), so that the
+// EXACT instantiation reproduces the reference's fp64 results bit for bit (no FMA contraction).
+#pragma once
+#include "fs_common.cuh"
+
+namespace fs {
+
+template <bool EXACT> struct Ar;
+template <> struct Ar<true> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+};
+template <> struct Ar<false> {
+    template <typename T> static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
+    template <typename T> static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    template <typename T> static __device__ __forceinline__ T sub(T a, T b) { return a - b; }
+};
+
+// packed coefficient planes: [0..D-1] face volumes (NaN on rows that are never computed),
+// [D] cell-centre volume, [D+a+b] edge/node volume between axes a<b.
+template <int D> struct CoefCount { static constexpr int value = (D == 3) ? 7 : 4; };
+
+enum RowMode { ROW_APPLY = 0, ROW_RHS = 1 };
+
+// NB(comp, idx) returns the neighbour value to use (already masked as the mode requires).
+template <typename T, int D, int A, bool EXACT, int MODE, class NB>
+__device__ __forceinline__ T visc_row(const T* const* __restrict__ coef, long long i, const long long* st,
+                                       T center, T own, T s, T s2, NB nb) {
+    using R = Ar<EXACT>;
+    T hi[D], lo[D];
+#pragma unroll
+    for (int ax = 0; ax < D; ++ax) {
+        if (ax == A) {
+            hi[ax] = __ldg(coef[D] + i);
+            lo[ax] = __ldg(coef[D] + i - st[A]);
+        } else {
+            const T* E = coef[D + A + ax];
+            hi[ax] = __ldg(E + i + st[ax]);
+            lo[ax] = __ldg(E + i);
+        }
+    }
+    T val;
+    if (MODE == ROW_APPLY) {
+        // diag = vol_center + scale*mu*(w*hi0 + w*lo0 + w*hi1 + ...)   left to right, w=2 on the own axis
+        T sum = T(0);
+#pragma unroll
+        for (int ax = 0; ax < D; ++ax) {
+            T h = (ax == A) ? R::mul(T(2), hi[ax]) : hi[ax];
+            T l = (ax == A) ? R::mul(T(2), lo[ax]) : lo[ax];
+            sum = (ax == 0) ? R::add(h, l) : R::add(R::add(sum, h), l);
+        }
+        T diag = R::add(center, R::mul(s, sum));
+        val = R::mul(diag, own);
+    } else {
+        val = R::mul(own, center);
+    }
+    // `plus` terms are subtracted by the apply and added by the RHS; `minus` terms the other way round
+    auto plus = [&](T c, T vol, T v) {
+        T t = R::mul(R::mul(c, vol), v);
+        val = (MODE == ROW_APPLY) ? R::sub(val, t) : R::add(val, t);
+    };
+    auto minus = [&](T c, T vol, T v) {
+        T t = R::mul(R::mul(c, vol), v);
+        val = (MODE == ROW_APPLY) ? R::add(val, t) : R::sub(val, t);
+    };
+#pragma unroll
+    for (int ax = 0; ax < D; ++ax) {
+        const T c = (ax == A) ? s2 : s;
+        plus(c, hi[ax], nb(A, i + st[ax]));
+        plus(c, lo[ax], nb(A, i - st[ax]));
+    }
+#pragma unroll
+    for (int B = 0; B < D; ++B) {
+        if (B == A) continue;
+        plus(s, hi[B], nb(B, i + st[B]));
+        minus(s, hi[B], nb(B, i + st[B] - st[A]));
+        minus(s, lo[B], nb(B, i));
+        plus(s, lo[B], nb(B, i - st[A]));
+    }
+    return val;
+}
+
+}  // namespace fs

@@ -1,0 +1,247 @@
+"""GPU parity tests: the sm_100a viscosity path (through the C ABI / drop-in classes) against the golden
+vectors of the reference's own kernels and against the NumPy oracle.
+
+Tolerances (BASELINE.json north_star): integer/mask work bit-exact; one operator apply within 1e-5
+relative for fp32 (we hold fp64 to 1e-13); CG iteration count within +-2 %, final velocities within
+1e-4 relative L2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float64, torch.float32]
+APPLY_TOL = {torch.float64: 1e-13, torch.float32: 1e-5}
+
+
+def _dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def _written(out, ref):
+    """entries the reference wrote (finite in the NaN-poisoned golden array)"""
+    m = ~np.isnan(ref)
+    return out[m], ref[m]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_matvecmul_and_rhs_vs_reference(dtype):
+    from solver import ViscosityCGSolver3D as V
+    f = load_golden("visc3d_kernels_6x7x8")
+    g = tuple(int(n) for n in f["gres"])
+    sc, mu = float(f["scale"]), float(f["mu"])
+    v = [_dev(f[k]) for k in ("vx", "vy", "vz")]
+    sphi, vol = _dev(f["sphi"]), _dev(f["vol"])
+    for fn, key in ((lambda o: V.matvecmul(g, sc, mu, *v, *o, sphi, vol, dtype=dtype), "q"),
+                    (lambda o: V.initialize_solver(g, sc, mu, *v, sphi, None, vol, *o, dtype=dtype), "b")):
+        outs = [torch.full_like(a, float("nan")) for a in v]
+        fn(outs)
+        for o, n in zip(outs, "xyz"):
+            ref = f[key + n]
+            o = o.cpu().numpy()
+            assert np.array_equal(np.isnan(o), np.isnan(ref)), "set of written entries differs from the reference"
+            a, b = _written(o, ref)
+            assert rel_max(a, b) < APPLY_TOL[dtype]
+            assert np.array_equal(a == 0, b == 0)            # solid rows are exactly zero
+            if dtype == torch.float64:
+                assert np.array_equal(a, b), "fp64 general apply/RHS is expected to be bit-exact"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_extrapolate_and_writeback_vs_reference(dtype):
+    from solver import ViscosityCGSolver3D as V
+    f = load_golden("visc3d_kernels_6x7x8")
+    g = tuple(int(n) for n in f["gres"])
+    v = [_dev(f[k]) for k in ("vx", "vy", "vz")]
+    V.extrapolate(g, 3, *v, _dev(f["sphi"]), dtype=dtype)
+    for o, n in zip(v, "xyz"):
+        ref = f["e" + n]
+        o = o.cpu().numpy()
+        changed_ref = ref != f["v" + n]
+        assert np.array_equal(o != f["v" + n], changed_ref) or dtype == torch.float32
+        assert rel_max(o, ref) < (1e-15 if dtype == torch.float64 else 1e-6)
+    # masked write-back into fp32 caller arrays: bit-exact (values round-trip through the solver dtype)
+    wb = [torch.full(a.shape, float("nan"), dtype=torch.float32, device="cuda") for a in v]
+    src = [_dev(f[k]) for k in ("vx", "vy", "vz")]
+    V.apply_viscosity(g, *wb, *src, _dev(f["sphi"]), None, dtype=torch.float64)
+    for o, n in zip(wb, "xyz"):
+        ref = f["wb" + n]
+        o = o.cpu().numpy()
+        assert np.array_equal(np.isnan(o), np.isnan(ref))
+        assert np.array_equal(o[~np.isnan(ref)], ref[~np.isnan(ref)])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("tag", ["visc3d_solve_8x10x8", "visc3d_solve_stiff_6x8x6"])
+def test_solve_vs_reference(tag, dtype):
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    f = load_golden(tag)
+    s = ViscosityCGSolver3D(f["gres"], f["bound_size"], dtype=dtype)
+    assert s.cell_vol == float(f["cell_vol"])
+    v = [_dev(f[k]) for k in ("vx", "vy", "vz")]          # fp32, as the notebook passes them
+    sv = torch.zeros(tuple(f["sphi"].shape) + (3,), dtype=torch.float64, device="cuda")
+    s.solve(float(f["dt"]), float(f["mu"]), float(f["rho"]), *v, _dev(f["sphi"]), sv, _dev(f["lphi"]), _dev(f["lvol"]), tol=float(f["tol"]))
+    it_ref = int(f["iterations"])
+    assert abs(s.iterations - it_ref) <= max(1, round(0.02 * it_ref)), (s.iterations, it_ref)
+    assert s.delta < float(f["tol"]) ** 2
+    for a, n in zip(v, "xyz"):
+        assert a.dtype == torch.float32
+        assert rel_l2(a.cpu().numpy(), f[f"v{n}_new"]) < 1e-4
+    for a, n in zip((s.x_x, s.x_y, s.x_z), "xyz"):
+        assert rel_l2(a.cpu().numpy(), f["x_" + n]) < 1e-4
+    for a, n in zip((s.b_x, s.b_y, s.b_z), "xyz"):
+        assert rel_l2(a.cpu().numpy(), f["b_" + n]) < (1e-13 if dtype == torch.float64 else 1e-6)
+    if dtype == torch.float64:
+        assert s.iterations == it_ref
+        for a, n in zip(v, "xyz"):
+            assert rel_l2(a.cpu().numpy(), f[f"v{n}_new"]) < 1e-7
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N,mu", [(24, 1.0), (32, 100.0)])
+def test_solve_vs_oracle_buckling(N, mu, dtype):
+    """The benchmark scene at sizes the NumPy oracle finishes in seconds."""
+    import scenes
+    from oracle import numpy_oracle as O
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    sc = scenes.buckling(N, device="cuda", mu=mu)
+    ref = O.ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
+    rv = [sc[k].cpu().numpy().copy() for k in ("vx", "vy", "vz")]
+    ref.solve(sc["dt"], mu, sc["rho"], *rv, sc["sphi"].cpu().numpy(), None, None, sc["lvol"].cpu().numpy())
+    s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], dtype=dtype)
+    v = [sc[k].clone() for k in ("vx", "vy", "vz")]
+    s.solve(sc["dt"], mu, sc["rho"], *v, sc["sphi"], None, sc["lphi"], sc["lvol"])
+    it_ref = ref.trace.iterations
+    assert it_ref > 10
+    assert abs(s.iterations - it_ref) <= max(1, round(0.02 * it_ref)), (s.iterations, it_ref)
+    for a, b in zip(v, rv):
+        assert rel_l2(a.cpu().numpy(), b) < 1e-4
+
+
+def test_fixed_iterations_raise_like_reference():
+    """max_iter exhausted -> ValueError("Failed to converge!") after exactly max_iter iterations, no write-back."""
+    import scenes
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    sc = scenes.buckling(16, device="cuda", mu=100.0)
+    s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
+    s.max_iter = 7
+    v = [sc[k].clone() for k in ("vx", "vy", "vz")]
+    with pytest.raises(ValueError, match="Failed to converge!"):
+        s.solve(sc["dt"], 100.0, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"], tol=0.0)
+    assert s.iterations == 7
+    for a, k in zip(v, ("vx", "vy", "vz")):
+        assert torch.equal(a, sc[k])
+
+
+def test_host_arrays_and_noncontiguous_inputs():
+    """solve() accepts host NumPy arrays (copied in/out) and non-contiguous device views, updating them in place."""
+    import scenes
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    sc = scenes.buckling(16, device="cuda")
+    s = ViscosityCGSolver3D(np.array(sc["gres"]), np.array(sc["bound_size"], dtype=np.float32))
+    ref = [sc[k].clone() for k in ("vx", "vy", "vz")]
+    s.solve(sc["dt"], 1.0, sc["rho"], *ref, sc["sphi"], None, None, sc["lvol"])
+    host = [sc[k].cpu().numpy().copy() for k in ("vx", "vy", "vz")]
+    s.solve(sc["dt"], 1.0, sc["rho"], *host, sc["sphi"].cpu().numpy(), None, None, sc["lvol"].cpu().numpy())
+    for a, b in zip(host, ref):
+        assert np.array_equal(a, b.cpu().numpy())
+    big = [torch.zeros(tuple(2 * n for n in sc[k].shape), dtype=torch.float32, device="cuda") for k in ("vx", "vy", "vz")]
+    views = [b[::2, ::2, ::2] for b in big]
+    for vw, k in zip(views, ("vx", "vy", "vz")):
+        vw.copy_(sc[k])
+    s.solve(sc["dt"], 1.0, sc["rho"], *views, sc["sphi"], None, None, sc["lvol"])
+    for a, b in zip(views, ref):
+        assert torch.equal(a, b)
+
+
+def test_argument_errors():
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    s = ViscosityCGSolver3D((8, 8, 8), (0.1, 0.1, 0.1))
+    bad = torch.zeros((8, 8, 8), device="cuda")
+    ok = [torch.zeros(sh, device="cuda") for sh in ((9, 8, 8), (8, 9, 8), (8, 8, 9))]
+    fine = torch.ones((17, 17, 17), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        s.solve(0.01, 1.0, 1000.0, bad, ok[1], ok[2], fine, None, None, fine)
+    with pytest.raises(TypeError):
+        s.solve(0.01, 1.0, 1000.0, ok[0].int(), ok[1], ok[2], fine, None, None, fine)
+    with pytest.raises(TypeError):
+        s.solve(0.01, 1.0, 1000.0, [1, 2], ok[1], ok[2], fine, None, None, fine)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_operator_properties_large(dtype):
+    """Size-independent properties at a grid the oracle would take minutes for: symmetry of the operator on
+    interior fluid rows and A*const = Vface*const when nothing is solid and vol == 1."""
+    from solver import ViscosityCGSolver3D as V
+    g = (96, 80, 112)
+    fine = tuple(2 * n + 1 for n in g)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    sphi = torch.randn(fine, dtype=torch.float64, device="cuda", generator=gen)
+    vol = torch.rand(fine, dtype=torch.float64, device="cuda", generator=gen)
+    shapes = [(g[0] + 1, g[1], g[2]), (g[0], g[1] + 1, g[2]), (g[0], g[1], g[2] + 1)]
+    offs = [(0, 1, 1), (1, 0, 1), (1, 1, 0)]
+
+    def field():
+        out = []
+        for s, o in zip(shapes, offs):
+            a = torch.zeros(s, dtype=torch.float64, device="cuda")
+            a[1:-1, 1:-1, 1:-1] = torch.randn(tuple(n - 2 for n in s), dtype=torch.float64, device="cuda", generator=gen)
+            m = sphi[o[0]::2, o[1]::2, o[2]::2][: s[0], : s[1], : s[2]] >= 0
+            out.append(a * m)
+        return out
+
+    a, b = field(), field()
+    Aa = [torch.zeros_like(x) for x in a]
+    Ab = [torch.zeros_like(x) for x in a]
+    V.matvecmul(g, 0.7, 1.3, *a, *Aa, sphi, vol, dtype=dtype)
+    V.matvecmul(g, 0.7, 1.3, *b, *Ab, sphi, vol, dtype=dtype)
+    lhs = sum(float((x * y).sum()) for x, y in zip(b, Aa))
+    rhs = sum(float((x * y).sum()) for x, y in zip(a, Ab))
+    assert abs(lhs - rhs) <= (1e-11 if dtype == torch.float64 else 2e-5) * abs(lhs)
+    ones = [torch.full(s, 3.0, dtype=torch.float64, device="cuda") for s in shapes]
+    q = [torch.zeros_like(x) for x in ones]
+    one = torch.ones(fine, dtype=torch.float64, device="cuda")
+    V.matvecmul(g, 0.7, 1.3, *ones, *q, one, one, dtype=dtype)
+    for x in q:
+        assert float((x[1:-1, 1:-1, 1:-1] - 3.0).abs().max()) < (1e-12 if dtype == torch.float64 else 1e-4)
+        assert float(x[0].abs().max()) == 0 and float(x[-1].abs().max()) == 0
+
+
+def test_cg_loop_kernel_matches_masked_apply():
+    """The CG-loop apply (no neighbour masks, NaN-tagged rows) equals the masked apply on vectors that vanish on
+    non-computed rows, and the alpha it feeds to K2 equals delta / (d.q)."""
+    import ctypes
+    import scenes
+    from solver import _native as N
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    sc = scenes.buckling(24, device="cuda", mu=10.0)
+    lib = N.load()
+    for dtype in DTYPES:
+        s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], dtype=dtype)
+        s.max_iter = 0                      # pack + load + extrapolate + RHS + r0, no iteration
+        v = [sc[k].clone() for k in ("vx", "vy", "vz")]
+        with pytest.raises(ValueError):
+            s.solve(sc["dt"], 10.0, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"], tol=0.0)
+        assert s.iterations == 0
+        e = s._e
+        scale = sc["dt"] / s.cell_vol / sc["rho"]
+        d = [x.double().clone() for x in (s.d_x, s.d_y, s.d_z)]
+        delta0 = sum(float((x * x).sum()) for x in d)
+        assert delta0 > 0
+        N.check(lib.fs_visc3d_apply(e.h, scale, 10.0, N.VEC_D, N.VEC_B, 0), "apply")      # masked kernel -> B
+        torch.cuda.synchronize()
+        masked = [x.double().clone() for x in (s.b_x, s.b_y, s.b_z)]
+        N.check(lib.fs_visc3d_cg_enqueue(e.h, scale, 10.0, 1, 0), "enqueue")              # K1 (-> Q), K2, K3
+        torch.cuda.synchronize()
+        hot = [x.double() for x in (s.q_x, s.q_y, s.q_z)]
+        for a, b in zip(hot, masked):
+            assert float((a - b).abs().max()) <= (1e-12 if dtype == torch.float64 else 2e-5) * float(b.abs().max())
+        st = N.CgStats()
+        N.check(lib.fs_visc3d_read_stats(e.h, ctypes.byref(st), 0), "stats")
+        assert st.iterations == 1
+        dq = sum(float((x * y).sum()) for x, y in zip(d, hot))
+        assert abs(st.alpha - delta0 / dq) <= 1e-9 * abs(st.alpha)
