@@ -21,6 +21,13 @@ __global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_ite
     for (int i = 0; i < 4; ++i) st->counter[i] = 0;
 }
 
+// bench hook: let already-initialised state run for an unbounded number of iterations (no convergence stop)
+__global__ void cg_state_unlimit_kernel(CgState* st) {
+    st->done = 0;
+    st->tol2 = -1.0;
+    st->max_iter = 0x7fffffffffffffffLL;
+}
+
 int CgHost::init() {
     FS_CUDA(cudaHostAlloc((void**)&st_pinned, 2 * sizeof(CgState), cudaHostAllocDefault));
     memset(st_pinned, 0, 2 * sizeof(CgState));

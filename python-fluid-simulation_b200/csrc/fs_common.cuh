@@ -135,32 +135,52 @@ constexpr int kVecThreads = 256;
 constexpr int kVecBlocksPerSM = 8;
 constexpr int kVecGrid = kSMs * kVecBlocksPerSM;  // persistent-style grid for streaming kernels
 
+// Streaming access helper: VEC elements per 16-byte access when the arrays are 16-byte aligned
+// (VEC = Vec16<T>::N), scalar otherwise (VEC = 1).  The scalar tail n % VEC is handled by the same loop body.
+template <typename T, int VEC> struct Chunk {
+    T a[VEC];
+    __device__ __forceinline__ void load(const T* p, long long i) {
+        if constexpr (VEC == 1) a[0] = p[i];
+        else v_get(reinterpret_cast<const typename Vec16<T>::type*>(p)[i], a);
+    }
+    __device__ __forceinline__ void store(T* p, long long i) const {
+        if constexpr (VEC == 1) p[i] = a[0];
+        else reinterpret_cast<typename Vec16<T>::type*>(p)[i] = v_make(a);
+    }
+};
+
+#define FS_STREAM_SETUP(n, VEC)                                             \
+    const long long _nv = (n) / (VEC);                                      \
+    const long long _stride = (long long)gridDim.x * blockDim.x;            \
+    const long long _t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+
 // K2:  alpha = delta/dq ; x += alpha d ; r -= alpha q ; delta' = r.r ; convergence bookkeeping.
-// (ViscosityCGSolver3D.py:594-606 / PressureCGSolver3D.py:211-219)   n must be a multiple of Vec16<T>::N.
-template <typename T>
+// (ViscosityCGSolver3D.py:594-606 / PressureCGSolver3D.py:211-219)
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, T* __restrict__ x, T* __restrict__ r,
                                                                    const T* __restrict__ d, const T* __restrict__ q,
                                                                    CgState* st, double* partials) {
     if (*(volatile int*)&st->done) return;
-    using V = typename Vec16<T>::type;
-    constexpr int N = Vec16<T>::N;
     const double alpha_d = st->delta / st->dq;
     const T alpha = (T)alpha_d;
     double acc = 0.0;
-    const long long nv = n / N;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
-        V xv = reinterpret_cast<V*>(x)[i], rv = reinterpret_cast<V*>(r)[i];
-        V dv = __ldg(reinterpret_cast<const V*>(d) + i), qv = __ldg(reinterpret_cast<const V*>(q) + i);
-        T xa[N], ra[N], da[N], qa[N];
-        v_get(xv, xa); v_get(rv, ra); v_get(dv, da); v_get(qv, qa);
+    FS_STREAM_SETUP(n, VEC)
+    for (long long i = _t0; i < _nv; i += _stride) {
+        Chunk<T, VEC> xv, rv, dv, qv;
+        xv.load(x, i); rv.load(r, i); dv.load(d, i); qv.load(q, i);
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            xa[k] = xa[k] + alpha * da[k];
-            ra[k] = ra[k] - alpha * qa[k];
-            acc += (double)ra[k] * (double)ra[k];
+        for (int k = 0; k < VEC; ++k) {
+            xv.a[k] = xv.a[k] + alpha * dv.a[k];
+            rv.a[k] = rv.a[k] - alpha * qv.a[k];
+            acc += (double)rv.a[k] * (double)rv.a[k];
         }
-        reinterpret_cast<V*>(x)[i] = v_make(xa);
-        reinterpret_cast<V*>(r)[i] = v_make(ra);
+        xv.store(x, i); rv.store(r, i);
+    }
+    for (long long i = _nv * VEC + _t0; i < n; i += _stride) {   // scalar tail (n % VEC elements)
+        x[i] = x[i] + alpha * d[i];
+        const T rr = r[i] - alpha * q[i];
+        r[i] = rr;
+        acc += (double)rr * (double)rr;
     }
     grid_sum_finish(acc, partials, &st->counter[1], [=](double s) {
         st->alpha = alpha_d;
@@ -173,45 +193,43 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, 
 }
 
 // K3:  beta = delta/delta_old ; d = r + beta d      (ViscosityCGSolver3D.py:607-610)
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kVecThreads) cg_update_d_kernel(long long n, T* __restrict__ d, const T* __restrict__ r, CgState* st) {
     if (*(volatile int*)&st->done) return;
-    using V = typename Vec16<T>::type;
-    constexpr int N = Vec16<T>::N;
     const double beta_d = st->delta / st->delta_old;
     const T beta = (T)beta_d;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->beta = beta_d;
-    const long long nv = n / N;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
-        V dv = reinterpret_cast<V*>(d)[i];
-        V rv = __ldg(reinterpret_cast<const V*>(r) + i);
-        T da[N], ra[N];
-        v_get(dv, da); v_get(rv, ra);
+    FS_STREAM_SETUP(n, VEC)
+    for (long long i = _t0; i < _nv; i += _stride) {
+        Chunk<T, VEC> dv, rv;
+        dv.load(d, i); rv.load(r, i);
 #pragma unroll
-        for (int k = 0; k < N; ++k) da[k] = ra[k] + beta * da[k];
-        reinterpret_cast<V*>(d)[i] = v_make(da);
+        for (int k = 0; k < VEC; ++k) dv.a[k] = rv.a[k] + beta * dv.a[k];
+        dv.store(d, i);
     }
+    for (long long i = _nv * VEC + _t0; i < n; i += _stride) d[i] = r[i] + beta * d[i];
 }
 
 // start of a solve:  d = b - q ; r = d ; delta0 = r.r   (ViscosityCGSolver3D.py:577-587)
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kVecThreads) cg_residual_init_kernel(long long n, const T* __restrict__ b, const T* __restrict__ q,
                                                                        T* __restrict__ d, T* __restrict__ r, CgState* st, double* partials) {
-    using V = typename Vec16<T>::type;
-    constexpr int N = Vec16<T>::N;
     double acc = 0.0;
-    const long long nv = n / N;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
-        V bv = __ldg(reinterpret_cast<const V*>(b) + i), qv = __ldg(reinterpret_cast<const V*>(q) + i);
-        T ba[N], qa[N], da[N];
-        v_get(bv, ba); v_get(qv, qa);
+    FS_STREAM_SETUP(n, VEC)
+    for (long long i = _t0; i < _nv; i += _stride) {
+        Chunk<T, VEC> bv, qv;
+        bv.load(b, i); qv.load(q, i);
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            da[k] = ba[k] - qa[k];
-            acc += (double)da[k] * (double)da[k];
+        for (int k = 0; k < VEC; ++k) {
+            bv.a[k] = bv.a[k] - qv.a[k];
+            acc += (double)bv.a[k] * (double)bv.a[k];
         }
-        reinterpret_cast<V*>(d)[i] = v_make(da);
-        reinterpret_cast<V*>(r)[i] = v_make(da);
+        bv.store(d, i); bv.store(r, i);
+    }
+    for (long long i = _nv * VEC + _t0; i < n; i += _stride) {
+        const T dd = b[i] - q[i];
+        d[i] = dd; r[i] = dd;
+        acc += (double)dd * (double)dd;
     }
     grid_sum_finish(acc, partials, &st->counter[2], [=](double s) {
         st->delta = s;
@@ -221,7 +239,48 @@ __global__ void __launch_bounds__(kVecThreads) cg_residual_init_kernel(long long
     });
 }
 
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+inline int vec_grid(long long n, int vec) {
+    long long b = (n / vec + kVecThreads - 1) / kVecThreads;
+    if (b < 1) b = 1;
+    return (int)(b < kVecGrid ? b : kVecGrid);
+}
+
+template <typename T>
+int cg_launch_update_xr(long long n, T* x, T* r, const T* d, const T* q, CgState* st, double* partials, cudaStream_t s) {
+    constexpr int N = Vec16<T>::N;
+    if (aligned16(x) && aligned16(r) && aligned16(d) && aligned16(q))
+        cg_update_xr_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials);
+    else
+        cg_update_xr_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials);
+    FS_LAUNCH_CHECK();
+    return FS_OK;
+}
+
+template <typename T>
+int cg_launch_update_d(long long n, T* d, const T* r, CgState* st, cudaStream_t s) {
+    constexpr int N = Vec16<T>::N;
+    if (aligned16(d) && aligned16(r))
+        cg_update_d_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, d, r, st);
+    else
+        cg_update_d_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, d, r, st);
+    FS_LAUNCH_CHECK();
+    return FS_OK;
+}
+
+template <typename T>
+int cg_launch_residual_init(long long n, const T* b, const T* q, T* d, T* r, CgState* st, double* partials, cudaStream_t s) {
+    constexpr int N = Vec16<T>::N;
+    if (aligned16(b) && aligned16(q) && aligned16(d) && aligned16(r))
+        cg_residual_init_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, b, q, d, r, st, partials);
+    else
+        cg_residual_init_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, b, q, d, r, st, partials);
+    FS_LAUNCH_CHECK();
+    return FS_OK;
+}
+
 __global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_iter);
+__global__ void cg_state_unlimit_kernel(CgState* st);
 
 // host-side CG control shared by all solvers ------------------------------------------------
 struct CgHost {

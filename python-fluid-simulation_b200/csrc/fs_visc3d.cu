@@ -462,10 +462,8 @@ static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
     const long long n = 3 * h->L.NL;
     FS_DISPATCH(h, visc3d_apply_dot_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials));
     FS_LAUNCH_CHECK();
-    FS_DISPATCH(h, cg_update_xr_kernel<T><<<kVecGrid, kVecThreads, 0, s>>>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials));
-    FS_LAUNCH_CHECK();
-    FS_DISPATCH(h, cg_update_d_kernel<T><<<kVecGrid, kVecThreads, 0, s>>>(n, vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st));
-    FS_LAUNCH_CHECK();
+    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr<T>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s)));
+    FS_DISPATCH(h, FS_TRY(cg_launch_update_d<T>(n, vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, s)));
     return FS_OK;
 }
 
@@ -474,8 +472,7 @@ static int visc3d_cg_begin(fs_visc3d* h, double scale, double mu, double tol, in
     cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter);
     FS_LAUNCH_CHECK();
     FS_TRY(visc3d_general(h, scale, mu, FS_VEC_X, FS_VEC_Q, ROW_APPLY, s));   // q = A x   (:575)
-    FS_DISPATCH(h, cg_residual_init_kernel<T><<<kVecGrid, kVecThreads, 0, s>>>(n, vec_ptr<T>(h, FS_VEC_B), vec_ptr<T>(h, FS_VEC_Q), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, h->partials));
-    FS_LAUNCH_CHECK();
+    FS_DISPATCH(h, FS_TRY(cg_launch_residual_init<T>(n, vec_ptr<T>(h, FS_VEC_B), vec_ptr<T>(h, FS_VEC_Q), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, h->partials, s)));
     return FS_OK;
 }
 
@@ -492,6 +489,8 @@ int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void*
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_cg_enqueue before fs_visc3d_pack");
     const double sm = scale * mu;
+    cg_state_unlimit_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->st);
+    FS_LAUNCH_CHECK();
     for (int64_t k = 0; k < n; ++k) FS_TRY(visc3d_iteration(h, sm, (cudaStream_t)stream));
     return FS_OK;
 }

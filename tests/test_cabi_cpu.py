@@ -1,0 +1,62 @@
+"""CPU: the C-ABI shared library builds/loads and exports every symbol include/fluidsolver_b200.h declares.
+No compute calls are made here (there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import REPO
+
+
+def _declared_functions():
+    text = open(os.path.join(REPO, "include", "fluidsolver_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from solver import _native as N
+    assert _declared_functions() == N.exported_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    from solver import _native as N
+    if not os.path.exists(N.LIB_PATH):
+        import build  # python-fluid-simulation_b200/build.py
+        build.build_library()
+    lib = ctypes.CDLL(N.LIB_PATH)
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/fluidsolver_b200.h but not exported"
+    N.load()
+    assert N.load().fs_abi_version() == 1
+
+
+def test_workspace_queries_without_gpu():
+    from solver import _native as N
+    lib = N.load()
+    assert lib.fs_visc3d_workspace_bytes(0, 4, 4, N.FS_F32) == 0
+    assert lib.fs_visc3d_workspace_bytes(4, 4, 4, 7) == 0
+    b32 = lib.fs_visc3d_workspace_bytes(64, 64, 64, N.FS_F32)
+    b64 = lib.fs_visc3d_workspace_bytes(64, 64, 64, N.FS_F64)
+    NL = 65 * 65 * 68
+    assert b32 >= 22 * NL * 4 + 9 * NL and b64 >= 22 * NL * 8 + 9 * NL and b64 > b32
+    assert lib.fs_visc2d_workspace_bytes(32, 32, N.FS_F64) > 14 * 33 * 36 * 8
+    assert lib.fs_press_workspace_bytes(16, 16, 16) > 0 and lib.fs_press_workspace_bytes(16, 16, 0) > 0
+
+
+def test_product_has_no_cpu_fallback():
+    """The solver classes must refuse to run without CUDA rather than fall back to the oracle."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ViscosityCGSolver3D((8, 8, 8), (1.0, 1.0, 1.0))
+    # and nothing under the product package imports the oracle
+    pkg = os.path.join(REPO, "python-fluid-simulation_b200")
+    for root, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, fn)).read()
+                assert "numpy_oracle" not in src and "import oracle" not in src and "from oracle" not in src, fn
