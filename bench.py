@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the north-star path: 3-D viscosity CG iterations/s on the 256^3 high-viscosity buckling scene
+(BASELINE.json config 4; SURVEY.md §8 d), 1..8 B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (C/OpenMP port of the reference's loop)
+
+A "step" is one fixed window of `--iters` (default 200) CG iterations of ViscosityCGSolver3D on the scene,
+started from scratch every step exactly the way config 1 prescribes it for the reference (max_iter=200, tol=0:
+the solve packs the inputs, extrapolates, builds the RHS, runs 200 iterations and raises "Failed to converge!").
+`value`  = CG iterations/s with every input already resident in HBM (device tensors passed to solve()).
+`e2e`    = the same call with HOST (pinned) buffers: H2D of vx,vy,vz,sphi,lvol and D2H of the solution inside the
+           timed region.
+`roofline` = the dominant kernel of the iteration timed alone with CUDA events (fs_visc3d_kernel_enqueue),
+           algorithmic bytes per launch / duration, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`cpu_baseline` = oracle/c_port (fp64 C/OpenMP restatement) timed on this box's host cores on a bounded sample.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "python-fluid-simulation_b200")
+for _p in (PKG, REPO):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "viscosity_cg_iters_per_s_256^3"
+UNIT = "CG iterations/s"
+
+
+def counts(n):
+    """faces F and used fine-grid volume classes V7 of an n^3 grid (SURVEY §8 d)"""
+    F = 3 * n * n * (n + 1)
+    V7 = F + n ** 3 + 3 * (n + 1) * (n + 1) * n
+    return F, V7
+
+
+def hbm_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU port on the host cores
+# ------------------------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import scenes
+    from oracle import c_port
+    n = args.size
+    sc = scenes.buckling(n, device="cpu", mu=args.mu)
+    s = c_port.ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
+    st = s.prepare(sc["dt"], args.mu, sc["rho"], sc["vx"].numpy(), sc["vy"].numpy(), sc["vz"].numpy(), sc["sphi"].numpy(), sc["lvol"].numpy())
+    sample = args.ref_iters
+    delta = st["delta"]
+
+    def step(delta):
+        _, d = c_port.cg(sc["gres"], st["scale"], args.mu, st["x"], st["r"], st["d"], st["q"], st["sphi"], st["vol"], 0.0, sample, delta)
+        return d
+
+    for _ in range(args.warmup):
+        delta = step(delta)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        delta = step(delta)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    cores = c_port.num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n, "cpu"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} CG iterations per step of the same {n}^3 buckling scene (fp64 C/OpenMP restatement, oracle/c_port)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference has no CPU implementation (Numba-CUDA only); this arm times a line-by-line C/OpenMP port of its CG loop",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, n, where):
+    return {"workload": f"buckling-{n}^3 high-viscosity (mu={args.mu:g}), ViscosityCGSolver3D fixed {args.iters}-iteration CG window per step"
+                        if where != "cpu" else f"buckling-{n}^3 high-viscosity (mu={args.mu:g}), ViscosityCGSolver3D CG iterations",
+            "grid": [n, n, n], "mu": args.mu, "dt": 1.0 / 300, "rho": 1000.0, "iters_per_step": args.iters if where != "cpu" else args.ref_iters,
+            "partition": f"x-slabs over {args.gpus} GPU(s)" if args.gpus > 1 else "single GPU",
+            "l2": "working set >> L2 (inputs larger than L2, no explicit flush)"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------------------
+
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import scenes
+    from solver import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    esz = 8 if args.dtype == "f64" else 4
+    n = args.size
+    F, V7 = counts(n)
+    words_iter = 11 * F + V7
+    peak, peak_src = hbm_peak()
+
+    if world > 1:
+        from solver.distributed import bench_distributed
+        return bench_distributed(args, METRIC, UNIT, workload_config(args, n, "gpu"), peak, peak_src)
+
+    lib = N.load()
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    sc = scenes.buckling(n, device="cuda", mu=args.mu)
+    solver = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], dtype=tdtype)
+    solver.max_iter = args.iters
+    dev_in = [sc[k] for k in ("vx", "vy", "vz")]
+
+    def step_device():
+        try:
+            solver.solve(sc["dt"], args.mu, sc["rho"], *dev_in, sc["sphi"], None, None, sc["lvol"], tol=0.0)
+        except ValueError:
+            pass                                  # "Failed to converge!" after exactly max_iter iterations (reference :611-612)
+        assert solver.iterations == args.iters
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    l0 = N.launch_count()
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            step_device()
+        ev1.record()
+        torch.cuda.synchronize()
+    launches = N.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    value = args.iters * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the same call with host (pinned) buffers -------------------------------------------------------
+    host = {k: sc[k].cpu().pin_memory() for k in ("vx", "vy", "vz", "sphi", "lvol")}
+    out_host = [torch.empty(tuple(a.shape), dtype=tdtype).pin_memory() for a in (solver.x_x, solver.x_y, solver.x_z)]
+    h2d = sum(host[k].numel() * host[k].element_size() for k in host)
+    d2h = sum(a.numel() * a.element_size() for a in out_host)
+
+    def step_e2e():
+        try:
+            solver.solve(sc["dt"], args.mu, sc["rho"], host["vx"], host["vy"], host["vz"], host["sphi"], None, None, host["lvol"], tol=0.0)
+        except ValueError:
+            pass
+        for o, x in zip(out_host, (solver.x_x, solver.x_y, solver.x_z)):
+            o.copy_(x, non_blocking=True)         # the step's result: the solution after the window
+        torch.cuda.synchronize()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1)
+    e2e_value = args.iters * e2e_steps / (e2e_ms * 1e-3)
+    del host
+
+    # ---- per-kernel timing for the roofline -----------------------------------------------------------------
+    scale = sc["dt"] / solver.cell_vol / sc["rho"]
+    stream = torch.cuda.current_stream().cuda_stream
+    kern = {}
+    kbytes = {"K1 visc3d_apply_dot": (2 * F + V7) * esz, "K2 cg_update_xr": 6 * F * esz, "K3 cg_update_d": 3 * F * esz}
+    reps = 30
+    for which, name in ((1, "K1 visc3d_apply_dot"), (2, "K2 cg_update_xr"), (3, "K3 cg_update_d")):
+        N.check(lib.fs_visc3d_kernel_enqueue(solver._e.h, which, scale, args.mu, 3, stream), "warm")
+        torch.cuda.synchronize()
+        ev0.record()
+        N.check(lib.fs_visc3d_kernel_enqueue(solver._e.h, which, scale, args.mu, reps, stream), "time")
+        ev1.record()
+        torch.cuda.synchronize()
+        kern[name] = ev0.elapsed_time(ev1) / reps
+    dom = max(kern, key=kern.get)
+    achieved = kbytes[dom] / (kern[dom] * 1e-3) / 1e9
+    iter_gbs = words_iter * esz * value / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "per_kernel_ms": kern, "per_kernel_GBps": {k: kbytes[k] / (kern[k] * 1e-3) / 1e9 for k in kern},
+                "iteration": {"algorithmic_GB_per_iter": words_iter * esz / 1e9, "achieved_GBps": iter_gbs, "frac": iter_gbs / peak,
+                              "formula": "(11F+V7) words/iter, SURVEY §8d"}}
+
+    # ---- CPU baseline (bounded sample) on this box's host cores ----------------------------------------------
+    cpu = cpu_baseline(args, sc, solver, lib, scale)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, n, "gpu"),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline(args, sc, solver, lib, scale):
+    """oracle/c_port on the host cores, a few iterations of the same workload from the same CG state."""
+    import numpy as np
+    import torch
+    from oracle import c_port
+    from solver import _native as N
+    try:
+        solver.max_iter = 0
+        try:
+            solver.solve(sc["dt"], args.mu, sc["rho"], sc["vx"], sc["vy"], sc["vz"], sc["sphi"], None, None, sc["lvol"], tol=0.0)
+        except ValueError:
+            pass
+        solver.max_iter = args.iters
+        x = [a.double().contiguous().cpu().numpy() for a in (solver.x_x, solver.x_y, solver.x_z)]
+        r = [a.double().contiguous().cpu().numpy() for a in (solver.r_x, solver.r_y, solver.r_z)]
+        d = [a.copy() for a in r]
+        q = [np.zeros_like(a) for a in r]
+        vol = (sc["lvol"] / (solver.cell_vol * 0.125)).cpu().numpy()
+        sphi = sc["sphi"].cpu().numpy()
+        delta = float(sum(np.sum(a * a) for a in r))
+        c_port.cg(sc["gres"], scale, args.mu, x, r, d, q, sphi, vol, 0.0, 1, delta)      # warm-up (page-in, threads)
+        k = args.ref_iters
+        t0 = time.perf_counter()
+        it, _ = c_port.cg(sc["gres"], scale, args.mu, x, r, d, q, sphi, vol, 0.0, k, delta)
+        dt = time.perf_counter() - t0
+        return {"value": it / dt, "unit": UNIT, "cores": c_port.num_threads(), "kind": "port",
+                "sample": f"{k} CG iterations of the same {args.size}^3 scene/state, fp64 C/OpenMP restatement (oracle/c_port), {dt:.1f} s"}
+    except Exception as e:                                           # the baseline must never sink the GPU number
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=200, help="CG iterations per step (fixed window)")
+    ap.add_argument("--ref-iters", type=int, default=4, help="CG iterations per step of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--mu", type=float, default=100.0)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="solver storage/arithmetic type (reference: f64)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

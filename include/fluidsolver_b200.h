@@ -110,7 +110,9 @@ int fs_visc3d_cg(fs_visc3d* h, double scale, double mu, double tol, int64_t max_
 /* Bench hook: enqueue exactly `n` CG iterations on the current state without any host sync or
  * convergence stop (the timed window of BASELINE.json's "fixed 200 iterations" configs). */
 int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void* stream);
-/* Same window with the d-update folded into the apply (2 kernels/iteration); see DESIGN.md */
+/* Profiling hook: enqueue `n` back-to-back launches of ONE kernel of the iteration on the current state
+ * (which = 1: K1 apply+d.q, 2: K2 x/r update + r.r, 3: K3 d update) so bench.py can time it with CUDA events. */
+int fs_visc3d_kernel_enqueue(fs_visc3d* h, int which, double scale, double mu, int64_t n, void* stream);
 int fs_visc3d_read_stats(fs_visc3d* h, fs_cg_stats* stats, void* stream);
 /* One call = ViscosityCGSolver3D.solve (:566-613): pack, load, 3-sweep extrapolation, RHS, CG,
  * masked write-back into vx,vy,vz (caller dtype `vel_dtype`). */

@@ -1,0 +1,162 @@
+/*
+ * TEST INFRASTRUCTURE ONLY — fp64 C/OpenMP restatement of the reference's 3-D viscosity CG hot loop, used as
+ * the CPU baseline ("port") of bench.py and as a faster checker than the NumPy oracle at 64^3..128^3.
+ * Never linked into or called by the product library.
+ *
+ * Follows ViscosityCGSolver3D.py:248-456 (matvecmul_{x,y,z}_kernel) and :588-610 (the CG loop) of the reference,
+ * on the reference's own data layout (dense C-order MAC arrays, (2n+1)^3 fine grids).  Pinned against the NumPy
+ * oracle (itself pinned bit-exactly to the reference's kernels) by tests/test_c_port_cpu.py; compiled with
+ * -ffp-contract=off so the apply is bit-identical to it.
+ *
+ * The three 15-term kernels are restated as one axis-generic rule on the fine grid.  With f the fine index of the
+ * face (2c + p_A, p_A = (0,1,1),(1,0,1),(1,1,0)), s = scale*mu, M(.) = [sphi >= 0]:
+ *   diag = vol[f] + s * sum_ax w_ax (vol[f+e_ax] + vol[f-e_ax]),  w_ax = 2 if ax == A else 1   (left-to-right)
+ *   q    = diag*v_A[c]
+ *          - sum_ax  (w_ax s) vol[f+e_ax] M(f+2e_ax) v_A[c+e_ax] - (w_ax s) vol[f-e_ax] M(f-2e_ax) v_A[c-e_ax]
+ *          - sum_{B != A, b = axis of B}
+ *                s vol[f+e_b] ( M(f+e_b+e_A) v_B[c+e_b] - M(f+e_b-e_A) v_B[c+e_b-e_A] )
+ *              + s vol[f-e_b] ( -M(f-e_b+e_A) v_B[c]    + M(f-e_b-e_A) v_B[c-e_A]     )
+ * evaluated term by term in the reference's order.
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    int n[3];            /* cells */
+    ptrdiff_t fs[3];     /* fine-grid strides */
+    int sh[3][3];        /* MAC array shapes per component */
+    ptrdiff_t cs[3][3];  /* MAC array strides per component */
+} geom_t;
+
+static void make_geom(geom_t* g, int nx, int ny, int nz) {
+    g->n[0] = nx; g->n[1] = ny; g->n[2] = nz;
+    g->fs[2] = 1; g->fs[1] = 2 * (ptrdiff_t)nz + 1; g->fs[0] = g->fs[1] * (2 * (ptrdiff_t)ny + 1);
+    for (int c = 0; c < 3; ++c) {
+        for (int k = 0; k < 3; ++k) g->sh[c][k] = g->n[k] + (k == c);
+        g->cs[c][2] = 1; g->cs[c][1] = g->sh[c][2]; g->cs[c][0] = (ptrdiff_t)g->sh[c][1] * g->sh[c][2];
+    }
+}
+
+static inline ptrdiff_t cidx(const geom_t* g, int comp, const int* c) {
+    return c[0] * g->cs[comp][0] + c[1] * g->cs[comp][1] + c[2] * g->cs[comp][2];
+}
+
+/* one row of component A at coarse index c (interior, fluid) */
+static inline double row_apply(const geom_t* g, int A, const int* c, double s, const double* const* v,
+                               const double* sphi, const double* vol) {
+    ptrdiff_t f = 0;
+    for (int k = 0; k < 3; ++k) f += (2 * (ptrdiff_t)c[k] + (k == A ? 0 : 1)) * g->fs[k];
+    double hi[3], lo[3];
+    for (int ax = 0; ax < 3; ++ax) { hi[ax] = vol[f + g->fs[ax]]; lo[ax] = vol[f - g->fs[ax]]; }
+    double sum = 0.0;
+    for (int ax = 0; ax < 3; ++ax) {
+        const double h = (ax == A) ? 2 * hi[ax] : hi[ax], l = (ax == A) ? 2 * lo[ax] : lo[ax];
+        sum = (ax == 0) ? h + l : (sum + h) + l;
+    }
+    const double diag = vol[f] + s * sum;
+    const double* va = v[A];
+    const ptrdiff_t i = cidx(g, A, c);
+    double val = diag * va[i];
+    for (int ax = 0; ax < 3; ++ax) {
+        const double cf = (ax == A) ? 2 * s : s;
+        if (sphi[f + 2 * g->fs[ax]] >= 0) val -= cf * hi[ax] * va[i + g->cs[A][ax]];
+        if (sphi[f - 2 * g->fs[ax]] >= 0) val -= cf * lo[ax] * va[i - g->cs[A][ax]];
+    }
+    for (int B = 0; B < 3; ++B) {
+        if (B == A) continue;
+        const double* vb = v[B];
+        const ptrdiff_t j = cidx(g, B, c);     /* v_B[c] */
+        const ptrdiff_t eb = g->cs[B][B], ea = g->cs[B][A];
+        if (sphi[f + g->fs[B] + g->fs[A]] >= 0) val -= s * hi[B] * vb[j + eb];
+        if (sphi[f + g->fs[B] - g->fs[A]] >= 0) val += s * hi[B] * vb[j + eb - ea];
+        if (sphi[f - g->fs[B] + g->fs[A]] >= 0) val += s * lo[B] * vb[j];
+        if (sphi[f - g->fs[B] - g->fs[A]] >= 0) val -= s * lo[B] * vb[j - ea];
+    }
+    return val;
+}
+
+void port_visc3d_matvecmul(int nx, int ny, int nz, double scale, double mu,
+                           const double* vx, const double* vy, const double* vz,
+                           double* ox, double* oy, double* oz, const double* sphi, const double* vol) {
+    geom_t g;
+    make_geom(&g, nx, ny, nz);
+    const double s = scale * mu;
+    const double* v[3] = {vx, vy, vz};
+    double* o[3] = {ox, oy, oz};
+    for (int A = 0; A < 3; ++A) {
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int x = 1; x <= g.sh[A][0] - 2; ++x)
+            for (int y = 1; y <= g.sh[A][1] - 2; ++y)
+                for (int z = 1; z <= g.sh[A][2] - 2; ++z) {
+                    const int c[3] = {x, y, z};
+                    ptrdiff_t f = 0;
+                    for (int k = 0; k < 3; ++k) f += (2 * (ptrdiff_t)c[k] + (k == A ? 0 : 1)) * g.fs[k];
+                    o[A][cidx(&g, A, c)] = (sphi[f] < 0) ? 0.0 : row_apply(&g, A, c, s, v, sphi, vol);
+                }
+    }
+}
+
+static double dot3(const geom_t* g, double* const* a, double* const* b) {
+    double tot = 0.0;
+    for (int A = 0; A < 3; ++A) {
+        const ptrdiff_t n = (ptrdiff_t)g->sh[A][0] * g->sh[A][1] * g->sh[A][2];
+        double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+        for (ptrdiff_t i = 0; i < n; ++i) s += a[A][i] * b[A][i];
+        tot += s;
+    }
+    return tot;
+}
+
+/* Runs up to max_iter CG iterations (ViscosityCGSolver3D.py:588-610) on caller-provided state x, r, d (q scratch),
+ * delta_io = current r.r.  Returns the number of iterations executed; stops early when delta < tol2. */
+int64_t port_visc3d_cg(int nx, int ny, int nz, double scale, double mu,
+                       double* xx, double* xy, double* xz, double* rx, double* ry, double* rz,
+                       double* dx, double* dy, double* dz, double* qx, double* qy, double* qz,
+                       const double* sphi, const double* vol, double tol2, int64_t max_iter, double* delta_io) {
+    geom_t g;
+    make_geom(&g, nx, ny, nz);
+    double* x[3] = {xx, xy, xz};
+    double* r[3] = {rx, ry, rz};
+    double* d[3] = {dx, dy, dz};
+    double* q[3] = {qx, qy, qz};
+    double delta = *delta_io;
+    int64_t it = 0;
+    while (it < max_iter) {
+        port_visc3d_matvecmul(nx, ny, nz, scale, mu, dx, dy, dz, qx, qy, qz, sphi, vol);
+        const double dq = dot3(&g, d, q);
+        const double alpha = delta / dq;
+        for (int A = 0; A < 3; ++A) {
+            const ptrdiff_t n = (ptrdiff_t)g.sh[A][0] * g.sh[A][1] * g.sh[A][2];
+#pragma omp parallel for schedule(static)
+            for (ptrdiff_t i = 0; i < n; ++i) {
+                x[A][i] += alpha * d[A][i];
+                r[A][i] -= alpha * q[A][i];
+            }
+        }
+        const double old = delta;
+        delta = dot3(&g, r, r);
+        ++it;
+        if (delta < tol2) break;
+        const double beta = delta / old;
+        for (int A = 0; A < 3; ++A) {
+            const ptrdiff_t n = (ptrdiff_t)g.sh[A][0] * g.sh[A][1] * g.sh[A][2];
+#pragma omp parallel for schedule(static)
+            for (ptrdiff_t i = 0; i < n; ++i) d[A][i] = r[A][i] + beta * d[A][i];
+        }
+    }
+    *delta_io = delta;
+    return it;
+}
+
+int port_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

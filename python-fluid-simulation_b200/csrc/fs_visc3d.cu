@@ -458,12 +458,26 @@ int fs_visc3d_apply(fs_visc3d* h, double scale, double mu, int src_vec, int dst_
     return visc3d_general(h, scale, mu, src_vec, dst_vec, ROW_APPLY, (cudaStream_t)stream);
 }
 
-static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
-    const long long n = 3 * h->L.NL;
+static int visc3d_k1(fs_visc3d* h, double sm, cudaStream_t s) {
     FS_DISPATCH(h, visc3d_apply_dot_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials));
     FS_LAUNCH_CHECK();
+    return FS_OK;
+}
+static int visc3d_k2(fs_visc3d* h, cudaStream_t s) {
+    const long long n = 3 * h->L.NL;
     FS_DISPATCH(h, FS_TRY(cg_launch_update_xr<T>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s)));
+    return FS_OK;
+}
+static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
+    const long long n = 3 * h->L.NL;
     FS_DISPATCH(h, FS_TRY(cg_launch_update_d<T>(n, vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, s)));
+    return FS_OK;
+}
+
+static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
+    FS_TRY(visc3d_k1(h, sm, s));
+    FS_TRY(visc3d_k2(h, s));
+    FS_TRY(visc3d_k3(h, s));
     return FS_OK;
 }
 
@@ -492,6 +506,22 @@ int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void*
     cg_state_unlimit_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->st);
     FS_LAUNCH_CHECK();
     for (int64_t k = 0; k < n; ++k) FS_TRY(visc3d_iteration(h, sm, (cudaStream_t)stream));
+    return FS_OK;
+}
+
+int fs_visc3d_kernel_enqueue(fs_visc3d* h, int which, double scale, double mu, int64_t n, void* stream) {
+    if (!h) return fail(FS_ERR_ARG, "null handle");
+    if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_kernel_enqueue before fs_visc3d_pack");
+    if (which < 1 || which > 3) return fail(FS_ERR_ARG, "fs_visc3d_kernel_enqueue: which must be 1, 2 or 3");
+    cudaStream_t s = (cudaStream_t)stream;
+    const double sm = scale * mu;
+    cg_state_unlimit_kernel<<<1, 1, 0, s>>>(h->st);
+    FS_LAUNCH_CHECK();
+    for (int64_t k = 0; k < n; ++k) {
+        if (which == 1) FS_TRY(visc3d_k1(h, sm, s));
+        else if (which == 2) FS_TRY(visc3d_k2(h, s));
+        else FS_TRY(visc3d_k3(h, s));
+    }
     return FS_OK;
 }
 

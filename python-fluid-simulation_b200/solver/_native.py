@@ -47,6 +47,7 @@ _SIGS = {
     "fs_visc3d_apply": (c_int, [c_void_p, c_double, c_double, c_int, c_int, c_void_p]),
     "fs_visc3d_cg": (c_int, [c_void_p, c_double, c_double, c_double, c_int64, POINTER(CgStats), c_void_p]),
     "fs_visc3d_cg_enqueue": (c_int, [c_void_p, c_double, c_double, c_int64, c_void_p]),
+    "fs_visc3d_kernel_enqueue": (c_int, [c_void_p, c_int, c_double, c_double, c_int64, c_void_p]),
     "fs_visc3d_read_stats": (c_int, [c_void_p, POINTER(CgStats), c_void_p]),
     "fs_visc3d_solve": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_int,
                                 c_void_p, c_void_p, c_double, c_int64, POINTER(CgStats), c_void_p]),
