@@ -122,6 +122,24 @@ int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_
                     double tol, int64_t max_iter, fs_cg_stats* stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU (new work; the reference is single-GPU): one process per GPU, the grid cut into x-slabs
+ * (x is the storage-slowest axis, so halo planes are contiguous).  A rank builds an ordinary fs_visc3d on
+ * its slab EXTENDED by one cell towards each existing neighbour and attaches a communicator; every
+ * fs_visc3d_* call then exchanges one plane of u,v,w per neighbour before each stencil apply and
+ * all-reduces the two CG scalars, so all ranks iterate in lock-step and stop on the same iteration.
+ * Bootstrap: rank 0 calls fs_comm_unique_id, the 128 bytes are broadcast by the host program
+ * (torch.distributed), every rank calls fs_comm_create.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fs_comm fs_comm;
+int fs_comm_unique_id(void* out128);
+int fs_comm_create(fs_comm** out, int rank, int nranks, const void* id128);
+void fs_comm_destroy(fs_comm* c);
+int fs_comm_rank(const fs_comm* c);
+int fs_comm_size(const fs_comm* c);
+/* Declare `h` to be a slab with a lower and/or higher neighbour (rank-1 / rank+1 of `comm`). */
+int fs_visc3d_set_slab(fs_visc3d* h, fs_comm* comm, int has_lo, int has_hi);
+
+/* ------------------------------------------------------------------------------------------
  * Viscosity, 2-D  (ViscosityCGSolver2D) — fluid test is sphi > 0, no extrapolation, tol 1e-4
  * lattice X=W+1, Y'=roundup(H+1,4); MAC faces u (W+1,H), v (W,H+1); fine grid (2W+1,2H+1)
  * ---------------------------------------------------------------------------------------- */

@@ -6,7 +6,7 @@ namespace fs {
 thread_local char g_err[512] = "";
 long long g_launches = 0;
 
-__global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_iter) {
+__global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_iter, int dist) {
     st->delta = 0.0;
     st->delta_old = 0.0;
     st->dq = 0.0;
@@ -17,8 +17,26 @@ __global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_ite
     st->iter = 0;
     st->max_iter = max_iter;
     st->done = 0;
-    st->pad = 0;
+    st->dist = dist;
+    st->red = 0.0;
     for (int i = 0; i < 4; ++i) st->counter[i] = 0;
+}
+
+__global__ void cg_finish_kernel(CgState* st, int which) {
+    if (st->done) return;
+    const double s = st->red;
+    if (which == 0) {
+        st->delta = s;
+        st->delta0 = s;
+        st->delta_old = s;
+        if (s < st->tol2) st->done = 1;
+    } else {
+        st->delta_old = st->delta;
+        st->delta = s;
+        st->iter += 1;
+        if (s < st->tol2) st->done = 1;
+        else if (st->iter >= st->max_iter || !(s == s)) st->done = 2;
+    }
 }
 
 // bench hook: let already-initialised state run for an unbounded number of iterations (no convergence stop)

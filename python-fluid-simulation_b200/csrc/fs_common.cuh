@@ -62,7 +62,8 @@ struct CgState {
     long long iter;
     long long max_iter;
     int done;          // 0 running, 1 converged, 2 iteration budget exhausted
-    int pad;
+    int dist;          // 1: multi-GPU — reducing kernels leave their LOCAL sum in `red`; cg_finish_kernel applies it after the allreduce
+    double red;
     unsigned int counter[4];  // last-block tickets (one per reducing kernel type)
 };
 
@@ -159,7 +160,7 @@ template <typename T, int VEC> struct Chunk {
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, T* __restrict__ x, T* __restrict__ r,
                                                                    const T* __restrict__ d, const T* __restrict__ q,
-                                                                   CgState* st, double* partials) {
+                                                                   CgState* st, double* partials, int freeze) {
     if (*(volatile int*)&st->done) return;
     const double alpha_d = st->delta / st->dq;
     const T alpha = (T)alpha_d;
@@ -183,7 +184,9 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, 
         acc += (double)rr * (double)rr;
     }
     grid_sum_finish(acc, partials, &st->counter[1], [=](double s) {
+        if (freeze) return;                      // profiling hook: keep alpha/delta fixed across repeated launches
         st->alpha = alpha_d;
+        if (st->dist) { st->red = s; return; }
         st->delta_old = st->delta;
         st->delta = s;
         st->iter += 1;
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_residual_init_kernel(long long
         acc += (double)dd * (double)dd;
     }
     grid_sum_finish(acc, partials, &st->counter[2], [=](double s) {
+        if (st->dist) { st->red = s; return; }
         st->delta = s;
         st->delta0 = s;
         st->delta_old = s;
@@ -247,12 +251,12 @@ inline int vec_grid(long long n, int vec) {
 }
 
 template <typename T>
-int cg_launch_update_xr(long long n, T* x, T* r, const T* d, const T* q, CgState* st, double* partials, cudaStream_t s) {
+int cg_launch_update_xr(long long n, T* x, T* r, const T* d, const T* q, CgState* st, double* partials, cudaStream_t s, int freeze = 0) {
     constexpr int N = Vec16<T>::N;
     if (aligned16(x) && aligned16(r) && aligned16(d) && aligned16(q))
-        cg_update_xr_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials);
+        cg_update_xr_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze);
     else
-        cg_update_xr_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials);
+        cg_update_xr_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze);
     FS_LAUNCH_CHECK();
     return FS_OK;
 }
@@ -279,8 +283,11 @@ int cg_launch_residual_init(long long n, const T* b, const T* q, T* d, T* r, CgS
     return FS_OK;
 }
 
-__global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_iter);
+__global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_iter, int dist = 0);
 __global__ void cg_state_unlimit_kernel(CgState* st);
+// multi-GPU: bookkeeping that the reducing kernels skip, run after `red` has been allreduced.
+// which = 0: start of a solve (delta0);  which = 1: after K2 (delta', iteration count, convergence flags)
+__global__ void cg_finish_kernel(CgState* st, int which);
 
 // host-side CG control shared by all solvers ------------------------------------------------
 struct CgHost {

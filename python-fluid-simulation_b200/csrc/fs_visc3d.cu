@@ -15,6 +15,7 @@
 //   vec[v][c]   X,R,D,Q,B  solver vectors, 3 components each, NL elements per component
 #include <type_traits>
 
+#include "fs_comm.cuh"
 #include "fs_common.cuh"
 #include "fs_visc_rows.cuh"
 
@@ -24,6 +25,7 @@ struct Lat3 {
     int nx, ny, nz;
     int X, Y, Zp;
     long long sx, sy, NL;
+    int u_xhi;   // last computed x-plane of u rows: nx-1, or nx-2 when a higher slab owns plane nx-1 (multi-GPU)
 };
 
 template <typename T> struct Visc3Dev {
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
         T v = nan;
         if (in) {
             fluid = sphi[f0 + fy + fz] >= 0.0;
-            const bool interior = x >= 1 && x <= L.nx - 1 && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
+            const bool interior = x >= 1 && x <= L.u_xhi && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
             if (fluid && interior) v = vol(fy + fz);
         }
         coef[0 * L.NL + i] = v;
@@ -207,8 +209,9 @@ __global__ void __launch_bounds__(kThreads) visc3d_general_kernel(Visc3Dev<T> P,
         constexpr int A = decltype(Atag)::value;
         int s0, s1, s2_;
         comp_shape(L, A, s0, s1, s2_);
-        const bool interior = x >= 1 && x <= s0 - 2 && y >= 1 && y <= s1 - 2 && z >= 1 && z <= s2_ - 2;
-        if (!interior) return;                    // boundary layer: never written (:251)
+        const int xhi = (A == 0) ? L.u_xhi : s0 - 2;
+        const bool interior = x >= 1 && x <= xhi && y >= 1 && y <= s1 - 2 && z >= 1 && z <= s2_ - 2;
+        if (!interior) return;                    // boundary layer (and rows owned by another slab): never written (:251)
         T out = T(0);
         if (mask[A][i]) {                         // solid rows -> 0 (:255-258)
             const T center = P.coef[A][i];
@@ -224,34 +227,55 @@ __global__ void __launch_bounds__(kThreads) visc3d_general_kernel(Visc3Dev<T> P,
 
 // ---------------------------------------------------------------------------------------------
 // K1: CG-loop apply fused with d.q.  Inside the loop d is exactly zero on every row that is not
-// computed (solid / boundary / padding), so neighbour masks are not needed (SURVEY A-1) and the row
-// flag rides in the NaN tag of the face volume.  One thread per lattice point, three rows each.
+// computed (solid / boundary / padding / other slab), so neighbour masks are not needed (SURVEY A-1)
+// and the row flag rides in the NaN tag of the face volume.
+//
+// Persistent grid (kK1BlocksPerSM CTAs per SM, grid-stride over the lattice, z contiguous across the
+// warp).  Per lattice point: the three NaN tags are loaded first; a warp whose 32 points carry no
+// computed row skips the body (the reference's `if sphi < 0: return`, made warp-uniform).  Otherwise
+// the body is branch-free — all 27 neighbour values and 16 coefficients are requested before the first
+// use, one memory-latency period per point instead of one per row — and rows that are not computed
+// select 0.  Loads of discarded lanes may fall outside the lattice; the workspace carries guard bands
+// of one plane + one row + one element around the coefficient and vector regions for exactly that.
+// One block reduction at the very end (fixed-order, deterministic).
 // ---------------------------------------------------------------------------------------------
+constexpr int kK1Threads = 256;
+constexpr int kK1BlocksPerSM = 3;
+
 template <typename T>
-__global__ void __launch_bounds__(kThreads) visc3d_apply_dot_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
-                                                                    CgState* st_, double* partials) {
+__global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
+                                                                                       CgState* st_, double* partials) {
     if (*(volatile int*)&st_->done) return;
     const Lat3& L = P.L;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long NL = L.NL;
     const long long st[3] = {L.sx, L.sy, 1};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long NLw = (NL + 31) & ~31LL;       // whole warps take part in every trip (ballot below)
+    const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
     double acc = 0.0;
-    if (i < NL) {
-        auto nb = [&](int comp, long long j) -> T { return __ldg(d + comp * NL + j); };
-        auto row = [&](auto Atag) {
-            constexpr int A = decltype(Atag)::value;
-            const T center = __ldg(P.coef[A] + i);
-            T out = T(0);
-            if (center == center) {
-                const T own = __ldg(d + A * NL + i);
-                out = visc_row<T, 3, A, false, ROW_APPLY>(P.coef, i, st, center, own, s, s2, nb);
-                acc += (double)own * (double)out;
-            }
-            q[A * NL + i] = out;
-        };
-        row(std::integral_constant<int, 0>{});
-        row(std::integral_constant<int, 1>{});
-        row(std::integral_constant<int, 2>{});
+    auto nb = [&](int comp, long long j) -> T { return __ldg(d + comp * NL + j); };
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < NLw; i += stride) {
+        const bool in = i < NL;
+        const T cu = in ? __ldg(P.coef[0] + i) : nan;
+        const T cv = in ? __ldg(P.coef[1] + i) : nan;
+        const T cw = in ? __ldg(P.coef[2] + i) : nan;
+        const bool au = cu == cu, av = cv == cv, aw = cw == cw;
+        T ou = T(0), ov = T(0), ow = T(0);
+        if (__any_sync(0xffffffffu, au || av || aw)) {
+            const long long j = in ? i : (NL - 1);
+            const T du = nb(0, j), dv = nb(1, j), dw = nb(2, j);
+            const T ru = visc_row<T, 3, 0, false, ROW_APPLY>(P.coef, j, st, cu, du, s, s2, nb);
+            const T rv = visc_row<T, 3, 1, false, ROW_APPLY>(P.coef, j, st, cv, dv, s, s2, nb);
+            const T rw = visc_row<T, 3, 2, false, ROW_APPLY>(P.coef, j, st, cw, dw, s, s2, nb);
+            if (au) { ou = ru; acc += (double)du * (double)ru; }
+            if (av) { ov = rv; acc += (double)dv * (double)rv; }
+            if (aw) { ow = rw; acc += (double)dw * (double)rw; }
+        }
+        if (in) {
+            q[i] = ou;
+            q[NL + i] = ov;
+            q[2 * NL + i] = ow;
+        }
     }
     grid_sum_finish(acc, partials, &st_->counter[0], [=](double sum) { st_->dq = sum; });
 }
@@ -278,6 +302,8 @@ struct fs_visc3d {
     CgHost cg;
     int grid_pts;    // blocks for one-thread-per-lattice-point kernels
     bool packed;
+    fs_comm* comm;   // multi-GPU: this handle is one x-slab (extended by one cell towards each neighbour)
+    int has_lo, has_hi;
 };
 
 static Lat3 make_lat3(int nx, int ny, int nz) {
@@ -285,6 +311,7 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     L.nx = nx; L.ny = ny; L.nz = nz;
     L.X = nx + 1; L.Y = ny + 1; L.Zp = (nz + 1 + 3) / 4 * 4;
     L.sy = L.Zp; L.sx = (long long)L.Y * L.Zp; L.NL = L.sx * L.X;
+    L.u_xhi = nx - 1;
     return L;
 }
 
@@ -294,8 +321,13 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
     size_t p = 0;
     o.grid_pts = (int)((L.NL + kThreads - 1) / kThreads);
-    o.coef = p; p = align_up(p + 7 * L.NL * esz, 256);
-    o.vecs = p; p = align_up(p + 15 * L.NL * esz, 256);
+    // guard bands (one plane + one row + one element) so that the branch-free K1 may issue neighbour loads for
+    // lanes whose rows are discarded, even at the first / last lattice planes
+    const size_t guard = align_up((size_t)(L.sx + L.sy + 1) * esz, 256);
+    p += guard;
+    o.coef = p; p = align_up(p + 7 * L.NL * esz, 256) + guard;
+    p += guard;
+    o.vecs = p; p = align_up(p + 15 * L.NL * esz, 256) + guard;
     o.mask = p; p = align_up(p + 3 * L.NL, 256);
     o.valid = p; p = align_up(p + 6 * L.NL, 256);
     size_t np = (size_t)(o.grid_pts > kVecGrid ? o.grid_pts : kVecGrid);
@@ -321,7 +353,40 @@ template <typename T> static T* vec_ptr(const fs_visc3d* h, int v) { return rein
         else { using T = double; __VA_ARGS__; }                  \
     } while (0)
 
+// Halo exchange of the three component planes of one lattice array family (solver vector or validity bytes).
+// Local planes: 0 = halo from the low neighbour, 1 = first owned; X-3 = last owned, X-2 = halo from the high neighbour
+// (plane X-1 only exists because the extended grid is a standalone lattice; nothing owned reads it).
+static int visc3d_halo(fs_visc3d* h, char* base /*[3][NL] elements of `esz` bytes*/, size_t esz, int type, cudaStream_t s) {
+    if (!h->comm || (!h->has_lo && !h->has_hi)) return FS_OK;
+    const Lat3& L = h->L;
+    const void* send_lo[3]; void* recv_lo[3]; const void* send_hi[3]; void* recv_hi[3];
+    for (int c = 0; c < 3; ++c) {
+        char* comp = base + (size_t)c * L.NL * esz;
+        recv_lo[c] = comp;
+        send_lo[c] = comp + (size_t)1 * L.sx * esz;
+        send_hi[c] = comp + (size_t)(L.X - 3) * L.sx * esz;
+        recv_hi[c] = comp + (size_t)(L.X - 2) * L.sx * esz;
+    }
+    return comm_halo_exchange(h->comm, h->has_lo, h->has_hi, 3, send_lo, recv_lo, send_hi, recv_hi, (size_t)L.sx, type, s);
+}
+
+static int visc3d_halo_vec(fs_visc3d* h, int vec, cudaStream_t s) {
+    return visc3d_halo(h, h->vecs + (size_t)vec * 3 * h->L.NL * h->esz, h->esz, h->dtype == FS_F32 ? COMM_F32 : COMM_F64, s);
+}
+
 extern "C" {
+
+int fs_visc3d_set_slab(fs_visc3d* h, fs_comm* comm, int has_lo, int has_hi) {
+    if (!h) return fail(FS_ERR_ARG, "null handle");
+    if ((has_lo || has_hi) && !comm) return fail(FS_ERR_ARG, "fs_visc3d_set_slab: neighbours need a communicator");
+    if (h->L.nx < 2 + (has_lo ? 1 : 0) + (has_hi ? 1 : 0)) return fail(FS_ERR_ARG, "fs_visc3d_set_slab: slab too thin");
+    h->comm = comm;
+    h->has_lo = has_lo ? 1 : 0;
+    h->has_hi = has_hi ? 1 : 0;
+    h->L.u_xhi = h->L.nx - 1 - h->has_hi;
+    h->packed = false;
+    return FS_OK;
+}
 
 size_t fs_visc3d_workspace_bytes(int nx, int ny, int nz, int dtype) {
     if (nx < 1 || ny < 1 || nz < 1 || (dtype != FS_F32 && dtype != FS_F64)) return 0;
@@ -346,6 +411,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->partials = (double*)(h->ws + lay.partials); h->st = (CgState*)(h->ws + lay.st);
     h->grid_pts = lay.grid_pts;
     h->packed = false;
+    h->comm = nullptr; h->has_lo = 0; h->has_hi = 0;
     int s = h->cg.init();
     if (s < 0) { delete h; return s; }
     h->cg.st_dev = h->st; h->cg.partials_dev = h->partials;
@@ -428,6 +494,10 @@ int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
             vec_ptr<T>(h, cur == 0 ? scratch : vec), h->valid + (size_t)(cur ^ 1) * NL3));
         FS_LAUNCH_CHECK();
         cur ^= 1;
+        if (h->comm) {   // the sweep is Jacobi over the GLOBAL grid: refresh the halo planes of the new values and flags
+            FS_TRY(visc3d_halo_vec(h, cur == 0 ? vec : scratch, s));
+            FS_TRY(visc3d_halo(h, (char*)(h->valid + (size_t)cur * NL3), 1, COMM_U8, s));
+        }
     }
     if (cur == 1) {  // result sits in scratch
         FS_CUDA(cudaMemcpyAsync(h->vecs + (size_t)vec * NL3 * h->esz, h->vecs + (size_t)scratch * NL3 * h->esz, NL3 * h->esz, cudaMemcpyDeviceToDevice, s));
@@ -459,13 +529,15 @@ int fs_visc3d_apply(fs_visc3d* h, double scale, double mu, int src_vec, int dst_
 }
 
 static int visc3d_k1(fs_visc3d* h, double sm, cudaStream_t s) {
-    FS_DISPATCH(h, visc3d_apply_dot_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials));
+    long long want = (h->L.NL + kK1Threads - 1) / kK1Threads;
+    const int grid = (int)(want < (long long)kSMs * kK1BlocksPerSM ? want : (long long)kSMs * kK1BlocksPerSM);
+    FS_DISPATCH(h, visc3d_apply_dot_kernel<T><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials));
     FS_LAUNCH_CHECK();
     return FS_OK;
 }
-static int visc3d_k2(fs_visc3d* h, cudaStream_t s) {
+static int visc3d_k2(fs_visc3d* h, cudaStream_t s, int freeze = 0) {
     const long long n = 3 * h->L.NL;
-    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr<T>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s)));
+    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr<T>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s, freeze)));
     return FS_OK;
 }
 static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
@@ -475,18 +547,30 @@ static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
 }
 
 static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
+    if (h->comm) FS_TRY(visc3d_halo_vec(h, FS_VEC_D, s));                       // neighbours' d planes for the stencil
     FS_TRY(visc3d_k1(h, sm, s));
+    if (h->comm) FS_TRY(comm_allreduce_sum_f64(h->comm, &h->st->dq, 1, s));     // d.q over all slabs
     FS_TRY(visc3d_k2(h, s));
+    if (h->comm) {
+        FS_TRY(comm_allreduce_sum_f64(h->comm, &h->st->red, 1, s));             // r.r over all slabs
+        cg_finish_kernel<<<1, 1, 0, s>>>(h->st, 1);
+        FS_LAUNCH_CHECK();
+    }
     FS_TRY(visc3d_k3(h, s));
     return FS_OK;
 }
 
 static int visc3d_cg_begin(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, cudaStream_t s) {
     const long long n = 3 * h->L.NL;
-    cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter);
+    cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, h->comm ? 1 : 0);
     FS_LAUNCH_CHECK();
     FS_TRY(visc3d_general(h, scale, mu, FS_VEC_X, FS_VEC_Q, ROW_APPLY, s));   // q = A x   (:575)
     FS_DISPATCH(h, FS_TRY(cg_launch_residual_init<T>(n, vec_ptr<T>(h, FS_VEC_B), vec_ptr<T>(h, FS_VEC_Q), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, h->partials, s)));
+    if (h->comm) {
+        FS_TRY(comm_allreduce_sum_f64(h->comm, &h->st->red, 1, s));
+        cg_finish_kernel<<<1, 1, 0, s>>>(h->st, 0);
+        FS_LAUNCH_CHECK();
+    }
     return FS_OK;
 }
 
@@ -519,7 +603,7 @@ int fs_visc3d_kernel_enqueue(fs_visc3d* h, int which, double scale, double mu, i
     FS_LAUNCH_CHECK();
     for (int64_t k = 0; k < n; ++k) {
         if (which == 1) FS_TRY(visc3d_k1(h, sm, s));
-        else if (which == 2) FS_TRY(visc3d_k2(h, s));
+        else if (which == 2) FS_TRY(visc3d_k2(h, s, 1));
         else FS_TRY(visc3d_k3(h, s));
     }
     return FS_OK;

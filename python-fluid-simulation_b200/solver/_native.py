@@ -51,6 +51,13 @@ _SIGS = {
     "fs_visc3d_read_stats": (c_int, [c_void_p, POINTER(CgStats), c_void_p]),
     "fs_visc3d_solve": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_int,
                                 c_void_p, c_void_p, c_double, c_int64, POINTER(CgStats), c_void_p]),
+    # multi-GPU
+    "fs_comm_unique_id": (c_int, [c_void_p]),
+    "fs_comm_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p]),
+    "fs_comm_destroy": (None, [c_void_p]),
+    "fs_comm_rank": (c_int, [c_void_p]),
+    "fs_comm_size": (c_int, [c_void_p]),
+    "fs_visc3d_set_slab": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     # viscosity 2-D
     "fs_visc2d_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "fs_visc2d_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_size_t]),

@@ -1,0 +1,250 @@
+"""Slab-partitioned multi-GPU viscosity CG (new work — the reference is single-GPU; SURVEY.md §8 e).
+
+One process per GPU (``torch.distributed``, NCCL).  The global ``nx x ny x nz`` grid is cut into contiguous
+x-slabs of cells (x is the storage-slowest axis of the reference's C-order arrays, so a halo is one contiguous
+plane).  Each rank holds its slab EXTENDED by one cell towards every existing neighbour and runs the ordinary
+single-GPU solver object on that extended grid with a communicator attached
+(``fs_visc3d_set_slab``): rows of the overlap cells are owned by the neighbour and are never computed locally,
+their ``d`` planes arrive by halo exchange before each operator apply, and the two CG scalars are all-reduced,
+so every rank executes the same iteration sequence and stops on the same iteration.
+
+The per-rank arrays passed to ``solve()`` are the extended slabs, cut from global arrays with
+``SlabPartition.slab(arr, kind)`` or generated directly per rank (``scenes.viscous_column(..., x0=, gx_total=)``).
+"""
+import ctypes
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _arrays as A
+from . import _native as N
+from .ViscosityCGSolver3D import _DT, _TORCH, _Engine, _fine_shape, _mac_args
+
+
+class SlabPartition:
+    """Balanced x-slabs.  ``[c0, c1)`` = owned cells, ``[e0, e1)`` = extended cells held locally."""
+
+    def __init__(self, gres, world, rank):
+        self.gres = tuple(int(n) for n in gres)
+        self.world, self.rank = int(world), int(rank)
+        nx = self.gres[0]
+        if nx < 2 * self.world:
+            raise ValueError(f"grid too thin for {world} slabs: nx={nx}")
+        base, rem = divmod(nx, self.world)
+        starts = [r * base + min(r, rem) for r in range(self.world + 1)]
+        self.c0, self.c1 = starts[self.rank], starts[self.rank + 1]
+        self.has_lo = self.rank > 0
+        self.has_hi = self.rank < self.world - 1
+        self.e0 = self.c0 - (1 if self.has_lo else 0)
+        self.e1 = self.c1 + (1 if self.has_hi else 0)
+        self.local_gres = (self.e1 - self.e0,) + self.gres[1:]
+
+    def slab(self, arr, kind):
+        """Cut this rank's extended slab out of a GLOBAL array.  kind: 'u' (x-faces, nx+1 planes), 'v'/'w'/'cell'
+        (nx planes) or 'fine' ((2nx+1) planes, also for arrays with trailing component axes)."""
+        if kind == "u":
+            return arr[self.e0: self.e1 + 1]
+        if kind in ("v", "w", "cell"):
+            return arr[self.e0: self.e1]
+        if kind == "fine":
+            return arr[2 * self.e0: 2 * self.e1 + 1]
+        raise ValueError(kind)
+
+    def owned_planes(self, kind):
+        """(lo, hi) local plane range of the entries this rank owns inside its extended slab."""
+        off = self.c0 - self.e0
+        n = self.c1 - self.c0
+        if kind == "u":
+            return off, off + n + (0 if self.has_hi else 1)
+        return off, off + n
+
+
+_comm_cache = {}
+
+
+def get_comm(group=None):
+    """Create (once per process group) the native NCCL communicator; the unique id travels over torch.distributed."""
+    key = id(group)
+    if key in _comm_cache:
+        return _comm_cache[key]
+    lib = N.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        N.check(lib.fs_comm_unique_id(buf), "fs_comm_unique_id")
+    box = [bytes(buf.raw)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    idbuf = ctypes.create_string_buffer(box[0], 128)
+    h = ctypes.c_void_p()
+    N.check(lib.fs_comm_create(ctypes.byref(h), rank, world, idbuf), "fs_comm_create")
+    _comm_cache[key] = h
+    return h
+
+
+class SlabViscosityCGSolver3D:
+    """Multi-GPU counterpart of ViscosityCGSolver3D: same ``solve()`` argument list, per-rank extended slabs."""
+
+    def __init__(self, gres, bound_size, dtype=torch.float64, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("SlabViscosityCGSolver3D needs an initialised torch.distributed process group")
+        self.gres = gres
+        self._g = A.to_host_ints(gres)
+        self.part = SlabPartition(self._g, dist.get_world_size(group), dist.get_rank(group))
+        self.cell_size = A.to_host_f64(bound_size, 3) / np.asarray(self._g, dtype=np.float64)
+        self.cell_vol = float(np.prod(self.cell_size))
+        self._code = _DT[dtype]
+        self._e = _Engine(self.part.local_gres, self._code)
+        self._comm = get_comm(group)
+        N.check(self._e.lib.fs_visc3d_set_slab(self._e.h, self._comm, int(self.part.has_lo), int(self.part.has_hi)), "fs_visc3d_set_slab")
+        for vec, nm in ((N.VEC_D, "d"), (N.VEC_R, "r"), (N.VEC_Q, "q"), (N.VEC_X, "x"), (N.VEC_B, "b")):
+            for c, ax in enumerate("xyz"):
+                setattr(self, f"{nm}_{ax}", self._e.view(vec, c))
+        self.alpha = self.beta = self.delta = 0.0
+        self.iterations = 0
+        self.max_iter = int(np.prod(np.asarray(self._g, dtype=np.int64)))
+
+    def solve(self, dt, mu, rho, vx, vy, vz, sphi, sv, lphi, lvol, tol=1e-3):
+        g, e = self.part.local_gres, self._e
+        v = _mac_args(g, (vx, vy, vz), ("vx", "vy", "vz"))
+        s = A.as_arg(sphi, "sphi", shape=_fine_shape(g), want=torch.float64)
+        vl = A.as_arg(lvol, "lvol", shape=_fine_shape(g), want=torch.float64)
+        st = N.CgStats()
+        status = N.check(
+            e.lib.fs_visc3d_solve(e.h, float(dt), float(mu), float(rho), self.cell_vol, v[0].ptr, v[1].ptr, v[2].ptr, v[0].code,
+                                  s.ptr, vl.ptr, float(tol), int(self.max_iter), ctypes.byref(st), A.stream_ptr()),
+            "fs_visc3d_solve")
+        self.delta, self.alpha, self.beta, self.iterations = st.delta, st.alpha, st.beta, int(st.iterations)
+        if status == N.FS_NOT_CONVERGED:
+            raise ValueError("Failed to converge!")
+        for a in v:
+            a.sync_back()
+
+
+def scatter_scene(sc, part):
+    """Per-rank extended slabs of a GLOBAL scene dict (scenes.buckling etc.)."""
+    out = dict(sc)
+    for k, kind in (("vx", "u"), ("vy", "v"), ("vz", "w"), ("sphi", "fine"), ("lvol", "fine"), ("lphi", "cell"), ("sv", "fine")):
+        if k in sc and sc[k] is not None:
+            out[k] = part.slab(sc[k], kind).contiguous()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# bench.py --gpus N>1
+# ------------------------------------------------------------------------------------------------------------
+
+def bench_distributed(args, metric, unit, config, peak, peak_src):
+    import scenes
+    from bench import ClockSampler, counts
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    esz = 8 if args.dtype == "f64" else 4
+    n = args.size
+    g = (n, n, n)
+    part = SlabPartition(g, world, rank)
+    full = scenes.buckling(n, device="cuda", mu=args.mu)
+    sc = scatter_scene(full, part)
+    bound = full["bound_size"]
+    del full
+    torch.cuda.empty_cache()
+    solver = SlabViscosityCGSolver3D(g, bound, dtype=tdtype)
+    solver.max_iter = args.iters
+    dev_in = [sc[k] for k in ("vx", "vy", "vz")]
+
+    def step_device():
+        try:
+            solver.solve(sc["dt"], args.mu, sc["rho"], *dev_in, sc["sphi"], None, None, sc["lvol"], tol=0.0)
+        except ValueError:
+            pass
+        assert solver.iterations == args.iters, solver.iterations
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # device time, max over ranks
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    l0 = N.launch_count()
+    with ClockSampler(local) as clocks:
+        ms = timed(step_device, args.steps)
+    launches = N.launch_count() - l0
+    value = args.iters * args.steps / (ms * 1e-3)
+
+    host = {k: sc[k].cpu().pin_memory() for k in ("vx", "vy", "vz", "sphi", "lvol")}
+    out_host = [torch.empty(tuple(a.shape), dtype=tdtype).pin_memory() for a in (solver.x_x, solver.x_y, solver.x_z)]
+    h2d = sum(host[k].numel() * host[k].element_size() for k in host)
+    d2h = sum(a.numel() * a.element_size() for a in out_host)
+
+    def step_e2e():
+        try:
+            solver.solve(sc["dt"], args.mu, sc["rho"], host["vx"], host["vy"], host["vz"], host["sphi"], None, None, host["lvol"], tol=0.0)
+        except ValueError:
+            pass
+        for o, x in zip(out_host, (solver.x_x, solver.x_y, solver.x_z)):
+            o.copy_(x, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_e2e()
+    e2e_ms = timed(step_e2e, e2e_steps)
+    e2e_value = args.iters * e2e_steps / (e2e_ms * 1e-3)
+    tot = torch.tensor([float(h2d), float(d2h), float(launches)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+
+    # per-kernel timing on this rank's slab (no communication inside these launches)
+    F, V7 = counts(n)
+    lib = solver._e.lib
+    scale = sc["dt"] / solver.cell_vol / sc["rho"]
+    stream = torch.cuda.current_stream().cuda_stream
+    frac_local = (part.e1 - part.e0 + 1) / (n + 1)
+    kbytes = {"K1 visc3d_apply_dot": (2 * F + V7) * esz * frac_local, "K2 cg_update_xr": 6 * F * esz * frac_local,
+              "K3 cg_update_d": 3 * F * esz * frac_local}
+    kern = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for which, name in ((1, "K1 visc3d_apply_dot"), (2, "K2 cg_update_xr"), (3, "K3 cg_update_d")):
+        N.check(lib.fs_visc3d_kernel_enqueue(solver._e.h, which, scale, args.mu, 3, stream), "warm")
+        torch.cuda.synchronize()
+        ev0.record()
+        N.check(lib.fs_visc3d_kernel_enqueue(solver._e.h, which, scale, args.mu, 30, stream), "time")
+        ev1.record()
+        torch.cuda.synchronize()
+        kern[name] = ev0.elapsed_time(ev1) / 30
+    dist.barrier()
+    if rank == 0:
+        dom = max(kern, key=kern.get)
+        achieved = kbytes[dom] / (kern[dom] * 1e-3) / 1e9
+        words_iter = 11 * F + V7
+        iter_gbs = words_iter * esz * value / 1e9
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(tot[2].item()),
+            "roofline": {"bound": "hbm", "kernel": dom + " (rank 0 slab)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "per_kernel_ms": kern,
+                         "iteration": {"algorithmic_GB_per_iter": words_iter * esz / 1e9, "achieved_GBps_all_gpus": iter_gbs,
+                                       "frac_of_aggregate_peak": iter_gbs / (peak * world)}},
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
