@@ -138,6 +138,21 @@ int fs_comm_rank(const fs_comm* c);
 int fs_comm_size(const fs_comm* c);
 /* Declare `h` to be a slab with a lower and/or higher neighbour (rank-1 / rank+1 of `comm`). */
 int fs_visc3d_set_slab(fs_visc3d* h, fs_comm* comm, int has_lo, int has_hi);
+/* Peer-memory transport (all GPUs on one NVSwitch box): device buffers that other ranks map with CUDA IPC.
+ * The slab's workspace and a 1 KiB mailbox are allocated with fs_shared_alloc, their 64-byte handles travel
+ * over the host program's process group, and every rank maps its neighbours' workspaces and all mailboxes. */
+void* fs_shared_alloc(size_t bytes);
+void fs_shared_free(void* p);
+int fs_shared_get_handle(void* p, void* out64);
+void* fs_shared_open(const void* handle64);
+void fs_shared_close(void* mapped);
+/* Switch the slab to kernel-fused collectives: K1 stores its boundary q planes straight into the neighbours'
+ * halo planes and the d.q / r.r all-reduces run inside the K1 / K2 tails through the mailboxes (no NCCL call per
+ * iteration).  lo_ws/hi_ws: IPC mappings of the neighbours' workspaces (NULL where there is none), lo_nx/hi_nx their
+ * extended slab thickness in cells; mailboxes[r]: mapping of rank r's mailbox (own entry = local pointer). */
+int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int hi_nx, void* const* mailboxes);
+/* 1 if a peer failed to answer inside a fused all-reduce (the solve then ends as not converged) */
+int fs_visc3d_peer_error(fs_visc3d* h);
 
 /* ------------------------------------------------------------------------------------------
  * Viscosity, 2-D  (ViscosityCGSolver2D) — fluid test is sphi > 0, no extrapolation, tol 1e-4

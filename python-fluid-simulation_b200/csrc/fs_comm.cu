@@ -118,6 +118,41 @@ void fs_comm_destroy(fs_comm* c) {
     delete c;
 }
 
+// ---- CUDA-IPC shared device buffers (peer-mapped over NVLink) ----------------------------------------
+void* fs_shared_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { fs::fail(FS_ERR_CUDA, "fs_shared_alloc: cudaMalloc failed"); return nullptr; }
+    if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); fs::fail(FS_ERR_CUDA, "fs_shared_alloc: cudaMemset failed"); return nullptr; }
+    return p;
+}
+
+void fs_shared_free(void* p) {
+    if (p) cudaFree(p);
+}
+
+int fs_shared_get_handle(void* p, void* out64) {
+    if (!p || !out64) return fs::fail(FS_ERR_ARG, "fs_shared_get_handle: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    FS_CUDA(cudaIpcGetMemHandle(&hd, p));
+    memcpy(out64, &hd, 64);
+    return FS_OK;
+}
+
+void* fs_shared_open(const void* handle64) {
+    if (!handle64) { fs::fail(FS_ERR_ARG, "fs_shared_open: null argument"); return nullptr; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { fs::fail(FS_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+void fs_shared_close(void* mapped) {
+    if (mapped) cudaIpcCloseMemHandle(mapped);
+}
+
 int fs_comm_rank(const fs_comm* c) { return c ? c->rank : -1; }
 int fs_comm_size(const fs_comm* c) { return c ? c->nranks : -1; }
 

@@ -68,6 +68,79 @@ struct CgState {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU peer block (device memory).  Pointers are CUDA-IPC mappings of the other ranks' buffers
+// (all GPUs of one NVSwitch box), so kernels exchange data with plain st.global / ld.global:
+//   * q_lo / q_hi : the neighbours' halo planes of q — K1 stores its boundary rows there directly;
+//   * mbox[r]     : rank r's scalar mailbox — the all-reduce of d.q and r.r is done by the last
+//                   block of K1 / K2 itself (LL-style 8-byte words carrying 4 data bytes + a 4-byte
+//                   sequence flag, so no fence/flag round trip is needed on the reader side).
+// The reduction order is rank 0..N-1 on every rank, so all ranks obtain bit-identical sums and take
+// identical convergence decisions.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 8;
+constexpr int kMboxWords = 2 /*kinds*/ * 2 /*parity*/ * kMaxRanks * 2 /*words*/;
+
+struct PeerInfo {
+    int rank, nranks;
+    int has_lo, has_hi;
+    char* q_lo[3];                         // low neighbour's plane X'-2 of q, per component (peer-mapped)
+    char* q_hi[3];                         // high neighbour's plane 0 of q
+    unsigned long long* mbox[kMaxRanks];   // every rank's mailbox (own entry is the local pointer)
+    unsigned int seq[2];                   // persistent sequence numbers of the two reductions (never reset)
+    int error;                             // set to 1 if a peer did not answer within the spin budget
+};
+
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All 32 lanes of ONE warp call this with the same `local`; returns the global sum (same bits on every rank).
+__device__ __forceinline__ double peer_allreduce_warp(double local, PeerInfo* P, int kind) {
+    const int lane = threadIdx.x & 31;
+    unsigned int seq = 0;
+    if (lane == 0) { seq = P->seq[kind] + 1; P->seq[kind] = seq; }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    const int n = P->nranks;
+    const int slot = ((kind * 2 + (int)(seq & 1u)) * kMaxRanks);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(local);
+    const unsigned long long w0 = ((unsigned long long)seq << 32) | (bits & 0xffffffffull);
+    const unsigned long long w1 = ((unsigned long long)seq << 32) | (bits >> 32);
+    __threadfence_system();                      // everything this rank wrote for its peers is visible first
+    if (lane < n) {                              // lane r publishes to rank r's mailbox (including our own)
+        unsigned long long* dst = P->mbox[lane] + (slot + P->rank) * 2;
+        st_sys_u64(dst, w0);
+        st_sys_u64(dst + 1, w1);
+    }
+    double v = 0.0;
+    bool ok = true;
+    if (lane < n) {                              // lane r collects rank r's contribution from OUR mailbox
+        const unsigned long long* src = P->mbox[P->rank] + (slot + lane) * 2;
+        unsigned long long a, b;
+        const long long t0 = clock64();
+        for (;;) {
+            a = ld_sys_u64(src);
+            b = ld_sys_u64(src + 1);
+            if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
+            if (clock64() - t0 > 20000000000LL) { ok = false; break; }     // ~10 s: a peer died; bail out instead of hanging
+        }
+        v = __longlong_as_double((long long)(((b & 0xffffffffull) << 32) | (a & 0xffffffffull)));
+    }
+    if (!__all_sync(0xffffffffu, ok)) {
+        if (lane == 0) P->error = 1;
+        return __longlong_as_double(0x7ff8000000000000LL);
+    }
+    double sum = 0.0;
+    for (int r = 0; r < n; ++r) sum += __shfl_sync(0xffffffffu, v, r);        // fixed rank order
+    __threadfence_system();
+    return sum;
+}
+
+// ---------------------------------------------------------------------------------------------
 // reductions: warp shuffle -> shared -> one partial per block -> last block sums the partials
 // in a fixed order (deterministic run to run; no floating-point atomics).
 // ---------------------------------------------------------------------------------------------
@@ -95,7 +168,8 @@ __device__ __forceinline__ double block_sum(double v, double* sm /*>=32 doubles*
 // Grid-wide sum with a "last block finishes" epilogue.  `fin(total)` runs in thread 0 of the last
 // block to arrive, after every block's partial is visible.  blockDim must be 1-D.
 template <class Fin>
-__device__ __forceinline__ void grid_sum_finish(double v, double* partials, unsigned int* counter, Fin fin) {
+__device__ __forceinline__ void grid_sum_finish(double v, double* partials, unsigned int* counter, Fin fin,
+                                                PeerInfo* peers = nullptr, int kind = 0) {
     __shared__ double sm[32];
     __shared__ bool is_last;
     const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
@@ -103,7 +177,7 @@ __device__ __forceinline__ void grid_sum_finish(double v, double* partials, unsi
     v = block_sum(v, sm);
     if (threadIdx.x == 0) {
         partials[bid] = v;
-        __threadfence();
+        if (peers) __threadfence_system(); else __threadfence();     // peer-memory stores of this block included
         unsigned int t = atomicAdd(counter, 1u);
         is_last = (t == nblocks - 1);
     }
@@ -113,6 +187,10 @@ __device__ __forceinline__ void grid_sum_finish(double v, double* partials, unsi
         double s = 0.0;
         for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) s += __ldcg(partials + i);
         s = block_sum(s, sm);
+        if (peers && threadIdx.x < 32) {          // fused all-reduce over the NVSwitch peers (warp 0 of the last block)
+            s = __shfl_sync(0xffffffffu, s, 0);
+            s = peer_allreduce_warp(s, peers, kind);
+        }
         if (threadIdx.x == 0) {
             *counter = 0;
             fin(s);
@@ -160,7 +238,7 @@ template <typename T, int VEC> struct Chunk {
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, T* __restrict__ x, T* __restrict__ r,
                                                                    const T* __restrict__ d, const T* __restrict__ q,
-                                                                   CgState* st, double* partials, int freeze) {
+                                                                   CgState* st, double* partials, int freeze, PeerInfo* peers) {
     if (*(volatile int*)&st->done) return;
     const double alpha_d = st->delta / st->dq;
     const T alpha = (T)alpha_d;
@@ -192,7 +270,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, 
         st->iter += 1;
         if (s < st->tol2) st->done = 1;
         else if (st->iter >= st->max_iter || !(s == s)) st->done = 2;  // NaN: the reference would spin to max_iter
-    });
+    }, freeze ? nullptr : peers, 1);
 }
 
 // K3:  beta = delta/delta_old ; d = r + beta d      (ViscosityCGSolver3D.py:607-610)
@@ -216,7 +294,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_d_kernel(long long n, T
 // start of a solve:  d = b - q ; r = d ; delta0 = r.r   (ViscosityCGSolver3D.py:577-587)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kVecThreads) cg_residual_init_kernel(long long n, const T* __restrict__ b, const T* __restrict__ q,
-                                                                       T* __restrict__ d, T* __restrict__ r, CgState* st, double* partials) {
+                                                                       T* __restrict__ d, T* __restrict__ r, CgState* st, double* partials, PeerInfo* peers) {
     double acc = 0.0;
     FS_STREAM_SETUP(n, VEC)
     for (long long i = _t0; i < _nv; i += _stride) {
@@ -240,7 +318,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_residual_init_kernel(long long
         st->delta0 = s;
         st->delta_old = s;
         if (s < st->tol2) st->done = 1;           // `if not self.delta < tol ** 2:` skips the loop
-    });
+    }, peers, 1);
 }
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -251,12 +329,13 @@ inline int vec_grid(long long n, int vec) {
 }
 
 template <typename T>
-int cg_launch_update_xr(long long n, T* x, T* r, const T* d, const T* q, CgState* st, double* partials, cudaStream_t s, int freeze = 0) {
+int cg_launch_update_xr(long long n, T* x, T* r, const T* d, const T* q, CgState* st, double* partials, cudaStream_t s, int freeze = 0,
+                        PeerInfo* peers = nullptr) {
     constexpr int N = Vec16<T>::N;
     if (aligned16(x) && aligned16(r) && aligned16(d) && aligned16(q))
-        cg_update_xr_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze);
+        cg_update_xr_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers);
     else
-        cg_update_xr_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze);
+        cg_update_xr_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers);
     FS_LAUNCH_CHECK();
     return FS_OK;
 }
@@ -273,12 +352,13 @@ int cg_launch_update_d(long long n, T* d, const T* r, CgState* st, cudaStream_t 
 }
 
 template <typename T>
-int cg_launch_residual_init(long long n, const T* b, const T* q, T* d, T* r, CgState* st, double* partials, cudaStream_t s) {
+int cg_launch_residual_init(long long n, const T* b, const T* q, T* d, T* r, CgState* st, double* partials, cudaStream_t s,
+                            PeerInfo* peers = nullptr) {
     constexpr int N = Vec16<T>::N;
     if (aligned16(b) && aligned16(q) && aligned16(d) && aligned16(r))
-        cg_residual_init_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, b, q, d, r, st, partials);
+        cg_residual_init_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, b, q, d, r, st, partials, peers);
     else
-        cg_residual_init_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, b, q, d, r, st, partials);
+        cg_residual_init_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, b, q, d, r, st, partials, peers);
     FS_LAUNCH_CHECK();
     return FS_OK;
 }

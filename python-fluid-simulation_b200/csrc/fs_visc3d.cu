@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(kThreads) visc3d_general_kernel(Visc3Dev<T> P,
 constexpr int kK1Threads = 256;
 constexpr int kK1BlocksPerSM = 3;
 
-template <typename T>
+template <typename T, bool DIST>
 __global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
-                                                                                       CgState* st_, double* partials) {
+                                                                                       CgState* st_, double* partials, PeerInfo* peers) {
     if (*(volatile int*)&st_->done) return;
     const Lat3& L = P.L;
     const long long NL = L.NL;
@@ -275,9 +275,26 @@ __global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_k
             q[i] = ou;
             q[NL + i] = ov;
             q[2 * NL + i] = ow;
+            if (DIST) {
+                // multi-GPU: my first / last owned planes are the neighbours' halo planes of q — store them straight
+                // into the peers' memory over NVLink; the all-reduce in this kernel's tail publishes them.
+                const long long lo0 = L.sx, hi0 = (long long)(L.X - 3) * L.sx;
+                if (peers->has_lo && i >= lo0 && i < lo0 + L.sx) {
+                    const long long o = i - lo0;
+                    reinterpret_cast<T*>(peers->q_lo[0])[o] = ou;
+                    reinterpret_cast<T*>(peers->q_lo[1])[o] = ov;
+                    reinterpret_cast<T*>(peers->q_lo[2])[o] = ow;
+                }
+                if (peers->has_hi && i >= hi0 && i < hi0 + L.sx) {
+                    const long long o = i - hi0;
+                    reinterpret_cast<T*>(peers->q_hi[0])[o] = ou;
+                    reinterpret_cast<T*>(peers->q_hi[1])[o] = ov;
+                    reinterpret_cast<T*>(peers->q_hi[2])[o] = ow;
+                }
+            }
         }
     }
-    grid_sum_finish(acc, partials, &st_->counter[0], [=](double sum) { st_->dq = sum; });
+    grid_sum_finish(acc, partials, &st_->counter[0], [=](double sum) { st_->dq = sum; }, DIST ? peers : nullptr, 0);
 }
 
 }  // namespace fs
@@ -304,6 +321,7 @@ struct fs_visc3d {
     bool packed;
     fs_comm* comm;   // multi-GPU: this handle is one x-slab (extended by one cell towards each neighbour)
     int has_lo, has_hi;
+    PeerInfo* peers; // device copy; non-null = collectives fused into K1/K2 over peer memory (NVLink), else NCCL per iteration
 };
 
 static Lat3 make_lat3(int nx, int ny, int nz) {
@@ -388,6 +406,44 @@ int fs_visc3d_set_slab(fs_visc3d* h, fs_comm* comm, int has_lo, int has_hi) {
     return FS_OK;
 }
 
+int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int hi_nx, void* const* mailboxes) {
+    if (!h || !mailboxes) return fail(FS_ERR_ARG, "fs_visc3d_set_peers: null argument");
+    if (!h->comm) return fail(FS_ERR_STATE, "fs_visc3d_set_peers: call fs_visc3d_set_slab first");
+    if ((h->has_lo && !lo_ws) || (h->has_hi && !hi_ws)) return fail(FS_ERR_ARG, "fs_visc3d_set_peers: missing neighbour workspace mapping");
+    if (h->comm->nranks > kMaxRanks) return fail(FS_ERR_ARG, "fs_visc3d_set_peers: more ranks than the mailbox supports");
+    PeerInfo pi;
+    memset(&pi, 0, sizeof(pi));
+    pi.rank = h->comm->rank; pi.nranks = h->comm->nranks;
+    pi.has_lo = h->has_lo; pi.has_hi = h->has_hi;
+    for (int r = 0; r < pi.nranks; ++r) {
+        if (!mailboxes[r]) return fail(FS_ERR_ARG, "fs_visc3d_set_peers: null mailbox");
+        pi.mbox[r] = (unsigned long long*)mailboxes[r];
+    }
+    const size_t esz = h->esz;
+    if (h->has_lo) {
+        Lat3 Ln = make_lat3(lo_nx, h->L.ny, h->L.nz);
+        Visc3Layout ln = visc3_layout(Ln, esz);
+        for (int c = 0; c < 3; ++c)
+            pi.q_lo[c] = (char*)lo_ws + ln.vecs + (((size_t)FS_VEC_Q * 3 + c) * Ln.NL + (size_t)(Ln.X - 2) * Ln.sx) * esz;
+    }
+    if (h->has_hi) {
+        Lat3 Ln = make_lat3(hi_nx, h->L.ny, h->L.nz);
+        Visc3Layout ln = visc3_layout(Ln, esz);
+        for (int c = 0; c < 3; ++c)
+            pi.q_hi[c] = (char*)hi_ws + ln.vecs + (((size_t)FS_VEC_Q * 3 + c) * Ln.NL) * esz;
+    }
+    if (!h->peers) FS_CUDA(cudaMalloc((void**)&h->peers, sizeof(PeerInfo)));
+    FS_CUDA(cudaMemcpy(h->peers, &pi, sizeof(pi), cudaMemcpyHostToDevice));
+    return FS_OK;
+}
+
+int fs_visc3d_peer_error(fs_visc3d* h) {
+    if (!h || !h->peers) return 0;
+    PeerInfo pi;
+    if (cudaMemcpy(&pi, h->peers, sizeof(pi), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return pi.error;
+}
+
 size_t fs_visc3d_workspace_bytes(int nx, int ny, int nz, int dtype) {
     if (nx < 1 || ny < 1 || nz < 1 || (dtype != FS_F32 && dtype != FS_F64)) return 0;
     Lat3 L = make_lat3(nx, ny, nz);
@@ -411,7 +467,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->partials = (double*)(h->ws + lay.partials); h->st = (CgState*)(h->ws + lay.st);
     h->grid_pts = lay.grid_pts;
     h->packed = false;
-    h->comm = nullptr; h->has_lo = 0; h->has_hi = 0;
+    h->comm = nullptr; h->has_lo = 0; h->has_hi = 0; h->peers = nullptr;
     int s = h->cg.init();
     if (s < 0) { delete h; return s; }
     h->cg.st_dev = h->st; h->cg.partials_dev = h->partials;
@@ -423,6 +479,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
 
 void fs_visc3d_destroy(fs_visc3d* h) {
     if (!h) return;
+    if (h->peers) cudaFree(h->peers);
     h->cg.destroy();
     delete h;
 }
@@ -531,13 +588,17 @@ int fs_visc3d_apply(fs_visc3d* h, double scale, double mu, int src_vec, int dst_
 static int visc3d_k1(fs_visc3d* h, double sm, cudaStream_t s) {
     long long want = (h->L.NL + kK1Threads - 1) / kK1Threads;
     const int grid = (int)(want < (long long)kSMs * kK1BlocksPerSM ? want : (long long)kSMs * kK1BlocksPerSM);
-    FS_DISPATCH(h, visc3d_apply_dot_kernel<T><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials));
+    if (h->peers) {
+        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, h->peers));
+    } else {
+        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, nullptr));
+    }
     FS_LAUNCH_CHECK();
     return FS_OK;
 }
 static int visc3d_k2(fs_visc3d* h, cudaStream_t s, int freeze = 0) {
     const long long n = 3 * h->L.NL;
-    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr<T>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s, freeze)));
+    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr<T>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s, freeze, h->peers)));
     return FS_OK;
 }
 static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
@@ -547,6 +608,14 @@ static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
 }
 
 static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
+    if (h->peers) {
+        // fused path: K1 pushes its boundary q planes into the neighbours and all-reduces d.q in its tail; K2 updates the
+        // halo rows of r with them and all-reduces r.r in its tail; K3 keeps the halo rows of d current.  No other traffic.
+        FS_TRY(visc3d_k1(h, sm, s));
+        FS_TRY(visc3d_k2(h, s));
+        FS_TRY(visc3d_k3(h, s));
+        return FS_OK;
+    }
     if (h->comm) FS_TRY(visc3d_halo_vec(h, FS_VEC_D, s));                       // neighbours' d planes for the stencil
     FS_TRY(visc3d_k1(h, sm, s));
     if (h->comm) FS_TRY(comm_allreduce_sum_f64(h->comm, &h->st->dq, 1, s));     // d.q over all slabs
@@ -562,14 +631,18 @@ static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
 
 static int visc3d_cg_begin(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, cudaStream_t s) {
     const long long n = 3 * h->L.NL;
-    cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, h->comm ? 1 : 0);
+    cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, (h->comm && !h->peers) ? 1 : 0);
     FS_LAUNCH_CHECK();
     FS_TRY(visc3d_general(h, scale, mu, FS_VEC_X, FS_VEC_Q, ROW_APPLY, s));   // q = A x   (:575)
-    FS_DISPATCH(h, FS_TRY(cg_launch_residual_init<T>(n, vec_ptr<T>(h, FS_VEC_B), vec_ptr<T>(h, FS_VEC_Q), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, h->partials, s)));
-    if (h->comm) {
+    FS_DISPATCH(h, FS_TRY(cg_launch_residual_init<T>(n, vec_ptr<T>(h, FS_VEC_B), vec_ptr<T>(h, FS_VEC_Q), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, h->partials, s, h->peers)));
+    if (h->comm && !h->peers) {
         FS_TRY(comm_allreduce_sum_f64(h->comm, &h->st->red, 1, s));
         cg_finish_kernel<<<1, 1, 0, s>>>(h->st, 0);
         FS_LAUNCH_CHECK();
+    }
+    if (h->peers) {   // one-time: halo rows of r and d (the fused iteration keeps them current from here on)
+        FS_TRY(visc3d_halo_vec(h, FS_VEC_R, s));
+        FS_TRY(visc3d_halo_vec(h, FS_VEC_D, s));
     }
     return FS_OK;
 }

@@ -34,10 +34,20 @@ def _fine_shape(g):
     return tuple(2 * n + 1 for n in g)
 
 
-class _Engine:
-    """Owns one native fs_visc3d handle + its device workspace."""
+class _RawDeviceBuffer:
+    """Lets torch alias a device allocation owned by the native library (``fs_shared_alloc``)."""
 
-    def __init__(self, g, dtype_code):
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class _Engine:
+    """Owns one native fs_visc3d handle + its device workspace.
+
+    ``shared=True`` allocates the workspace with ``fs_shared_alloc`` (plain cudaMalloc, exportable through CUDA IPC) so
+    that neighbouring ranks can map it; otherwise it comes from torch's caching allocator."""
+
+    def __init__(self, g, dtype_code, shared=False):
         self.lib = N.load()
         self.g = tuple(g)
         self.code = dtype_code
@@ -45,7 +55,16 @@ class _Engine:
         nbytes = self.lib.fs_visc3d_workspace_bytes(*self.g, dtype_code)
         if nbytes == 0:
             raise ValueError(f"invalid grid resolution {self.g}")
-        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device())
+        self.nbytes = nbytes
+        self.shared_ptr = None
+        if shared:
+            A.device()
+            self.shared_ptr = self.lib.fs_shared_alloc(nbytes)
+            if not self.shared_ptr:
+                raise N.NativeError("fs_shared_alloc failed: " + (self.lib.fs_last_error() or b"?").decode())
+            self.ws = torch.as_tensor(_RawDeviceBuffer(self.shared_ptr, nbytes), device=A.device())
+        else:
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device())
         h = ctypes.c_void_p()
         N.check(self.lib.fs_visc3d_create(ctypes.byref(h), *self.g, dtype_code, self.ws.data_ptr(), nbytes), "fs_visc3d_create")
         self.h = h
@@ -59,6 +78,10 @@ class _Engine:
             if getattr(self, "h", None):
                 self.lib.fs_visc3d_destroy(self.h)
                 self.h = None
+            if getattr(self, "shared_ptr", None):
+                self.ws = None
+                self.lib.fs_shared_free(self.shared_ptr)
+                self.shared_ptr = None
         except Exception:
             pass
 

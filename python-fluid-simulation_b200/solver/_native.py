@@ -58,6 +58,13 @@ _SIGS = {
     "fs_comm_rank": (c_int, [c_void_p]),
     "fs_comm_size": (c_int, [c_void_p]),
     "fs_visc3d_set_slab": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "fs_shared_alloc": (c_void_p, [c_size_t]),
+    "fs_shared_free": (None, [c_void_p]),
+    "fs_shared_get_handle": (c_int, [c_void_p, c_void_p]),
+    "fs_shared_open": (c_void_p, [c_void_p]),
+    "fs_shared_close": (None, [c_void_p]),
+    "fs_visc3d_set_peers": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(c_void_p)]),
+    "fs_visc3d_peer_error": (c_int, [c_void_p]),
     # viscosity 2-D
     "fs_visc2d_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "fs_visc2d_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_size_t]),

@@ -88,7 +88,12 @@ def get_comm(group=None):
 class SlabViscosityCGSolver3D:
     """Multi-GPU counterpart of ViscosityCGSolver3D: same ``solve()`` argument list, per-rank extended slabs."""
 
-    def __init__(self, gres, bound_size, dtype=torch.float64, group=None):
+    def __init__(self, gres, bound_size, dtype=torch.float64, group=None, transport=None):
+        """transport: "p2p" (default; collectives fused into the kernels over CUDA-IPC peer memory, one NVSwitch box)
+        or "nccl" (one NCCL halo exchange + two NCCL all-reduces per iteration; also the fallback if IPC is unavailable)."""
+        transport = transport or os.environ.get("FLUIDSOLVER_B200_TRANSPORT", "p2p")
+        if transport not in ("p2p", "nccl"):
+            raise ValueError("transport must be 'p2p' or 'nccl'")
         if not dist.is_initialized():
             raise RuntimeError("SlabViscosityCGSolver3D needs an initialised torch.distributed process group")
         self.gres = gres
@@ -97,15 +102,76 @@ class SlabViscosityCGSolver3D:
         self.cell_size = A.to_host_f64(bound_size, 3) / np.asarray(self._g, dtype=np.float64)
         self.cell_vol = float(np.prod(self.cell_size))
         self._code = _DT[dtype]
-        self._e = _Engine(self.part.local_gres, self._code)
+        self.transport = transport
+        self._e = _Engine(self.part.local_gres, self._code, shared=(transport == "p2p"))
         self._comm = get_comm(group)
         N.check(self._e.lib.fs_visc3d_set_slab(self._e.h, self._comm, int(self.part.has_lo), int(self.part.has_hi)), "fs_visc3d_set_slab")
+        self._mapped = []
+        if transport == "p2p" and self.part.world > 1:
+            self._connect_peers(group)
         for vec, nm in ((N.VEC_D, "d"), (N.VEC_R, "r"), (N.VEC_Q, "q"), (N.VEC_X, "x"), (N.VEC_B, "b")):
             for c, ax in enumerate("xyz"):
                 setattr(self, f"{nm}_{ax}", self._e.view(vec, c))
         self.alpha = self.beta = self.delta = 0.0
         self.iterations = 0
         self.max_iter = int(np.prod(np.asarray(self._g, dtype=np.int64)))
+
+    def _connect_peers(self, group):
+        """Exchange CUDA-IPC handles of the slab workspaces and scalar mailboxes and map the peers' buffers."""
+        lib, e, part = self._e.lib, self._e, self.part
+        rank, world = part.rank, part.world
+        self._mbox = lib.fs_shared_alloc(1024)
+        if not self._mbox:
+            raise N.NativeError("fs_shared_alloc(mailbox) failed")
+        hw, hm = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+        N.check(lib.fs_shared_get_handle(e.shared_ptr, hw), "fs_shared_get_handle")
+        N.check(lib.fs_shared_get_handle(self._mbox, hm), "fs_shared_get_handle")
+        infos = [None] * world
+        dist.all_gather_object(infos, (bytes(hw.raw), bytes(hm.raw), int(part.local_gres[0])), group=group)
+
+        def _open(raw):
+            p = lib.fs_shared_open(ctypes.create_string_buffer(raw, 64))
+            if not p:
+                raise N.NativeError("fs_shared_open failed: " + (lib.fs_last_error() or b"?").decode())
+            self._mapped.append(p)
+            return p
+
+        lo_ws = _open(infos[rank - 1][0]) if part.has_lo else None
+        hi_ws = _open(infos[rank + 1][0]) if part.has_hi else None
+        lo_nx = infos[rank - 1][2] if part.has_lo else 0
+        hi_nx = infos[rank + 1][2] if part.has_hi else 0
+        boxes = (ctypes.c_void_p * world)()
+        for r in range(world):
+            boxes[r] = self._mbox if r == rank else _open(infos[r][1])
+        N.check(lib.fs_visc3d_set_peers(e.h, lo_ws, lo_nx, hi_ws, hi_nx, boxes), "fs_visc3d_set_peers")
+        dist.barrier(group=group)
+
+    def close(self, group=None):
+        """Collective teardown: unmap the peers' buffers before any rank frees its own."""
+        lib = self._e.lib
+        torch.cuda.synchronize()
+        if dist.is_initialized() and self.part.world > 1:
+            dist.barrier(group=group)
+        for p in self._mapped:
+            lib.fs_shared_close(p)
+        self._mapped = []
+        if dist.is_initialized() and self.part.world > 1:
+            dist.barrier(group=group)
+        if getattr(self, "_mbox", None):
+            lib.fs_shared_free(self._mbox)
+            self._mbox = None
+
+    def __del__(self):
+        try:                       # best effort (no collective here: GC order differs between ranks)
+            lib = self._e.lib
+            for p in getattr(self, "_mapped", []):
+                lib.fs_shared_close(p)
+            self._mapped = []
+            if getattr(self, "_mbox", None):
+                lib.fs_shared_free(self._mbox)
+                self._mbox = None
+        except Exception:
+            pass
 
     def solve(self, dt, mu, rho, vx, vy, vz, sphi, sv, lphi, lvol, tol=1e-3):
         g, e = self.part.local_gres, self._e
@@ -118,6 +184,8 @@ class SlabViscosityCGSolver3D:
                                   s.ptr, vl.ptr, float(tol), int(self.max_iter), ctypes.byref(st), A.stream_ptr()),
             "fs_visc3d_solve")
         self.delta, self.alpha, self.beta, self.iterations = st.delta, st.alpha, st.beta, int(st.iterations)
+        if self.transport == "p2p" and e.lib.fs_visc3d_peer_error(e.h):
+            raise RuntimeError("a peer GPU did not answer inside a fused all-reduce")
         if status == N.FS_NOT_CONVERGED:
             raise ValueError("Failed to converge!")
         for a in v:
@@ -154,6 +222,7 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
     del full
     torch.cuda.empty_cache()
     solver = SlabViscosityCGSolver3D(g, bound, dtype=tdtype)
+    config = dict(config, transport=solver.transport)
     solver.max_iter = args.iters
     dev_in = [sc[k] for k in ("vx", "vy", "vz")]
 
@@ -245,6 +314,7 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
+    solver.close()
     dist.barrier()
     dist.destroy_process_group()
     return 0

@@ -23,12 +23,15 @@ def main():
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
 
     ok = True
-    for N, mu, dtype, g in ((24, 10.0, torch.float64, None), (32, 100.0, torch.float64, (37, 24, 28)), (32, 100.0, torch.float32, None)):
+    cases = [(24, 10.0, torch.float64, None, "nccl"), (24, 10.0, torch.float64, None, "p2p"),
+             (32, 100.0, torch.float64, (37, 24, 28), "p2p"), (32, 100.0, torch.float32, None, "p2p"),
+             (32, 100.0, torch.float64, (37, 24, 28), "nccl")]
+    for N, mu, dtype, g, transport in cases:
         full = scenes.buckling(N, device="cuda", mu=mu, gres=g)
         gres = full["gres"]
         part = SlabPartition(gres, world, rank)
         sc = scatter_scene(full, part)
-        s = SlabViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype)
+        s = SlabViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype, transport=transport)
         v = [sc[k].clone() for k in ("vx", "vy", "vz")]
         s.solve(full["dt"], mu, full["rho"], *v, sc["sphi"], None, None, sc["lvol"])
         its = torch.tensor([s.iterations], device="cuda")
@@ -54,9 +57,11 @@ def main():
             shp_ok = all(a.shape == b.shape for a, b in zip(pieces, rv))
             good = same_it and it_ok and shp_ok and max(errs) < 1e-4
             ok = ok and good
-            print(f"[dist_check] gres={gres} mu={mu} {dtype}: world={world} iters={s.iterations} (single-GPU {ref.iterations}) "
+            print(f"[dist_check] {transport} gres={gres} mu={mu} {dtype}: world={world} iters={s.iterations} (single-GPU {ref.iterations}) "
                   f"lockstep={same_it} rel_l2={['%.2e' % e for e in errs]} -> {'OK' if good else 'MISMATCH'}", flush=True)
         dist.barrier()
+        s.close()
+        del s
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
