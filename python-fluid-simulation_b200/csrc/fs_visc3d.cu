@@ -271,7 +271,10 @@ __global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_k
             if (av) { ov = rv; acc += (double)dv * (double)rv; }
             if (aw) { ow = rw; acc += (double)dw * (double)rw; }
         }
-        if (in) {
+        // multi-GPU: the halo planes of q (0 and X-2) are written by the NEIGHBOURS' K1 over NVLink — never by this rank
+        const bool halo_plane = DIST && ((peers->has_lo && i < L.sx) ||
+                                         (peers->has_hi && i >= (long long)(L.X - 2) * L.sx && i < (long long)(L.X - 1) * L.sx));
+        if (in && !halo_plane) {
             q[i] = ou;
             q[NL + i] = ov;
             q[2 * NL + i] = ow;
