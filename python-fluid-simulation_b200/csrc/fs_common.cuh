@@ -88,6 +88,9 @@ struct PeerInfo {
     unsigned long long* mbox[kMaxRanks];   // every rank's mailbox (own entry is the local pointer)
     unsigned int seq[2];                   // persistent sequence numbers of the two reductions (never reset)
     int error;                             // set to 1 if a peer did not answer within the spin budget
+    // halo rows inside each component array of `comp_len` elements (they mirror rows OWNED by a neighbour and must not
+    // be counted in r.r): [0, halo_lo_end) and [halo_hi_begin, halo_hi_end)
+    long long comp_len, halo_lo_end, halo_hi_begin, halo_hi_end;
 };
 
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -235,7 +238,9 @@ template <typename T, int VEC> struct Chunk {
 
 // K2:  alpha = delta/dq ; x += alpha d ; r -= alpha q ; delta' = r.r ; convergence bookkeeping.
 // (ViscosityCGSolver3D.py:594-606 / PressureCGSolver3D.py:211-219)
-template <typename T, int VEC>
+// DIST (multi-GPU, fused transport): halo rows are updated like any other row (their q was stored by the owner), but
+// only rows owned by this rank enter r.r; the all-reduce over the peers runs in the tail of this kernel.
+template <typename T, int VEC, bool DIST>
 __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, T* __restrict__ x, T* __restrict__ r,
                                                                    const T* __restrict__ d, const T* __restrict__ q,
                                                                    CgState* st, double* partials, int freeze, PeerInfo* peers) {
@@ -244,14 +249,21 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, 
     const T alpha = (T)alpha_d;
     double acc = 0.0;
     FS_STREAM_SETUP(n, VEC)
+    long long clen = n, lo_end = 0, hi_b = 0, hi_e = 0;
+    if (DIST) { clen = peers->comp_len; lo_end = peers->halo_lo_end; hi_b = peers->halo_hi_begin; hi_e = peers->halo_hi_end; }
     for (long long i = _t0; i < _nv; i += _stride) {
         Chunk<T, VEC> xv, rv, dv, qv;
         xv.load(x, i); rv.load(r, i); dv.load(d, i); qv.load(q, i);
+        bool own = true;
+        if (DIST) {                                   // a 16-byte chunk never straddles a plane (plane size % 4 == 0)
+            const long long e = (i * VEC) % clen;
+            own = !(e < lo_end || (e >= hi_b && e < hi_e));
+        }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
             xv.a[k] = xv.a[k] + alpha * dv.a[k];
             rv.a[k] = rv.a[k] - alpha * qv.a[k];
-            acc += (double)rv.a[k] * (double)rv.a[k];
+            if (own) acc += (double)rv.a[k] * (double)rv.a[k];
         }
         xv.store(x, i); rv.store(r, i);
     }
@@ -259,7 +271,9 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, 
         x[i] = x[i] + alpha * d[i];
         const T rr = r[i] - alpha * q[i];
         r[i] = rr;
-        acc += (double)rr * (double)rr;
+        bool own = true;
+        if (DIST) { const long long e = i % clen; own = !(e < lo_end || (e >= hi_b && e < hi_e)); }
+        if (own) acc += (double)rr * (double)rr;
     }
     grid_sum_finish(acc, partials, &st->counter[1], [=](double s) {
         if (freeze) return;                      // profiling hook: keep alpha/delta fixed across repeated launches
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, 
         st->iter += 1;
         if (s < st->tol2) st->done = 1;
         else if (st->iter >= st->max_iter || !(s == s)) st->done = 2;  // NaN: the reference would spin to max_iter
-    }, freeze ? nullptr : peers, 1);
+    }, (DIST && !freeze) ? peers : nullptr, 1);
 }
 
 // K3:  beta = delta/delta_old ; d = r + beta d      (ViscosityCGSolver3D.py:607-610)
@@ -332,10 +346,14 @@ template <typename T>
 int cg_launch_update_xr(long long n, T* x, T* r, const T* d, const T* q, CgState* st, double* partials, cudaStream_t s, int freeze = 0,
                         PeerInfo* peers = nullptr) {
     constexpr int N = Vec16<T>::N;
-    if (aligned16(x) && aligned16(r) && aligned16(d) && aligned16(q))
-        cg_update_xr_kernel<T, N><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers);
-    else
-        cg_update_xr_kernel<T, 1><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers);
+    const bool vec = aligned16(x) && aligned16(r) && aligned16(d) && aligned16(q);
+    if (peers) {
+        if (vec) cg_update_xr_kernel<T, N, true><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers);
+        else cg_update_xr_kernel<T, 1, true><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers);
+    } else {
+        if (vec) cg_update_xr_kernel<T, N, false><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, nullptr);
+        else cg_update_xr_kernel<T, 1, false><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, nullptr);
+    }
     FS_LAUNCH_CHECK();
     return FS_OK;
 }

@@ -435,6 +435,10 @@ int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int h
         for (int c = 0; c < 3; ++c)
             pi.q_hi[c] = (char*)hi_ws + ln.vecs + (((size_t)FS_VEC_Q * 3 + c) * Ln.NL) * esz;
     }
+    pi.comp_len = h->L.NL;
+    pi.halo_lo_end = h->has_lo ? h->L.sx : 0;
+    pi.halo_hi_begin = h->has_hi ? (long long)(h->L.X - 2) * h->L.sx : 0;
+    pi.halo_hi_end = h->has_hi ? (long long)(h->L.X - 1) * h->L.sx : 0;
     if (!h->peers) FS_CUDA(cudaMalloc((void**)&h->peers, sizeof(PeerInfo)));
     FS_CUDA(cudaMemcpy(h->peers, &pi, sizeof(pi), cudaMemcpyHostToDevice));
     return FS_OK;
@@ -637,6 +641,15 @@ static int visc3d_cg_begin(fs_visc3d* h, double scale, double mu, double tol, in
     cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, (h->comm && !h->peers) ? 1 : 0);
     FS_LAUNCH_CHECK();
     FS_TRY(visc3d_general(h, scale, mu, FS_VEC_X, FS_VEC_Q, ROW_APPLY, s));   // q = A x   (:575)
+    if (h->peers) {
+        // fused transport: the halo planes of q still hold what the neighbours stored during the previous solve; they must
+        // read as zero (rows not computed here) when r0 = b - q and delta0 are formed
+        for (int c = 0; c < 3; ++c) {
+            char* comp = h->vecs + ((size_t)FS_VEC_Q * 3 + c) * h->L.NL * h->esz;
+            if (h->has_lo) FS_CUDA(cudaMemsetAsync(comp, 0, (size_t)h->L.sx * h->esz, s));
+            if (h->has_hi) FS_CUDA(cudaMemsetAsync(comp + (size_t)(h->L.X - 2) * h->L.sx * h->esz, 0, (size_t)h->L.sx * h->esz, s));
+        }
+    }
     FS_DISPATCH(h, FS_TRY(cg_launch_residual_init<T>(n, vec_ptr<T>(h, FS_VEC_B), vec_ptr<T>(h, FS_VEC_Q), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, h->partials, s, h->peers)));
     if (h->comm && !h->peers) {
         FS_TRY(comm_allreduce_sum_f64(h->comm, &h->st->red, 1, s));
