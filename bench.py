@@ -136,6 +136,9 @@ def run_reference(args):
 
 
 def workload_config(args, n, where):
+    if getattr(args, "scene", "buckling") != "buckling":
+        return {"workload": f"viscous-column-{n}^3 (dense fluid, kernel study; NOT the BASELINE config)", "grid": [n, n, n], "mu": args.mu,
+                "iters_per_step": args.iters, "l2": "working set >> L2"}
     return {"workload": f"buckling-{n}^3 high-viscosity (mu={args.mu:g}), ViscosityCGSolver3D fixed {args.iters}-iteration CG window per step"
                         if where != "cpu" else f"buckling-{n}^3 high-viscosity (mu={args.mu:g}), ViscosityCGSolver3D CG iterations",
             "grid": [n, n, n], "mu": args.mu, "dt": 1.0 / 300, "rho": 1000.0, "iters_per_step": args.iters if where != "cpu" else args.ref_iters,
@@ -163,6 +166,7 @@ def run_native(args):
             sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fluidsolver_b200_nccl_%h_%p.log")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tdtype = torch.float64 if args.dtype == "f64" else torch.float32
     esz = 8 if args.dtype == "f64" else 4
@@ -177,7 +181,7 @@ def run_native(args):
 
     lib = N.load()
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
-    sc = scenes.buckling(n, device="cuda", mu=args.mu)
+    sc = scenes.buckling(n, device="cuda", mu=args.mu) if args.scene == "buckling" else scenes.viscous_column((n, n, n), device="cuda", mu=args.mu)
     solver = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], dtype=tdtype)
     solver.max_iter = args.iters
     dev_in = [sc[k] for k in ("vx", "vy", "vz")]
@@ -312,6 +316,8 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=4, help="CG iterations per step of the CPU arm / cpu_baseline sample")
     ap.add_argument("--mu", type=float, default=100.0)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="solver storage/arithmetic type (reference: f64)")
+    ap.add_argument("--scene", default="buckling", choices=["buckling", "column"],
+                    help="buckling = BASELINE config 4 (default); column = dense-fluid viscous column (config 5 geometry) for kernel studies")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
