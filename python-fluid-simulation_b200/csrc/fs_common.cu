@@ -1,4 +1,6 @@
 // Library-wide state and the small non-template pieces of the CG control.
+#include <stdlib.h>
+
 #include "fs_common.cuh"
 
 namespace fs {
@@ -44,6 +46,15 @@ __global__ void cg_state_unlimit_kernel(CgState* st) {
     st->done = 0;
     st->tol2 = -1.0;
     st->max_iter = 0x7fffffffffffffffLL;
+}
+
+bool IterGraph::enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("FLUIDSOLVER_B200_GRAPH");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
 }
 
 int CgHost::init() {

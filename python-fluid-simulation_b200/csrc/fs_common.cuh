@@ -397,10 +397,70 @@ struct CgHost {
     void destroy();
 };
 
-// Runs `iter_fn(stream)` (enqueue K1,K2,K3 once) in batches until the device flags completion.
+// A batch of CG iterations captured once into a CUDA graph (3 kernel nodes per iteration) and replayed: removes the
+// per-launch gaps that dominate when an iteration is only ~100 us of work (multi-GPU slabs, 64^3, the 2-D configs).
+// Capture happens on an internal non-blocking stream because the caller's stream is usually the legacy default
+// stream, which cannot be captured; the instantiated graph is then launched into the caller's stream.
+struct IterGraph {
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t cap = nullptr;
+    double key = 0.0;
+    int iters = 0;
+    bool valid = false;
+    static bool enabled();
+
+    template <class EnqueueOne>
+    int ensure(double key_, int iters_, EnqueueOne one) {
+        if (valid && key == key_ && iters == iters_) return FS_OK;
+        if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
+        valid = false;
+        if (!cap) FS_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        const long long launches_before = g_launches;
+        FS_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        int status = FS_OK;
+        for (int k = 0; k < iters_ && status >= 0; ++k) status = one(cap);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(cap, &graph);
+        per_launch = g_launches - launches_before;
+        g_launches = launches_before;
+        if (status < 0) { if (graph) cudaGraphDestroy(graph); return status; }
+        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { exec = nullptr; return fail(FS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+        key = key_; iters = iters_; valid = true;
+        return FS_OK;
+    }
+    int launch(cudaStream_t s) {
+        FS_CUDA(cudaGraphLaunch(exec, s));
+        g_launches += per_launch;
+        return FS_OK;
+    }
+    void destroy() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (cap) cudaStreamDestroy(cap);
+        exec = nullptr; cap = nullptr; valid = false;
+    }
+    long long per_launch = 0;
+};
+
+constexpr int kCgBatch = 16;
+
+// Enqueue `n` iterations: whole batches of kCgBatch through the graph, the remainder launch by launch.
+template <class EnqueueOne>
+int cg_enqueue_iterations(IterGraph& g, bool use_graph, double key, long long n, EnqueueOne one, cudaStream_t s) {
+    if (use_graph && IterGraph::enabled() && n >= kCgBatch) {
+        FS_TRY(g.ensure(key, kCgBatch, one));
+        while (n >= kCgBatch) { FS_TRY(g.launch(s)); n -= kCgBatch; }
+    }
+    for (long long k = 0; k < n; ++k) FS_TRY(one(s));
+    return FS_OK;
+}
+
+// Runs `batch_fn(stream, nb)` (enqueue nb iterations of K1,K2,K3) until the device flags completion.
 // Blocks the calling thread; fills stats.  Returns FS_OK / FS_NOT_CONVERGED / <0.
-template <class IterFn>
-int cg_drive(CgHost& c, IterFn iter_fn, long long max_iter, fs_cg_stats* stats, cudaStream_t s, int batch = 16) {
+template <class BatchFn>
+int cg_drive(CgHost& c, BatchFn batch_fn, long long max_iter, fs_cg_stats* stats, cudaStream_t s, int batch = kCgBatch) {
     // state already initialised and residual_init enqueued by the caller
     int slot = 0;
     bool pending[2] = {false, false};
@@ -409,7 +469,7 @@ int cg_drive(CgHost& c, IterFn iter_fn, long long max_iter, fs_cg_stats* stats, 
     for (;;) {
         long long nb = batch;
         if (enq + nb > max_iter) nb = max_iter - enq;
-        for (long long k = 0; k < nb; ++k) FS_TRY(iter_fn(s));
+        FS_TRY(batch_fn(s, nb));
         enq += nb;
         FS_CUDA(cudaMemcpyAsync(&c.st_pinned[slot], c.st_dev, sizeof(CgState), cudaMemcpyDeviceToHost, s));
         FS_CUDA(cudaEventRecord(c.ev[slot], s));

@@ -245,6 +245,8 @@ struct fs_press {
     CgState* st;
     CgHost cg;
     int grid;
+    IterGraph graph;
+    const void* gkey[9];   // pointer set the captured graph was built for
 };
 
 static size_t press_ws(long long ncells, size_t* off_st) {
@@ -284,12 +286,27 @@ static int press_apply_launch(fs_press* h, const double* v, double* out, const d
     return FS_OK;
 }
 
+static bool press_same_ptrs(fs_press* h, const void* const* p) {
+    for (int k = 0; k < 9; ++k) if (h->gkey[k] != p[k]) return false;
+    return true;
+}
+
 static int press_iteration(fs_press* h, double* x, double* d, double* r, double* q, const double* wx, const double* wy, const double* wz,
                            const double* lphi, cudaStream_t s) {
     FS_TRY(press_apply_launch(h, d, q, wx, wy, wz, lphi, true, s));
     FS_TRY((cg_launch_update_xr<double>(h->ncells, x, r, d, q, h->st, h->partials, s)));
     FS_TRY((cg_launch_update_d<double>(h->ncells, d, r, h->st, s)));
     return FS_OK;
+}
+
+static int press_iterations(fs_press* h, double* x, double* d, double* r, double* q, const double* wx, const double* wy, const double* wz,
+                            const double* lphi, long long n, cudaStream_t s) {
+    const void* ptrs[9] = {x, d, r, q, wx, wy, wz, lphi, nullptr};
+    if (!press_same_ptrs(h, ptrs)) {                      // the graph bakes the array pointers in
+        h->graph.valid = false;
+        for (int k = 0; k < 9; ++k) h->gkey[k] = ptrs[k];
+    }
+    return cg_enqueue_iterations(h->graph, true, 1.0, n, [&](cudaStream_t ss) { return press_iteration(h, x, d, r, q, wx, wy, wz, lphi, ss); }, s);
 }
 
 extern "C" {
@@ -312,6 +329,7 @@ int fs_press_create(fs_press** out, int nx, int ny, int nz, void* ws, size_t ws_
     h->partials = (double*)ws;
     h->st = (CgState*)((char*)ws + off_st);
     h->grid = (int)((h->ncells + kPT - 1) / kPT);
+    for (int k = 0; k < 9; ++k) h->gkey[k] = nullptr;
     int s = h->cg.init();
     if (s < 0) { delete h; return s; }
     h->cg.st_dev = h->st; h->cg.partials_dev = h->partials;
@@ -323,6 +341,7 @@ int fs_press_create(fs_press** out, int nx, int ny, int nz, void* ws, size_t ws_
 
 void fs_press_destroy(fs_press* h) {
     if (!h) return;
+    h->graph.destroy();
     h->cg.destroy();
     delete h;
 }
@@ -383,7 +402,8 @@ int fs_press_cg(fs_press* h, double* x, double* d, double* r, double* q, const d
     FS_CUDA(cudaMemsetAsync(x, 0, h->ncells * sizeof(double), s));                       // self.x *= 0.0   (:198)
     FS_TRY(press_apply_launch(h, x, q, wx, wy, wz, lphi, false, s));                     // q = A x         (:201)
     FS_TRY((cg_launch_residual_init<double>(h->ncells, b, q, d, r, h->st, h->partials, s)));   // d = b - q ; r = d ; delta (:202-204)
-    return cg_drive(h->cg, [&](cudaStream_t ss) { return press_iteration(h, x, d, r, q, wx, wy, wz, lphi, ss); }, (long long)max_iter, stats, s);
+    return cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return press_iterations(h, x, d, r, q, wx, wy, wz, lphi, nb, ss); },
+                    (long long)max_iter, stats, s);
 }
 
 int fs_press_cg_enqueue(fs_press* h, double* x, double* d, double* r, double* q,
@@ -391,8 +411,7 @@ int fs_press_cg_enqueue(fs_press* h, double* x, double* d, double* r, double* q,
     if (!h || !x || !d || !r || !q || !wx || !wy || !lphi || (h->nz > 0 && !wz)) return fail(FS_ERR_ARG, "fs_press_cg_enqueue: null argument");
     cg_state_unlimit_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->st);
     FS_LAUNCH_CHECK();
-    for (int64_t k = 0; k < n; ++k) FS_TRY(press_iteration(h, x, d, r, q, wx, wy, wz, lphi, (cudaStream_t)stream));
-    return FS_OK;
+    return press_iterations(h, x, d, r, q, wx, wy, wz, lphi, n, (cudaStream_t)stream);
 }
 
 int fs_solidfrac3d(int nx, int ny, int nz, const double* sphi, double* wx, double* wy, double* wz, void* stream) {

@@ -176,6 +176,7 @@ struct fs_visc2d {
     CgHost cg;
     int grid_pts;
     bool packed;
+    IterGraph graph;
 };
 
 static Lat2 make_lat2(int W, int H) {
@@ -273,6 +274,7 @@ int fs_visc2d_create(fs_visc2d** out, int W, int H, int dtype, void* ws, size_t 
 
 void fs_visc2d_destroy(fs_visc2d* h) {
     if (!h) return;
+    h->graph.destroy();
     h->cg.destroy();
     delete h;
 }
@@ -347,7 +349,9 @@ int fs_visc2d_cg(fs_visc2d* h, double scale, double mu, double tol, int64_t max_
     FS_TRY(v2_general(h, scale, mu, FS_VEC_X, FS_VEC_Q, ROW_APPLY, s));
     FS_DISPATCH2(h, FS_TRY(cg_launch_residual_init<T>(n, vec2<T>(h, FS_VEC_B), vec2<T>(h, FS_VEC_Q), vec2<T>(h, FS_VEC_D), vec2<T>(h, FS_VEC_R), h->st, h->partials, s)));
     const double sm = scale * mu;
-    return cg_drive(h->cg, [&](cudaStream_t ss) { return v2_iteration(h, sm, ss); }, (long long)max_iter, stats, s);
+    return cg_drive(h->cg, [&](cudaStream_t ss, long long nb) {
+        return cg_enqueue_iterations(h->graph, true, sm, nb, [&](cudaStream_t s3) { return v2_iteration(h, sm, s3); }, ss);
+    }, (long long)max_iter, stats, s);
 }
 
 int fs_visc2d_solve(fs_visc2d* h, double dt, double mu, double rho, double cell_vol, void* vx, void* vy, int vel_dtype,

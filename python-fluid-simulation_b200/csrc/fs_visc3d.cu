@@ -324,6 +324,7 @@ struct fs_visc3d {
     bool packed;
     fs_comm* comm;   // multi-GPU: this handle is one x-slab (extended by one cell towards each neighbour)
     int has_lo, has_hi;
+    IterGraph graph; // captured batch of iterations (single GPU and fused multi-GPU transport)
     PeerInfo* peers; // device copy; non-null = collectives fused into K1/K2 over peer memory (NVLink), else NCCL per iteration
 };
 
@@ -406,6 +407,7 @@ int fs_visc3d_set_slab(fs_visc3d* h, fs_comm* comm, int has_lo, int has_hi) {
     h->has_hi = has_hi ? 1 : 0;
     h->L.u_xhi = h->L.nx - 1 - h->has_hi;
     h->packed = false;
+    h->graph.valid = false;
     return FS_OK;
 }
 
@@ -441,6 +443,7 @@ int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int h
     pi.halo_hi_end = h->has_hi ? (long long)(h->L.X - 1) * h->L.sx : 0;
     if (!h->peers) FS_CUDA(cudaMalloc((void**)&h->peers, sizeof(PeerInfo)));
     FS_CUDA(cudaMemcpy(h->peers, &pi, sizeof(pi), cudaMemcpyHostToDevice));
+    h->graph.valid = false;
     return FS_OK;
 }
 
@@ -487,6 +490,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
 void fs_visc3d_destroy(fs_visc3d* h) {
     if (!h) return;
     if (h->peers) cudaFree(h->peers);
+    h->graph.destroy();
     h->cg.destroy();
     delete h;
 }
@@ -636,6 +640,12 @@ static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
     return FS_OK;
 }
 
+// NCCL calls are not captured: graphs are used on a single GPU and with the fused peer-memory transport only
+static int visc3d_iterations(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
+    const bool graph_ok = !(h->comm && !h->peers);
+    return cg_enqueue_iterations(h->graph, graph_ok, sm, n, [&](cudaStream_t ss) { return visc3d_iteration(h, sm, ss); }, s);
+}
+
 static int visc3d_cg_begin(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, cudaStream_t s) {
     const long long n = 3 * h->L.NL;
     cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, (h->comm && !h->peers) ? 1 : 0);
@@ -669,7 +679,7 @@ int fs_visc3d_cg(fs_visc3d* h, double scale, double mu, double tol, int64_t max_
     cudaStream_t s = (cudaStream_t)stream;
     FS_TRY(visc3d_cg_begin(h, scale, mu, tol, max_iter, s));
     const double sm = scale * mu;
-    return cg_drive(h->cg, [&](cudaStream_t ss) { return visc3d_iteration(h, sm, ss); }, (long long)max_iter, stats, s);
+    return cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter, stats, s);
 }
 
 int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void* stream) {
@@ -678,8 +688,7 @@ int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void*
     const double sm = scale * mu;
     cg_state_unlimit_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->st);
     FS_LAUNCH_CHECK();
-    for (int64_t k = 0; k < n; ++k) FS_TRY(visc3d_iteration(h, sm, (cudaStream_t)stream));
-    return FS_OK;
+    return visc3d_iterations(h, sm, n, (cudaStream_t)stream);
 }
 
 int fs_visc3d_kernel_enqueue(fs_visc3d* h, int which, double scale, double mu, int64_t n, void* stream) {

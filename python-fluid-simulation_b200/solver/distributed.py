@@ -25,17 +25,52 @@ from . import _native as N
 from .ViscosityCGSolver3D import _DT, _TORCH, _Engine, _fine_shape, _mac_args
 
 
-class SlabPartition:
-    """Balanced x-slabs.  ``[c0, c1)`` = owned cells, ``[e0, e1)`` = extended cells held locally."""
+def balanced_starts(cost, world, min_cells=2):
+    """Slab boundaries that equalise the summed per-plane cost (prefix-sum splitting, every slab >= min_cells)."""
+    cost = np.asarray(cost, dtype=np.float64)
+    nx = cost.size
+    pre = np.concatenate([[0.0], np.cumsum(cost)])
+    starts = [0]
+    for r in range(1, world):
+        target = pre[-1] * r / world
+        b = int(np.searchsorted(pre, target, side="left"))
+        if b > 0 and abs(pre[b - 1] - target) < abs(pre[b] - target):
+            b -= 1
+        b = max(b, starts[-1] + min_cells)
+        b = min(b, nx - min_cells * (world - r))
+        starts.append(b)
+    starts.append(nx)
+    return starts
 
-    def __init__(self, gres, world, rank):
+
+def plane_cost_from_sphi(sphi, gres, fluid_weight=0.4):
+    """Relative cost of each x-plane of cells for the viscosity iteration: K2/K3 stream every row alike, K1 skips solid
+    rows, so a plane costs 1 + fluid_weight * (fraction of its cell centres inside the fluid region sphi >= 0).
+    fluid_weight was fitted on B200 (fluid planes cost ~1.4x solid ones at 256^3 fp64)."""
+    g = tuple(int(n) for n in gres)
+    centres = sphi[1::2, 1::2, 1::2][: g[0], : g[1], : g[2]]
+    frac = (centres >= 0).to(torch.float64).mean(dim=(1, 2)).cpu().numpy()
+    return 1.0 + fluid_weight * frac
+
+
+class SlabPartition:
+    """x-slabs.  ``[c0, c1)`` = owned cells, ``[e0, e1)`` = extended cells held locally.  With ``plane_cost`` (one
+    relative cost per x-plane of cells) the cuts equalise the summed cost instead of the cell count."""
+
+    def __init__(self, gres, world, rank, plane_cost=None):
         self.gres = tuple(int(n) for n in gres)
         self.world, self.rank = int(world), int(rank)
         nx = self.gres[0]
         if nx < 2 * self.world:
             raise ValueError(f"grid too thin for {world} slabs: nx={nx}")
-        base, rem = divmod(nx, self.world)
-        starts = [r * base + min(r, rem) for r in range(self.world + 1)]
+        if plane_cost is not None:
+            if len(plane_cost) != nx:
+                raise ValueError("plane_cost needs one entry per x-plane of cells")
+            starts = balanced_starts(plane_cost, self.world)
+        else:
+            base, rem = divmod(nx, self.world)
+            starts = [r * base + min(r, rem) for r in range(self.world + 1)]
+        self.starts = starts
         self.c0, self.c1 = starts[self.rank], starts[self.rank + 1]
         self.has_lo = self.rank > 0
         self.has_hi = self.rank < self.world - 1
@@ -88,8 +123,9 @@ def get_comm(group=None):
 class SlabViscosityCGSolver3D:
     """Multi-GPU counterpart of ViscosityCGSolver3D: same ``solve()`` argument list, per-rank extended slabs."""
 
-    def __init__(self, gres, bound_size, dtype=torch.float64, group=None, transport=None):
-        """transport: "p2p" (default; collectives fused into the kernels over CUDA-IPC peer memory, one NVSwitch box)
+    def __init__(self, gres, bound_size, dtype=torch.float64, group=None, transport=None, partition=None):
+        """partition: a SlabPartition (e.g. cost-balanced); default = equal cell counts.
+        transport: "p2p" (default; collectives fused into the kernels over CUDA-IPC peer memory, one NVSwitch box)
         or "nccl" (one NCCL halo exchange + two NCCL all-reduces per iteration; also the fallback if IPC is unavailable)."""
         transport = transport or os.environ.get("FLUIDSOLVER_B200_TRANSPORT", "p2p")
         if transport not in ("p2p", "nccl"):
@@ -98,7 +134,9 @@ class SlabViscosityCGSolver3D:
             raise RuntimeError("SlabViscosityCGSolver3D needs an initialised torch.distributed process group")
         self.gres = gres
         self._g = A.to_host_ints(gres)
-        self.part = SlabPartition(self._g, dist.get_world_size(group), dist.get_rank(group))
+        self.part = partition if partition is not None else SlabPartition(self._g, dist.get_world_size(group), dist.get_rank(group))
+        if self.part.gres != tuple(self._g) or self.part.world != dist.get_world_size(group) or self.part.rank != dist.get_rank(group):
+            raise ValueError("partition does not match gres / process group")
         self.cell_size = A.to_host_f64(bound_size, 3) / np.asarray(self._g, dtype=np.float64)
         self.cell_vol = float(np.prod(self.cell_size))
         self._code = _DT[dtype]
@@ -215,14 +253,15 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
     esz = 8 if args.dtype == "f64" else 4
     n = args.size
     g = (n, n, n)
-    part = SlabPartition(g, world, rank)
     full = scenes.buckling(n, device="cuda", mu=args.mu)
+    balance = os.environ.get("FLUIDSOLVER_B200_BALANCE", "1") != "0"
+    part = SlabPartition(g, world, rank, plane_cost=plane_cost_from_sphi(full["sphi"], g) if balance else None)
     sc = scatter_scene(full, part)
     bound = full["bound_size"]
     del full
     torch.cuda.empty_cache()
-    solver = SlabViscosityCGSolver3D(g, bound, dtype=tdtype)
-    config = dict(config, transport=solver.transport)
+    solver = SlabViscosityCGSolver3D(g, bound, dtype=tdtype, partition=part)
+    config = dict(config, transport=solver.transport, slab_starts=part.starts, balanced=balance)
     solver.max_iter = args.iters
     dev_in = [sc[k] for k in ("vx", "vy", "vz")]
 

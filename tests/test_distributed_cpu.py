@@ -31,6 +31,25 @@ def test_partition_covers_grid_exactly():
                 assert covered == list(range(total))
 
 
+def test_cost_balanced_partition():
+    from solver.distributed import SlabPartition, balanced_starts
+    cost = np.ones(64)
+    cost[16:48] = 1.5                      # fluid planes cost more
+    starts = balanced_starts(cost, 8)
+    assert starts[0] == 0 and starts[-1] == 64 and all(b - a >= 2 for a, b in zip(starts, starts[1:]))
+    sums = [cost[a:b].sum() for a, b in zip(starts, starts[1:])]
+    assert max(sums) <= 1.15 * (cost.sum() / 8)
+    eq = [cost[a:b].sum() for a, b in zip(range(0, 64, 8), range(8, 72, 8))]
+    assert max(sums) < max(eq)
+    parts = [SlabPartition((64, 4, 4), 8, r, plane_cost=cost) for r in range(8)]
+    assert [p.c0 for p in parts] + [64] == starts
+    # degenerate: all the cost in one plane still leaves every slab >= 2 cells
+    spike = np.full(16, 1e-6)
+    spike[7] = 1.0
+    st = balanced_starts(spike, 4)
+    assert all(b - a >= 2 for a, b in zip(st, st[1:])) and st[-1] == 16
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
