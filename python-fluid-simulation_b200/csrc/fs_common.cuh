@@ -93,6 +93,15 @@ struct PeerInfo {
     long long comp_len, halo_lo_end, halo_hi_begin, halo_hi_end;
 };
 
+// The fields the per-point / per-chunk code paths need, passed to kernels BY VALUE (constant bank) so that no global
+// load sits in the inner loops; the PeerInfo pointer is only dereferenced in the reduction tail.
+struct PeerHot {
+    int has_lo, has_hi;
+    char* q_lo[3];
+    char* q_hi[3];
+    long long comp_len, halo_lo_end, halo_hi_begin, halo_hi_end;
+};
+
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -172,7 +181,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm /*>=32 doubles*
 // block to arrive, after every block's partial is visible.  blockDim must be 1-D.
 template <class Fin>
 __device__ __forceinline__ void grid_sum_finish(double v, double* partials, unsigned int* counter, Fin fin,
-                                                PeerInfo* peers = nullptr, int kind = 0) {
+                                                PeerInfo* peers = nullptr, int kind = 0, bool wrote_peer = false) {
     __shared__ double sm[32];
     __shared__ bool is_last;
     const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
@@ -180,7 +189,7 @@ __device__ __forceinline__ void grid_sum_finish(double v, double* partials, unsi
     v = block_sum(v, sm);
     if (threadIdx.x == 0) {
         partials[bid] = v;
-        if (peers) __threadfence_system(); else __threadfence();     // peer-memory stores of this block included
+        if (wrote_peer) __threadfence_system(); else __threadfence();   // system scope only if this block stored into a peer GPU
         unsigned int t = atomicAdd(counter, 1u);
         is_last = (t == nblocks - 1);
     }
@@ -243,37 +252,43 @@ template <typename T, int VEC> struct Chunk {
 template <typename T, int VEC, bool DIST>
 __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, T* __restrict__ x, T* __restrict__ r,
                                                                    const T* __restrict__ d, const T* __restrict__ q,
-                                                                   CgState* st, double* partials, int freeze, PeerInfo* peers) {
+                                                                   CgState* st, double* partials, int freeze, PeerInfo* peers, PeerHot hot) {
     if (*(volatile int*)&st->done) return;
     const double alpha_d = st->delta / st->dq;
     const T alpha = (T)alpha_d;
     double acc = 0.0;
-    FS_STREAM_SETUP(n, VEC)
-    long long clen = n, lo_end = 0, hi_b = 0, hi_e = 0;
-    if (DIST) { clen = peers->comp_len; lo_end = peers->halo_lo_end; hi_b = peers->halo_hi_begin; hi_e = peers->halo_hi_end; }
-    for (long long i = _t0; i < _nv; i += _stride) {
-        Chunk<T, VEC> xv, rv, dv, qv;
-        xv.load(x, i); rv.load(r, i); dv.load(d, i); qv.load(q, i);
-        bool own = true;
-        if (DIST) {                                   // a 16-byte chunk never straddles a plane (plane size % 4 == 0)
-            const long long e = (i * VEC) % clen;
-            own = !(e < lo_end || (e >= hi_b && e < hi_e));
-        }
+    const long long _stride = (long long)gridDim.x * blockDim.x;
+    const long long _t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // DIST: walk the component arrays one after the other so that "is this a halo row" is three compares on the index
+    // inside the component (a 16-byte chunk never straddles a plane: plane sizes are multiples of 4 elements).
+    const long long clen = DIST ? hot.comp_len : n;
+    const int ncomp = DIST ? (int)(n / clen) : 1;
+    const long long nv = clen / VEC;
+    for (int c = 0; c < ncomp; ++c) {
+        T* xc = x + c * clen; T* rc = r + c * clen;
+        const T* dc = d + c * clen; const T* qc = q + c * clen;
+        for (long long i = _t0; i < nv; i += _stride) {
+            Chunk<T, VEC> xv, rv, dv, qv;
+            xv.load(xc, i); rv.load(rc, i); dv.load(dc, i); qv.load(qc, i);
+            bool own = true;
+            if (DIST) {
+                const long long e = i * VEC;
+                own = !(e < hot.halo_lo_end || (e >= hot.halo_hi_begin && e < hot.halo_hi_end));
+            }
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            xv.a[k] = xv.a[k] + alpha * dv.a[k];
-            rv.a[k] = rv.a[k] - alpha * qv.a[k];
-            if (own) acc += (double)rv.a[k] * (double)rv.a[k];
+            for (int k = 0; k < VEC; ++k) {
+                xv.a[k] = xv.a[k] + alpha * dv.a[k];
+                rv.a[k] = rv.a[k] - alpha * qv.a[k];
+                if (own) acc += (double)rv.a[k] * (double)rv.a[k];
+            }
+            xv.store(xc, i); rv.store(rc, i);
         }
-        xv.store(x, i); rv.store(r, i);
-    }
-    for (long long i = _nv * VEC + _t0; i < n; i += _stride) {   // scalar tail (n % VEC elements)
-        x[i] = x[i] + alpha * d[i];
-        const T rr = r[i] - alpha * q[i];
-        r[i] = rr;
-        bool own = true;
-        if (DIST) { const long long e = i % clen; own = !(e < lo_end || (e >= hi_b && e < hi_e)); }
-        if (own) acc += (double)rr * (double)rr;
+        for (long long i = nv * VEC + _t0; i < clen; i += _stride) {   // scalar tail (clen % VEC elements; never a halo row)
+            xc[i] = xc[i] + alpha * dc[i];
+            const T rr = rc[i] - alpha * qc[i];
+            rc[i] = rr;
+            acc += (double)rr * (double)rr;
+        }
     }
     grid_sum_finish(acc, partials, &st->counter[1], [=](double s) {
         if (freeze) return;                      // profiling hook: keep alpha/delta fixed across repeated launches
@@ -284,7 +299,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, 
         st->iter += 1;
         if (s < st->tol2) st->done = 1;
         else if (st->iter >= st->max_iter || !(s == s)) st->done = 2;  // NaN: the reference would spin to max_iter
-    }, (DIST && !freeze) ? peers : nullptr, 1);
+    }, (DIST && !freeze) ? peers : nullptr, 1, false);
 }
 
 // K3:  beta = delta/delta_old ; d = r + beta d      (ViscosityCGSolver3D.py:607-610)
@@ -344,15 +359,19 @@ inline int vec_grid(long long n, int vec) {
 
 template <typename T>
 int cg_launch_update_xr(long long n, T* x, T* r, const T* d, const T* q, CgState* st, double* partials, cudaStream_t s, int freeze = 0,
-                        PeerInfo* peers = nullptr) {
+                        PeerInfo* peers = nullptr, const PeerHot* hotp = nullptr) {
+    PeerHot hot;
+    memset(&hot, 0, sizeof(hot));
+    if (hotp) hot = *hotp;
     constexpr int N = Vec16<T>::N;
     const bool vec = aligned16(x) && aligned16(r) && aligned16(d) && aligned16(q);
     if (peers) {
-        if (vec) cg_update_xr_kernel<T, N, true><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers);
-        else cg_update_xr_kernel<T, 1, true><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers);
+        const long long per = hot.comp_len > 0 ? hot.comp_len : n;
+        if (vec) cg_update_xr_kernel<T, N, true><<<vec_grid(per, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers, hot);
+        else cg_update_xr_kernel<T, 1, true><<<vec_grid(per, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers, hot);
     } else {
-        if (vec) cg_update_xr_kernel<T, N, false><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, nullptr);
-        else cg_update_xr_kernel<T, 1, false><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, nullptr);
+        if (vec) cg_update_xr_kernel<T, N, false><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, nullptr, hot);
+        else cg_update_xr_kernel<T, 1, false><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, nullptr, hot);
     }
     FS_LAUNCH_CHECK();
     return FS_OK;

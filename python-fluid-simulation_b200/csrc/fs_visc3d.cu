@@ -244,7 +244,7 @@ constexpr int kK1BlocksPerSM = 3;
 
 template <typename T, bool DIST>
 __global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
-                                                                                       CgState* st_, double* partials, PeerInfo* peers) {
+                                                                                       CgState* st_, double* partials, PeerInfo* peers, PeerHot hot) {
     if (*(volatile int*)&st_->done) return;
     const Lat3& L = P.L;
     const long long NL = L.NL;
@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_k
     const long long NLw = (NL + 31) & ~31LL;       // whole warps take part in every trip (ballot below)
     const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
     double acc = 0.0;
+    bool wrote_peer = false;
     auto nb = [&](int comp, long long j) -> T { return __ldg(d + comp * NL + j); };
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < NLw; i += stride) {
         const bool in = i < NL;
@@ -272,8 +273,8 @@ __global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_k
             if (aw) { ow = rw; acc += (double)dw * (double)rw; }
         }
         // multi-GPU: the halo planes of q (0 and X-2) are written by the NEIGHBOURS' K1 over NVLink — never by this rank
-        const bool halo_plane = DIST && ((peers->has_lo && i < L.sx) ||
-                                         (peers->has_hi && i >= (long long)(L.X - 2) * L.sx && i < (long long)(L.X - 1) * L.sx));
+        const bool halo_plane = DIST && ((hot.has_lo && i < L.sx) ||
+                                         (hot.has_hi && i >= (long long)(L.X - 2) * L.sx && i < (long long)(L.X - 1) * L.sx));
         if (in && !halo_plane) {
             q[i] = ou;
             q[NL + i] = ov;
@@ -282,22 +283,25 @@ __global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_k
                 // multi-GPU: my first / last owned planes are the neighbours' halo planes of q — store them straight
                 // into the peers' memory over NVLink; the all-reduce in this kernel's tail publishes them.
                 const long long lo0 = L.sx, hi0 = (long long)(L.X - 3) * L.sx;
-                if (peers->has_lo && i >= lo0 && i < lo0 + L.sx) {
+                if (hot.has_lo && i >= lo0 && i < lo0 + L.sx) {
                     const long long o = i - lo0;
-                    reinterpret_cast<T*>(peers->q_lo[0])[o] = ou;
-                    reinterpret_cast<T*>(peers->q_lo[1])[o] = ov;
-                    reinterpret_cast<T*>(peers->q_lo[2])[o] = ow;
+                    reinterpret_cast<T*>(hot.q_lo[0])[o] = ou;
+                    reinterpret_cast<T*>(hot.q_lo[1])[o] = ov;
+                    reinterpret_cast<T*>(hot.q_lo[2])[o] = ow;
+                    wrote_peer = true;
                 }
-                if (peers->has_hi && i >= hi0 && i < hi0 + L.sx) {
+                if (hot.has_hi && i >= hi0 && i < hi0 + L.sx) {
                     const long long o = i - hi0;
-                    reinterpret_cast<T*>(peers->q_hi[0])[o] = ou;
-                    reinterpret_cast<T*>(peers->q_hi[1])[o] = ov;
-                    reinterpret_cast<T*>(peers->q_hi[2])[o] = ow;
+                    reinterpret_cast<T*>(hot.q_hi[0])[o] = ou;
+                    reinterpret_cast<T*>(hot.q_hi[1])[o] = ov;
+                    reinterpret_cast<T*>(hot.q_hi[2])[o] = ow;
+                    wrote_peer = true;
                 }
             }
         }
     }
-    grid_sum_finish(acc, partials, &st_->counter[0], [=](double sum) { st_->dq = sum; }, DIST ? peers : nullptr, 0);
+    const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
+    grid_sum_finish(acc, partials, &st_->counter[0], [=](double sum) { st_->dq = sum; }, DIST ? peers : nullptr, 0, block_wrote_peer);
 }
 
 }  // namespace fs
@@ -325,6 +329,7 @@ struct fs_visc3d {
     fs_comm* comm;   // multi-GPU: this handle is one x-slab (extended by one cell towards each neighbour)
     int has_lo, has_hi;
     IterGraph graph; // captured batch of iterations (single GPU and fused multi-GPU transport)
+    PeerHot hot;     // by-value copy of the per-point fields of `peers`
     PeerInfo* peers; // device copy; non-null = collectives fused into K1/K2 over peer memory (NVLink), else NCCL per iteration
 };
 
@@ -441,6 +446,10 @@ int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int h
     pi.halo_lo_end = h->has_lo ? h->L.sx : 0;
     pi.halo_hi_begin = h->has_hi ? (long long)(h->L.X - 2) * h->L.sx : 0;
     pi.halo_hi_end = h->has_hi ? (long long)(h->L.X - 1) * h->L.sx : 0;
+    h->hot.has_lo = pi.has_lo; h->hot.has_hi = pi.has_hi;
+    for (int c = 0; c < 3; ++c) { h->hot.q_lo[c] = pi.q_lo[c]; h->hot.q_hi[c] = pi.q_hi[c]; }
+    h->hot.comp_len = pi.comp_len; h->hot.halo_lo_end = pi.halo_lo_end;
+    h->hot.halo_hi_begin = pi.halo_hi_begin; h->hot.halo_hi_end = pi.halo_hi_end;
     if (!h->peers) FS_CUDA(cudaMalloc((void**)&h->peers, sizeof(PeerInfo)));
     FS_CUDA(cudaMemcpy(h->peers, &pi, sizeof(pi), cudaMemcpyHostToDevice));
     h->graph.valid = false;
@@ -478,6 +487,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->grid_pts = lay.grid_pts;
     h->packed = false;
     h->comm = nullptr; h->has_lo = 0; h->has_hi = 0; h->peers = nullptr;
+    memset(&h->hot, 0, sizeof(h->hot));
     int s = h->cg.init();
     if (s < 0) { delete h; return s; }
     h->cg.st_dev = h->st; h->cg.partials_dev = h->partials;
@@ -600,16 +610,16 @@ static int visc3d_k1(fs_visc3d* h, double sm, cudaStream_t s) {
     long long want = (h->L.NL + kK1Threads - 1) / kK1Threads;
     const int grid = (int)(want < (long long)kSMs * kK1BlocksPerSM ? want : (long long)kSMs * kK1BlocksPerSM);
     if (h->peers) {
-        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, h->peers));
+        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, h->peers, h->hot));
     } else {
-        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, nullptr));
+        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, nullptr, h->hot));
     }
     FS_LAUNCH_CHECK();
     return FS_OK;
 }
 static int visc3d_k2(fs_visc3d* h, cudaStream_t s, int freeze = 0) {
     const long long n = 3 * h->L.NL;
-    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr<T>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s, freeze, h->peers)));
+    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr<T>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s, freeze, h->peers, h->peers ? &h->hot : nullptr)));
     return FS_OK;
 }
 static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
