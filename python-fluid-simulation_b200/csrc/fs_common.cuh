@@ -100,6 +100,7 @@ struct PeerHot {
     char* q_lo[3];
     char* q_hi[3];
     long long comp_len, halo_lo_end, halo_hi_begin, halo_hi_end;
+    long long hb[6], he[6];   // the same halo rows as [begin,end) intervals of the flat 3-component index (empty if unused)
 };
 
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -257,38 +258,29 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_xr_kernel(long long n, 
     const double alpha_d = st->delta / st->dq;
     const T alpha = (T)alpha_d;
     double acc = 0.0;
-    const long long _stride = (long long)gridDim.x * blockDim.x;
-    const long long _t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // DIST: walk the component arrays one after the other so that "is this a halo row" is three compares on the index
-    // inside the component (a 16-byte chunk never straddles a plane: plane sizes are multiples of 4 elements).
-    const long long clen = DIST ? hot.comp_len : n;
-    const int ncomp = DIST ? (int)(n / clen) : 1;
-    const long long nv = clen / VEC;
-    for (int c = 0; c < ncomp; ++c) {
-        T* xc = x + c * clen; T* rc = r + c * clen;
-        const T* dc = d + c * clen; const T* qc = q + c * clen;
-        for (long long i = _t0; i < nv; i += _stride) {
-            Chunk<T, VEC> xv, rv, dv, qv;
-            xv.load(xc, i); rv.load(rc, i); dv.load(dc, i); qv.load(qc, i);
-            bool own = true;
-            if (DIST) {
-                const long long e = i * VEC;
-                own = !(e < hot.halo_lo_end || (e >= hot.halo_hi_begin && e < hot.halo_hi_end));
-            }
+    FS_STREAM_SETUP(n, VEC)
+    for (long long i = _t0; i < _nv; i += _stride) {
+        Chunk<T, VEC> xv, rv, dv, qv;
+        xv.load(x, i); rv.load(r, i); dv.load(d, i); qv.load(q, i);
+        bool own = true;
+        if (DIST) {                                   // a 16-byte chunk never straddles a plane (plane size % 4 == 0)
+            const long long e = i * VEC;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                xv.a[k] = xv.a[k] + alpha * dv.a[k];
-                rv.a[k] = rv.a[k] - alpha * qv.a[k];
-                if (own) acc += (double)rv.a[k] * (double)rv.a[k];
-            }
-            xv.store(xc, i); rv.store(rc, i);
+            for (int k = 0; k < 6; ++k) own = own && !(e >= hot.hb[k] && e < hot.he[k]);
         }
-        for (long long i = nv * VEC + _t0; i < clen; i += _stride) {   // scalar tail (clen % VEC elements; never a halo row)
-            xc[i] = xc[i] + alpha * dc[i];
-            const T rr = rc[i] - alpha * qc[i];
-            rc[i] = rr;
-            acc += (double)rr * (double)rr;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            xv.a[k] = xv.a[k] + alpha * dv.a[k];
+            rv.a[k] = rv.a[k] - alpha * qv.a[k];
+            if (own) acc += (double)rv.a[k] * (double)rv.a[k];
         }
+        xv.store(x, i); rv.store(r, i);
+    }
+    for (long long i = _nv * VEC + _t0; i < n; i += _stride) {   // scalar tail (n % VEC elements; never a halo row)
+        x[i] = x[i] + alpha * d[i];
+        const T rr = r[i] - alpha * q[i];
+        r[i] = rr;
+        acc += (double)rr * (double)rr;
     }
     grid_sum_finish(acc, partials, &st->counter[1], [=](double s) {
         if (freeze) return;                      // profiling hook: keep alpha/delta fixed across repeated launches
@@ -366,9 +358,8 @@ int cg_launch_update_xr(long long n, T* x, T* r, const T* d, const T* q, CgState
     constexpr int N = Vec16<T>::N;
     const bool vec = aligned16(x) && aligned16(r) && aligned16(d) && aligned16(q);
     if (peers) {
-        const long long per = hot.comp_len > 0 ? hot.comp_len : n;
-        if (vec) cg_update_xr_kernel<T, N, true><<<vec_grid(per, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers, hot);
-        else cg_update_xr_kernel<T, 1, true><<<vec_grid(per, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers, hot);
+        if (vec) cg_update_xr_kernel<T, N, true><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers, hot);
+        else cg_update_xr_kernel<T, 1, true><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, peers, hot);
     } else {
         if (vec) cg_update_xr_kernel<T, N, false><<<vec_grid(n, N), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, nullptr, hot);
         else cg_update_xr_kernel<T, 1, false><<<vec_grid(n, 1), kVecThreads, 0, s>>>(n, x, r, d, q, st, partials, freeze, nullptr, hot);

@@ -450,6 +450,10 @@ int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int h
     for (int c = 0; c < 3; ++c) { h->hot.q_lo[c] = pi.q_lo[c]; h->hot.q_hi[c] = pi.q_hi[c]; }
     h->hot.comp_len = pi.comp_len; h->hot.halo_lo_end = pi.halo_lo_end;
     h->hot.halo_hi_begin = pi.halo_hi_begin; h->hot.halo_hi_end = pi.halo_hi_end;
+    for (int c = 0; c < 3; ++c) {
+        h->hot.hb[2 * c] = c * pi.comp_len;                        h->hot.he[2 * c] = c * pi.comp_len + pi.halo_lo_end;
+        h->hot.hb[2 * c + 1] = c * pi.comp_len + pi.halo_hi_begin; h->hot.he[2 * c + 1] = c * pi.comp_len + pi.halo_hi_end;
+    }
     if (!h->peers) FS_CUDA(cudaMalloc((void**)&h->peers, sizeof(PeerInfo)));
     FS_CUDA(cudaMemcpy(h->peers, &pi, sizeof(pi), cudaMemcpyHostToDevice));
     h->graph.valid = false;
