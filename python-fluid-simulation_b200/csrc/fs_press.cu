@@ -78,41 +78,45 @@ __device__ __forceinline__ double edge_in_fraction(double l, double r) {
 // ---------------------------------------------------------------------------------------------
 // matvecmul_kernel (PressureCGSolver3D.py:52-130 / 2D :46-100), optionally fused with d.q
 // ---------------------------------------------------------------------------------------------
+// Persistent grid (kPressBlocksPerSM CTAs per SM), grid-stride over the cells with the fastest axis across the warp, one
+// deterministic block reduction at the very end (a reduction per 256 cells made the first version barrier-bound).
+constexpr int kPressBlocksPerSM = 6;
+
 template <int D, bool CG>
 __global__ void __launch_bounds__(kPT) press_apply_kernel(Grid<D> g, const double* __restrict__ v, double* __restrict__ out, PressW<D> W,
                                                           const double* __restrict__ lphi, CgState* st, double* partials) {
     if (CG) { if (*(volatile int*)&st->done) return; }
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double acc = 0.0;
-    if (i < g.ncells) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.ncells; i += stride) {
         int c[D];
         decode<D>(g, i, c);
-        if (interior<D>(g, c)) {
-            const double phi = lphi[i];
-            double res = 0.0;
-            if (phi < 0) {
-                double val = 0.0, diag = 0.0;
+        if (!interior<D>(g, c)) continue;
+        const double phi = __ldg(lphi + i);
+        double res = 0.0;
+        if (phi < 0) {
+            double val = 0.0, diag = 0.0;
+            const double vc = __ldg(v + i);
 #pragma unroll
-                for (int a = 0; a < D; ++a) {
+            for (int a = 0; a < D; ++a) {
 #pragma unroll
-                    for (int sgn = 1; sgn >= -1; sgn -= 2) {          // +a then -a
-                        const long long j = i + sgn * g.cs[a];
-                        const double nphi = lphi[j];
-                        const double w = W.w[a][face_idx<D>(g, a, c, sgn > 0 ? 1 : 0)];
-                        if (nphi < 0) {
-                            val = __dsub_rn(val, __dmul_rn(w, v[j]));
-                            diag = __dadd_rn(diag, w);
-                        } else {
-                            const double frac = fmin(1.0, fmax(0.01, phi / __dsub_rn(phi, nphi)));
-                            diag = __dadd_rn(diag, w / frac);
-                        }
+                for (int sgn = 1; sgn >= -1; sgn -= 2) {          // +a then -a
+                    const long long j = i + sgn * g.cs[a];
+                    const double nphi = __ldg(lphi + j);
+                    const double w = __ldg(W.w[a] + face_idx<D>(g, a, c, sgn > 0 ? 1 : 0));
+                    if (nphi < 0) {
+                        val = __dsub_rn(val, __dmul_rn(w, __ldg(v + j)));
+                        diag = __dadd_rn(diag, w);
+                    } else {
+                        const double frac = fmin(1.0, fmax(0.01, phi / __dsub_rn(phi, nphi)));
+                        diag = __dadd_rn(diag, w / frac);
                     }
                 }
-                res = __dadd_rn(val, __dmul_rn(diag, v[i]));
-                if (CG) acc = v[i] * res;
             }
-            out[i] = res;
+            res = __dadd_rn(val, __dmul_rn(diag, vc));
+            if (CG) acc += vc * res;
         }
+        out[i] = res;
     }
     if (CG) grid_sum_finish(acc, partials, &st->counter[0], [=](double s) { st->dq = s; });
 }
@@ -273,14 +277,15 @@ template <typename S, int D> static Vel<D, S> mkV(S* vx, S* vy, S* vz) {
 
 static int press_apply_launch(fs_press* h, const double* v, double* out, const double* wx, const double* wy, const double* wz,
                               const double* lphi, bool cg, cudaStream_t s) {
+    const int pg = h->grid < kSMs * kPressBlocksPerSM ? h->grid : kSMs * kPressBlocksPerSM;
     if (h->nz > 0) {
         auto g = make_grid<3>(h->nx, h->ny, h->nz);
-        if (cg) press_apply_kernel<3, true><<<h->grid, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
-        else press_apply_kernel<3, false><<<h->grid, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
+        if (cg) press_apply_kernel<3, true><<<pg, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
+        else press_apply_kernel<3, false><<<pg, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
     } else {
         auto g = make_grid<2>(h->nx, h->ny, 0);
-        if (cg) press_apply_kernel<2, true><<<h->grid, kPT, 0, s>>>(g, v, out, mkW<2>(wx, wy, nullptr), lphi, h->st, h->partials);
-        else press_apply_kernel<2, false><<<h->grid, kPT, 0, s>>>(g, v, out, mkW<2>(wx, wy, nullptr), lphi, h->st, h->partials);
+        if (cg) press_apply_kernel<2, true><<<pg, kPT, 0, s>>>(g, v, out, mkW<2>(wx, wy, nullptr), lphi, h->st, h->partials);
+        else press_apply_kernel<2, false><<<pg, kPT, 0, s>>>(g, v, out, mkW<2>(wx, wy, nullptr), lphi, h->st, h->partials);
     }
     FS_LAUNCH_CHECK();
     return FS_OK;

@@ -131,30 +131,34 @@ __global__ void __launch_bounds__(kT2) visc2d_general_kernel(Visc2Dev<T> P, T s,
     row(std::integral_constant<int, 1>{});
 }
 
+// Persistent grid-stride version (same reasoning as the 3-D K1): one block reduction at the end instead of one per 256 points.
+constexpr int kV2BlocksPerSM = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(kT2) visc2d_apply_dot_kernel(Visc2Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
                                                                CgState* st_, double* partials) {
     if (*(volatile int*)&st_->done) return;
     const Lat2& L = P.L;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long NL = L.NL;
     const long long st[2] = {L.Yp, 1};
     double acc = 0.0;
-    if (i < NL) {
-        auto nb = [&](int comp, long long j) -> T { return __ldg(d + comp * NL + j); };
-        auto row = [&](auto Atag) {
-            constexpr int A = decltype(Atag)::value;
-            const T center = __ldg(P.coef[A] + i);
-            T out = T(0);
-            if (center == center) {
-                const T own = __ldg(d + A * NL + i);
-                out = visc_row<T, 2, A, false, ROW_APPLY>(P.coef, i, st, center, own, s, s2, nb);
-                acc += (double)own * (double)out;
-            }
-            q[A * NL + i] = out;
-        };
-        row(std::integral_constant<int, 0>{});
-        row(std::integral_constant<int, 1>{});
+    auto nb = [&](int comp, long long j) -> T { return __ldg(d + comp * NL + j); };
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < NL; i += stride) {
+        const T cu = __ldg(P.coef[0] + i), cv = __ldg(P.coef[1] + i);
+        T ou = T(0), ov = T(0);
+        if (cu == cu) {          // computed rows are interior, so every neighbour index is inside the lattice
+            const T own = __ldg(d + i);
+            ou = visc_row<T, 2, 0, false, ROW_APPLY>(P.coef, i, st, cu, own, s, s2, nb);
+            acc += (double)own * (double)ou;
+        }
+        if (cv == cv) {
+            const T own = __ldg(d + NL + i);
+            ov = visc_row<T, 2, 1, false, ROW_APPLY>(P.coef, i, st, cv, own, s, s2, nb);
+            acc += (double)own * (double)ov;
+        }
+        q[i] = ou;
+        q[NL + i] = ov;
     }
     grid_sum_finish(acc, partials, &st_->counter[0], [=](double sum) { st_->dq = sum; });
 }
@@ -233,7 +237,8 @@ static int v2_general(fs_visc2d* h, double scale, double mu, int src, int dst, i
 
 static int v2_iteration(fs_visc2d* h, double sm, cudaStream_t s) {
     const long long n = 2 * h->L.NL;
-    FS_DISPATCH2(h, visc2d_apply_dot_kernel<T><<<h->grid_pts, kT2, 0, s>>>(dev_view2<T>(h), (T)sm, (T)(2 * sm), vec2<T>(h, FS_VEC_D), vec2<T>(h, FS_VEC_Q), h->st, h->partials));
+    const int grid = h->grid_pts < kSMs * kV2BlocksPerSM ? h->grid_pts : kSMs * kV2BlocksPerSM;
+    FS_DISPATCH2(h, visc2d_apply_dot_kernel<T><<<grid, kT2, 0, s>>>(dev_view2<T>(h), (T)sm, (T)(2 * sm), vec2<T>(h, FS_VEC_D), vec2<T>(h, FS_VEC_Q), h->st, h->partials));
     FS_LAUNCH_CHECK();
     FS_DISPATCH2(h, FS_TRY(cg_launch_update_xr<T>(n, vec2<T>(h, FS_VEC_X), vec2<T>(h, FS_VEC_R), vec2<T>(h, FS_VEC_D), vec2<T>(h, FS_VEC_Q), h->st, h->partials, s)));
     FS_DISPATCH2(h, FS_TRY(cg_launch_update_d<T>(n, vec2<T>(h, FS_VEC_D), vec2<T>(h, FS_VEC_R), h->st, s)));
