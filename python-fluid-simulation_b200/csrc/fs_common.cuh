@@ -302,7 +302,15 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_d_kernel(long long n, T
     const T beta = (T)beta_d;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->beta = beta_d;
     FS_STREAM_SETUP(n, VEC)
-    for (long long i = _t0; i < _nv; i += _stride) {
+    long long i = _t0;
+    for (; i + _stride < _nv; i += 2 * _stride) {     // two chunks per trip: four 16-byte loads in flight per thread
+        Chunk<T, VEC> d0, r0, d1, r1;
+        d0.load(d, i); r0.load(r, i); d1.load(d, i + _stride); r1.load(r, i + _stride);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { d0.a[k] = r0.a[k] + beta * d0.a[k]; d1.a[k] = r1.a[k] + beta * d1.a[k]; }
+        d0.store(d, i); d1.store(d, i + _stride);
+    }
+    for (; i < _nv; i += _stride) {
         Chunk<T, VEC> dv, rv;
         dv.load(d, i); rv.load(r, i);
 #pragma unroll

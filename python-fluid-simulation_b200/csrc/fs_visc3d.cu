@@ -32,6 +32,7 @@ template <typename T> struct Visc3Dev {
     Lat3 L;
     const T* coef[7];
     const uint8_t* mask[3];
+    const uint8_t* act;      // per lattice point: bit c set <=> row c is computed (same information as the NaN tags, 1 byte)
 };
 
 __device__ __forceinline__ void lat_decode(const Lat3& L, long long i, int& x, int& y, int& z) {
@@ -55,7 +56,8 @@ constexpr int kThreads = 256;
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const double* __restrict__ sphi, const double* __restrict__ lvol,
-                                                               double vol_norm, T* __restrict__ coef /*[7][NL]*/, uint8_t* __restrict__ mask /*[3][NL]*/) {
+                                                               double vol_norm, T* __restrict__ coef /*[7][NL]*/, uint8_t* __restrict__ mask /*[3][NL]*/,
+                                                               uint8_t* __restrict__ act /*[NL + 32]*/) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.NL) return;
     int x, y, z;
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
     const bool ix = x < L.nx, iy = y < L.ny, iz = z < L.nz, inz = z <= L.nz;
     const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
     auto vol = [&](long long off) { return (T)(lvol[f0 + off] / vol_norm); };
+    unsigned int abits = 0;
     // faces: fine parities (0,1,1) (1,0,1) (1,1,0)
     {
         const bool in = iy && iz;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
         if (in) {
             fluid = sphi[f0 + fy + fz] >= 0.0;
             const bool interior = x >= 1 && x <= L.u_xhi && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
-            if (fluid && interior) v = vol(fy + fz);
+            if (fluid && interior) { v = vol(fy + fz); if (v == v) abits |= 1u; }
         }
         coef[0 * L.NL + i] = v;
         mask[0 * L.NL + i] = fluid;
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
         if (in) {
             fluid = sphi[f0 + fx + fz] >= 0.0;
             const bool interior = x >= 1 && x <= L.nx - 2 && y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2;
-            if (fluid && interior) v = vol(fx + fz);
+            if (fluid && interior) { v = vol(fx + fz); if (v == v) abits |= 2u; }
         }
         coef[1 * L.NL + i] = v;
         mask[1 * L.NL + i] = fluid;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
         if (in) {
             fluid = sphi[f0 + fx + fy] >= 0.0;
             const bool interior = x >= 1 && x <= L.nx - 2 && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1;
-            if (fluid && interior) v = vol(fx + fy);
+            if (fluid && interior) { v = vol(fx + fy); if (v == v) abits |= 4u; }
         }
         coef[2 * L.NL + i] = v;
         mask[2 * L.NL + i] = fluid;
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
     coef[4 * L.NL + i] = (iz) ? vol(fz) : T(0);                         // Exy: (0,0,1)
     coef[5 * L.NL + i] = (iy && inz) ? vol(fy) : T(0);                  // Exz: (0,1,0)
     coef[6 * L.NL + i] = (ix && inz) ? vol(fx) : T(0);                  // Eyz: (1,0,0)
+    act[i] = (uint8_t)abits;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -255,15 +259,22 @@ __global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_k
     double acc = 0.0;
     bool wrote_peer = false;
     auto nb = [&](int comp, long long j) -> T { return __ldg(d + comp * NL + j); };
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < NLw; i += stride) {
+    // The activity byte of the NEXT trip is requested before this trip's work: in solid regions a trip is a single 1-byte
+    // load, and without the prefetch each warp would have one memory round trip in flight.
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int a_n = i < NL ? __ldg(P.act + i) : 0u;
+    for (; i < NLw; i += stride) {
         const bool in = i < NL;
-        const T cu = in ? __ldg(P.coef[0] + i) : nan;
-        const T cv = in ? __ldg(P.coef[1] + i) : nan;
-        const T cw = in ? __ldg(P.coef[2] + i) : nan;
-        const bool au = cu == cu, av = cv == cv, aw = cw == cw;
+        const unsigned int a = a_n;
+        {
+            const long long i2 = i + stride;
+            a_n = i2 < NL ? __ldg(P.act + i2) : 0u;
+        }
+        const bool au = a & 1u, av = a & 2u, aw = a & 4u;
         T ou = T(0), ov = T(0), ow = T(0);
-        if (__any_sync(0xffffffffu, au || av || aw)) {
+        if (__any_sync(0xffffffffu, a != 0u)) {
             const long long j = in ? i : (NL - 1);
+            const T cu = __ldg(P.coef[0] + j), cv = __ldg(P.coef[1] + j), cw = __ldg(P.coef[2] + j);
             const T du = nb(0, j), dv = nb(1, j), dw = nb(2, j);
             const T ru = visc_row<T, 3, 0, false, ROW_APPLY>(P.coef, j, st, cu, du, s, s2, nb);
             const T rv = visc_row<T, 3, 1, false, ROW_APPLY>(P.coef, j, st, cv, dv, s, s2, nb);
@@ -275,26 +286,29 @@ __global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_k
         // multi-GPU: the halo planes of q (0 and X-2) are written by the NEIGHBOURS' K1 over NVLink — never by this rank
         const bool halo_plane = DIST && ((hot.has_lo && i < L.sx) ||
                                          (hot.has_hi && i >= (long long)(L.X - 2) * L.sx && i < (long long)(L.X - 1) * L.sx));
-        if (in && !halo_plane) {
-            q[i] = ou;
-            q[NL + i] = ov;
-            q[2 * NL + i] = ow;
+        // Rows that are not computed hold q == 0 since the masked apply at the start of the solve (which writes 0 on every
+        // interior non-fluid row) and are never written afterwards, so only computed rows are stored — in solid regions
+        // K1 therefore moves one byte per lattice point.
+        if (in && !halo_plane && a != 0u) {
+            if (au) q[i] = ou;
+            if (av) q[NL + i] = ov;
+            if (aw) q[2 * NL + i] = ow;
             if (DIST) {
                 // multi-GPU: my first / last owned planes are the neighbours' halo planes of q — store them straight
                 // into the peers' memory over NVLink; the all-reduce in this kernel's tail publishes them.
                 const long long lo0 = L.sx, hi0 = (long long)(L.X - 3) * L.sx;
                 if (hot.has_lo && i >= lo0 && i < lo0 + L.sx) {
                     const long long o = i - lo0;
-                    reinterpret_cast<T*>(hot.q_lo[0])[o] = ou;
-                    reinterpret_cast<T*>(hot.q_lo[1])[o] = ov;
-                    reinterpret_cast<T*>(hot.q_lo[2])[o] = ow;
+                    if (au) reinterpret_cast<T*>(hot.q_lo[0])[o] = ou;
+                    if (av) reinterpret_cast<T*>(hot.q_lo[1])[o] = ov;
+                    if (aw) reinterpret_cast<T*>(hot.q_lo[2])[o] = ow;
                     wrote_peer = true;
                 }
                 if (hot.has_hi && i >= hi0 && i < hi0 + L.sx) {
                     const long long o = i - hi0;
-                    reinterpret_cast<T*>(hot.q_hi[0])[o] = ou;
-                    reinterpret_cast<T*>(hot.q_hi[1])[o] = ov;
-                    reinterpret_cast<T*>(hot.q_hi[2])[o] = ow;
+                    if (au) reinterpret_cast<T*>(hot.q_hi[0])[o] = ou;
+                    if (av) reinterpret_cast<T*>(hot.q_hi[1])[o] = ov;
+                    if (aw) reinterpret_cast<T*>(hot.q_hi[2])[o] = ow;
                     wrote_peer = true;
                 }
             }
@@ -321,6 +335,7 @@ struct fs_visc3d {
     char* vecs;      // [5][3][NL] T
     uint8_t* mask;   // [3][NL]
     uint8_t* valid;  // [2][3][NL]
+    uint8_t* act;    // [NL] computed-row bits
     double* partials;
     CgState* st;
     CgHost cg;
@@ -342,7 +357,7 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     return L;
 }
 
-struct Visc3Layout { size_t coef, vecs, mask, valid, partials, st, total; int grid_pts; };
+struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, total; int grid_pts; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -357,6 +372,7 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     o.vecs = p; p = align_up(p + 15 * L.NL * esz, 256) + guard;
     o.mask = p; p = align_up(p + 3 * L.NL, 256);
     o.valid = p; p = align_up(p + 6 * L.NL, 256);
+    o.act = p; p = align_up(p + L.NL + 64, 256);
     size_t np = (size_t)(o.grid_pts > kVecGrid ? o.grid_pts : kVecGrid);
     o.partials = p; p = align_up(p + np * sizeof(double), 256);
     o.st = p; p = align_up(p + sizeof(CgState), 256);
@@ -369,6 +385,7 @@ template <typename T> static Visc3Dev<T> dev_view(const fs_visc3d* h) {
     P.L = h->L;
     for (int k = 0; k < 7; ++k) P.coef[k] = reinterpret_cast<const T*>(h->coef) + k * h->L.NL;
     for (int k = 0; k < 3; ++k) P.mask[k] = h->mask + k * h->L.NL;
+    P.act = h->act;
     return P;
 }
 
@@ -486,7 +503,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     if (ws_bytes < lay.total) { delete h; return fail(FS_ERR_ARG, "fs_visc3d_create: workspace too small"); }
     h->ws = (char*)ws; h->ws_bytes = ws_bytes;
     h->coef = h->ws + lay.coef; h->vecs = h->ws + lay.vecs;
-    h->mask = (uint8_t*)(h->ws + lay.mask); h->valid = (uint8_t*)(h->ws + lay.valid);
+    h->mask = (uint8_t*)(h->ws + lay.mask); h->valid = (uint8_t*)(h->ws + lay.valid); h->act = (uint8_t*)(h->ws + lay.act);
     h->partials = (double*)(h->ws + lay.partials); h->st = (CgState*)(h->ws + lay.st);
     h->grid_pts = lay.grid_pts;
     h->packed = false;
@@ -526,7 +543,7 @@ void* fs_visc3d_vector_ptr(const fs_visc3d* h, int vec, int comp) {
 int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double vol_norm, void* stream) {
     if (!h || !sphi || !lvol) return fail(FS_ERR_ARG, "fs_visc3d_pack: null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask));
+    FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act));
     FS_LAUNCH_CHECK();
     h->packed = true;
     return FS_OK;
