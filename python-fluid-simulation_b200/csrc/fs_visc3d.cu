@@ -244,10 +244,14 @@ __global__ void __launch_bounds__(kThreads) visc3d_general_kernel(Visc3Dev<T> P,
 // One block reduction at the very end (fixed-order, deterministic).
 // ---------------------------------------------------------------------------------------------
 constexpr int kK1Threads = 256;
-constexpr int kK1BlocksPerSM = 3;
+// CTAs per SM: the fp64 body keeps 43 loaded values (86 registers) in flight, so it gets 128 registers per thread
+// (2 CTAs/SM); with an 80-register cap (3 CTAs/SM) ptxas split the loads into dependent phases and the dense-scene
+// K1 ran at 0.556 ms instead of 0.357 ms.  fp32 needs half the registers.
+template <typename T> struct K1Occ { static constexpr int value = 2; };
+template <> struct K1Occ<float> { static constexpr int value = 3; };
 
 template <typename T, bool DIST>
-__global__ void __launch_bounds__(kK1Threads, kK1BlocksPerSM) visc3d_apply_dot_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
+__global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
                                                                                        CgState* st_, double* partials, PeerInfo* peers, PeerHot hot) {
     if (*(volatile int*)&st_->done) return;
     const Lat3& L = P.L;
@@ -629,7 +633,8 @@ int fs_visc3d_apply(fs_visc3d* h, double scale, double mu, int src_vec, int dst_
 
 static int visc3d_k1(fs_visc3d* h, double sm, cudaStream_t s) {
     long long want = (h->L.NL + kK1Threads - 1) / kK1Threads;
-    const int grid = (int)(want < (long long)kSMs * kK1BlocksPerSM ? want : (long long)kSMs * kK1BlocksPerSM);
+    const long long cap = (long long)kSMs * (h->dtype == FS_F32 ? K1Occ<float>::value : K1Occ<double>::value);
+    const int grid = (int)(want < cap ? want : cap);
     if (h->peers) {
         FS_DISPATCH(h, visc3d_apply_dot_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, h->peers, h->hot));
     } else {

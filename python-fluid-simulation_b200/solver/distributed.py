@@ -43,10 +43,11 @@ def balanced_starts(cost, world, min_cells=2):
     return starts
 
 
-def plane_cost_from_sphi(sphi, gres, fluid_weight=0.4):
+def plane_cost_from_sphi(sphi, gres, fluid_weight=1.0):
     """Relative cost of each x-plane of cells for the viscosity iteration: K2/K3 stream every row alike, K1 skips solid
     rows, so a plane costs 1 + fluid_weight * (fraction of its cell centres inside the fluid region sphi >= 0).
-    fluid_weight was fitted on B200 (fluid planes cost ~1.4x solid ones at 256^3 fp64)."""
+    fluid_weight was fitted on B200 at 256^3 fp64: a fully fluid plane costs ~2x a solid one (K1 ~1 us per 40 %-fluid plane on
+    top of ~2.3 us of K2+K3 per plane)."""
     g = tuple(int(n) for n in gres)
     centres = sphi[1::2, 1::2, 1::2][: g[0], : g[1], : g[2]]
     frac = (centres >= 0).to(torch.float64).mean(dim=(1, 2)).cpu().numpy()
