@@ -690,3 +690,184 @@ class PressureCGSolver2D(_PressureCGSolver):
     def solve(self, vx, vy, sphi, sv, lphi, wx=None, wy=None, tol=1e-3):
         ws = None if (wx is None or wy is None) else (wx, wy)
         self._solve((vx, vy), sphi, sv, lphi, ws, tol)
+
+
+# --------------------------------------------------------------------------------------
+# Density (volume-conservation) solver — DensityCGSolver3D.py:8-350   (§8 "next" row f-1)
+# --------------------------------------------------------------------------------------
+
+
+def _trilinear(px, bound_min, cell_size, bias, shape):
+    """Indices and weights of the 8 grid points around each particle (DensityCGSolver3D.py:14-34 / :218-238).
+
+    gi = floor((x - bound_min)/cell - bias); w = |gx - x|/cell with gx = (gi + bias)*cell + bound_min;
+    corner (ix,iy,iz): index clamped to [0, shape-1], weight prod_d (i_d + (-1)^i_d (1 - w_d)).
+    """
+    px = np.asarray(px, dtype=F64)
+    bm = np.asarray(bound_min, dtype=F64)
+    cs = np.asarray(cell_size, dtype=F64)
+    bias = np.asarray(bias, dtype=F64)
+    gi = np.floor((px - bm) / cs - bias).astype(np.int64)
+    gx = (gi + bias) * cs + bm
+    w = np.abs(gx - px) / cs
+    out = []
+    for ix in (0, 1):
+        for iy in (0, 1):
+            for iz in (0, 1):
+                off = (ix, iy, iz)
+                idx = tuple(np.clip(gi[:, d] + off[d], 0, shape[d] - 1) for d in range(3))
+                ww = [off[d] + ((-1) ** off[d]) * (1 - w[:, d]) for d in range(3)]
+                out.append((idx, ww[0] * ww[1] * ww[2]))
+    return out
+
+
+def density_initialize_density(bound_min, cell_size, gres, px, pm, pvol, gm, gvol):
+    """Particle -> cell scatter of mass and volume (:8-36).  Accumulation order is particle-major as in a sequential run."""
+    g = tuple(int(n) for n in gres)
+    for idx, weight in _trilinear(px, bound_min, cell_size, (0.5, 0.5, 0.5), g):
+        np.add.at(gm, idx, weight * np.asarray(pm, dtype=F64))
+        np.add.at(gvol, idx, weight * float(pvol))
+
+
+def density_fix_volume(cell_size, gres, lvol, gvol, sphi, lphi, ws):
+    """:38-92 — interior cells: full cells deep inside the liquid and away from solids count as cvol; cap by the open fraction."""
+    g = tuple(int(n) for n in gres)
+    if min(g) < 3:
+        return
+    cs = np.asarray(cell_size, dtype=F64)
+    cvol = float(np.prod(cs))
+    dx = float(np.min(cs))
+    I = _interior(g)
+    fluid_vol = gvol[I].copy()
+    near_solid = _fine(sphi, (1, 1, 1), g) < dx
+    inside = lphi[I] < 0
+    for a in range(3):
+        for sgn in (1, -1):
+            off = tuple(sgn if k == a else 0 for k in range(3))
+            inside = inside & (_coarse(lphi, off, g) < 0)
+    fluid_vol = np.where(inside & ~near_solid, cvol, fluid_vol)
+    frac = _density_open_fraction(g, ws)
+    gvol[I] = np.minimum(fluid_vol, cvol * frac)
+
+
+def _density_open_fraction(g, ws):
+    zero = (0, 0, 0)
+    s = _coarse(ws[0], zero, g) + _coarse(ws[0], (1, 0, 0), g)
+    s = s + _coarse(ws[1], zero, g)
+    s = s + _coarse(ws[1], (0, 1, 0), g)
+    s = s + _coarse(ws[2], zero, g)
+    s = s + _coarse(ws[2], (0, 0, 1), g)
+    return s / 6
+
+
+def density_initialize_solver(rho0, dt, gres, cell_size, gm, gvol, lphi, ws, b):
+    """:94-125 — b = (1 - clamp(density/rho0, 0.5, 1.5)) / dt on interior fluid cells."""
+    g = tuple(int(n) for n in gres)
+    if min(g) < 3:
+        return
+    cvol = float(np.prod(np.asarray(cell_size, dtype=F64)))
+    I = _interior(g)
+    frac = _density_open_fraction(g, ws)
+    solid_vol = (1 - frac) * cvol
+    solid_mass = rho0 * solid_vol
+    cell_mass = gm[I] + solid_mass
+    cell_vol = gvol[I] + solid_vol
+    dens = cell_mass / np.maximum(cell_vol, 1e-10) / rho0
+    dens = np.where(cell_mass < 1e-10, 1.0, dens)
+    dens = np.maximum(0.5, np.minimum(1.5, dens))
+    b[I] = np.where(lphi[I] < 0, (1 - dens) / dt, 0.0)
+
+
+def density_matvecmul(gres, v, out, ws, lphi):
+    """:127-204 — like the pressure apply but with UNIT diagonal weights, and the -z off-diagonal term reads
+    wz[x,y,z+1] (not wz[x,y,z]) exactly as the reference does (:196)."""
+    g = tuple(int(n) for n in gres)
+    if min(g) < 3:
+        return
+    zero = (0, 0, 0)
+    phi = lphi[_interior(g)]
+    val = np.zeros(phi.shape, dtype=F64)
+    diag = np.zeros(phi.shape, dtype=F64)
+    for a in range(3):
+        e = _unit(3, a)
+        for sgn in (+1, -1):
+            noff = tuple(sgn * ee for ee in e)
+            nphi = _coarse(lphi, noff, g)
+            woff = e if (sgn > 0 or a == 2) else zero
+            w = _coarse(ws[a], woff, g)
+            nfluid = nphi < 0
+            val = val - np.where(nfluid, w * _coarse(v, noff, g), 0.0)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                frac = np.minimum(1.0, np.maximum(0.01, phi / (phi - nphi)))
+                diag = diag + np.where(nfluid, 1.0, 1.0 / frac)
+    val = val + diag * v[_interior(g)]
+    out[_interior(g)] = np.where(phi < 0, val, 0.0)
+
+
+def density_compute_displacement(gres, dt, cell_size, disp, pv, lphi):
+    """:206-219 — indices 1..g-1 on all axes; note: NOT restricted to faces next to liquid."""
+    g = tuple(int(n) for n in gres)
+    cs = np.asarray(cell_size, dtype=F64)
+    sl = tuple(slice(1, n) for n in g)
+    for a in range(3):
+        slm = tuple(slice(1 - (1 if k == a else 0), n - (1 if k == a else 0)) for k, n in enumerate(g))
+        theta = np.minimum(1.0, np.maximum(0.01, edge_in_fraction(lphi[sl], lphi[slm])))
+        disp[a][sl] = (pv[sl] - pv[slm]) * dt * cs[a] / theta
+
+
+def density_apply_displacement(px, d_arr, bound_min, cell_size, grid_bias, axis):
+    """:221-248 — trilinear gather of one displacement component onto the particles (in place on px[:, axis])."""
+    for idx, weight in _trilinear(px.copy(), bound_min, cell_size, grid_bias, d_arr.shape):
+        px[:, axis] += weight * d_arr[idx]
+
+
+class DensityCGSolver3D:
+    """DensityCGSolver3D.py:283-350."""
+
+    def __init__(self, buf, gres, bound_min, bound_size):
+        self.gres = np.asarray(gres, dtype=np.int64)
+        self.bound_min = np.asarray(bound_min, dtype=F64)
+        self.cell_size = np.asarray(bound_size, dtype=F64) / self.gres
+        g = tuple(int(n) for n in self.gres)
+        self.buf = buf
+        self.m = np.zeros(g, dtype=F64)
+        self.vol = np.zeros(g, dtype=F64)
+        self.x = np.zeros(g, dtype=F64)
+        self.ws = [np.zeros(tuple(n + (1 if i == a else 0) for i, n in enumerate(g)), dtype=F64) for a in range(3)]
+        self.disp = [np.zeros(w.shape, dtype=F64) for w in self.ws]
+        self.alpha = self.beta = self.delta = 0.0
+        self.max_iter = int(np.prod(self.gres))
+        self.trace = CGTrace()
+
+    wx = property(lambda self: self.ws[0])
+    wy = property(lambda self: self.ws[1])
+    wz = property(lambda self: self.ws[2])
+    dx = property(lambda self: self.disp[0])
+    dy = property(lambda self: self.disp[1])
+    dz = property(lambda self: self.disp[2])
+
+    def solve(self, rho0, dt, px, pm, pvol, vx, vy, vz, sphi, sv, lphi, lvol, wx=None, wy=None, wz=None, tol=1e-3):
+        if wx is None or wy is None or wz is None:
+            solidfrac3d(self.gres, sphi, *self.ws)
+            ws = self.ws
+        else:
+            ws = (wx, wy, wz)
+        self.m *= 0
+        self.vol *= 0
+        self.x *= 0
+        density_initialize_density(self.bound_min, self.cell_size, self.gres, px, pm, pvol, self.m, self.vol)
+        density_fix_volume(self.cell_size, self.gres, lvol, self.vol, sphi, lphi, ws)
+        density_initialize_solver(rho0, dt, self.gres, self.cell_size, self.m, self.vol, lphi, ws, self.buf.b)
+
+        def A(vs, qs):
+            density_matvecmul(self.gres, vs[0], qs[0], ws, lphi)
+
+        self.trace = CGTrace()
+        self.delta, self.alpha, self.beta, _, (ds, rs, qs) = _cg(A, [self.x], [self.buf.b], tol, self.max_iter, trace=self.trace)
+        self.buf.d[...] = ds[0]
+        self.buf.r[...] = rs[0]
+        self.buf.q[...] = qs[0]
+        density_compute_displacement(self.gres, dt, self.cell_size, self.disp, self.x, lphi)
+        bias = ((0, 0.5, 0.5), (0.5, 0, 0.5), (0.5, 0.5, 0))
+        for a in range(3):
+            density_apply_displacement(px, self.disp[a], self.bound_min, self.cell_size, bias[a], a)

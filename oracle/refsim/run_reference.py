@@ -315,7 +315,76 @@ def case_press2d_solve():
           b=buf.b, iterations=iters, delta=s.delta)
 
 
+def _density_inputs(g, dx, seed, n_per_cell=2):
+    """particles jittered inside the liquid of small_scene + the grid fields the density solve needs"""
+    sphi, lvol, lphi, vel = small_scene(g, dx, seed)
+    rng = np.random.default_rng(seed + 1000)
+    cells = np.argwhere(lphi < 0.5 * dx)
+    reps = np.repeat(cells, n_per_cell, axis=0)
+    px = (reps + rng.random(reps.shape)) * dx
+    px = np.clip(px, 0.02 * dx, (np.array(g) - 0.02) * dx)
+    pm = np.full(px.shape[0], 1000.0 * (dx / 2) ** 3) * (1 + 0.1 * rng.standard_normal(px.shape[0]))
+    pvol = (dx / 2) ** 3
+    return sphi, lvol, lphi, vel, px, pm, pvol
+
+
+def case_density3d_kernels():
+    from solver import DensityCGSolver3D as Dn
+    from solver.SolidFraction3D import compute_solid_frac
+    g = (7, 8, 6)
+    dx = 0.05
+    sphi, lvol, lphi, vel, px, pm, pvol = _density_inputs(g, dx, 61)
+    gres = cp.array(g, dtype=cp.int64)
+    bound_min = cp.array([0.0, 0.0, 0.0])
+    cell = cp.array([dx, dx, dx])
+    ws = [cp.zeros(s) for s in _mac_shapes(g)]
+    compute_solid_frac(gres, _c(sphi), *ws)
+    gm, gvol = cp.zeros(g), cp.zeros(g)
+    Dn.initialize_density(bound_min, cell, gres, _c(px), _c(pm), pvol, gm, gvol, _c(sphi), _c(lphi))
+    gvol_fixed = _c(gvol)
+    Dn.fix_volume(cell, gres, _c(lvol), gvol_fixed, _c(sphi), _c(lphi), *ws)
+    b = cp.asarray(np.full(g, np.nan))
+    Dn.initialize_solver(1000.0, 1.0 / 300, gres, cell, gm, gvol_fixed, _c(lphi), *ws, b)
+    rng = np.random.default_rng(62)
+    pv = rng.standard_normal(g)
+    q = cp.asarray(np.full(g, np.nan))
+    Dn.matvecmul(gres, _c(pv), q, *ws, _c(lphi))
+    disp = [cp.asarray(np.full(s, np.nan)) for s in _mac_shapes(g)]
+    Dn.compute_displacement(gres, 1.0 / 300, cell, *disp, _c(pv), _c(lphi))
+    dfield = [rng.standard_normal(s) * 1e-3 for s in _mac_shapes(g)]
+    pmoved = _c(px)
+    bias = ([0, 0.5, 0.5], [0.5, 0, 0.5], [0.5, 0.5, 0])
+    for a in range(3):
+        Dn.apply_displacement(pmoved, _c(dfield[a]), bound_min, cell, cp.array(bias[a], dtype=cp.float64), a)
+    _save("density3d_kernels_7x8x6", gres=np.array(g), dx=dx, sphi=sphi, lvol=lvol, lphi=lphi, px=px, pm=pm, pvol=pvol,
+          wx=ws[0], wy=ws[1], wz=ws[2], gm=gm, gvol=gvol, gvol_fixed=gvol_fixed, b=b, pv=pv, q=q,
+          dispx=disp[0], dispy=disp[1], dispz=disp[2], dfx=dfield[0], dfy=dfield[1], dfz=dfield[2], pmoved=pmoved)
+
+
+def case_density3d_solve():
+    from solver import DensityCGSolver3D as Dn
+    from solver.CGSolverBuffer import CGSolverBuffer
+    g = (8, 10, 8)
+    dx = 0.0125
+    sphi, lvol, lphi, vel, px, pm, pvol = _density_inputs(g, dx, 63)
+    gres = cp.array(g, dtype=cp.int64)
+    buf = CGSolverBuffer(gres)
+    s = Dn.DensityCGSolver3D(buf, gres, cp.array([0.0, 0.0, 0.0]), cp.array([n * dx for n in g], dtype=cp.float32))
+    pout = _c(px)
+    box, restore = _count_calls(Dn, "matvecmul")
+    t = time.time()
+    s.solve(1000.0, 1.0 / 300, pout, _c(pm), pvol, *[_c(v) for v in vel], _c(sphi), None, _c(lphi), _c(lvol), tol=1e-3)
+    restore()
+    iters = box["n"] - 1
+    print(f"  density3d solve: {iters} iterations, delta={s.delta:.3e}, {time.time()-t:.0f}s")
+    _save("density3d_solve_8x10x8", gres=np.array(g), dx=dx, bound_size=np.asarray([n * dx for n in g], dtype=np.float32), sphi=sphi, lvol=lvol,
+          lphi=lphi, px=px, pm=pm, pvol=pvol, px_new=pout, x=s.x, wx=s.wx, wy=s.wy, wz=s.wz, m=s.m, vol=s.vol, b=buf.b,
+          dispx=s.dx, dispy=s.dy, dispz=s.dz, iterations=iters, delta=s.delta, tol=1e-3)
+
+
 CASES = {
+    "density3d_kernels": case_density3d_kernels,
+    "density3d_solve": case_density3d_solve,
     "visc3d_kernels": case_visc3d_kernels,
     "solidfrac3d": case_solidfrac3d,
     "solidfrac2d": case_solidfrac2d,
