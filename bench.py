@@ -182,7 +182,7 @@ def run_native(args):
     lib = N.load()
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
     sc = scenes.buckling(n, device="cuda", mu=args.mu) if args.scene == "buckling" else scenes.viscous_column((n, n, n), device="cuda", mu=args.mu)
-    solver = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], dtype=tdtype)
+    solver = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], dtype=tdtype, active_set=args.active_set, cg_mode=args.cg_mode)
     solver.max_iter = args.iters
     dev_in = [sc[k] for k in ("vx", "vy", "vz")]
 
@@ -240,7 +240,13 @@ def run_native(args):
     scale = sc["dt"] / solver.cell_vol / sc["rho"]
     stream = torch.cuda.current_stream().cuda_stream
     kern = {}
-    kbytes = {"K1 visc3d_apply_dot": (2 * F + V7) * esz, "K2 cg_update_xr": 6 * F * esz, "K3 cg_update_d": 3 * F * esz}
+    # bytes per launch: the kernels walk the active 32-point lattice segments only, so the unit is the lattice
+    # point of an active segment: K1 reads d (3) + coefficients (7) and writes q (3) = 13 words + 1 activity byte;
+    # K2 reads x,d,r,q and writes x,r = 18 words; K3 reads r,d and writes d = 9 words (3 components per point)
+    segs, segs_total, rows = solver.active_info()
+    pts = segs * 32
+    kbytes = {"K1 visc3d_apply_dot": pts * (13 * esz + 1), "K2 cg_update_xr": pts * 18 * esz, "K3 cg_update_d": pts * 9 * esz}
+    working_set = pts * (22 * esz + 1)
     reps = 30
     for which, name in ((1, "K1 visc3d_apply_dot"), (2, "K2 cg_update_xr"), (3, "K3 cg_update_d")):
         N.check(lib.fs_visc3d_kernel_enqueue(solver._e.h, which, scale, args.mu, 3, stream), "warm")
@@ -256,8 +262,15 @@ def run_native(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
                 "per_kernel_ms": kern, "per_kernel_GBps": {k: kbytes[k] / (kern[k] * 1e-3) / 1e9 for k in kern},
-                "iteration": {"algorithmic_GB_per_iter": words_iter * esz / 1e9, "achieved_GBps": iter_gbs, "frac": iter_gbs / peak,
-                              "formula": "(11F+V7) words/iter, SURVEY §8d"}}
+                "bytes_per_launch": kbytes,
+                "cg_mode": args.cg_mode,
+                "active_set": {"mode": args.active_set, "segments": segs, "segments_total": segs_total, "computed_rows": rows,
+                               "faces": F, "row_fraction": rows / F, "cg_working_set_MB": working_set / 1e6,
+                               "l2_resident": working_set < 100e6},
+                "note": "bytes = lattice points of ACTIVE segments x words per point; when the CG working set is L2-resident the "
+                        "achieved figure is L2, not HBM, bandwidth (see --scene column for the HBM-bound dense case)",
+                "dense_equivalent": {"algorithmic_GB_per_iter": words_iter * esz / 1e9, "achieved_GBps": iter_gbs, "frac": iter_gbs / peak,
+                                     "formula": "(11F+V7) words/iter if every face row were streamed, SURVEY §8d"}}
 
     # ---- CPU baseline (bounded sample) on this box's host cores ----------------------------------------------
     cpu = cpu_baseline(args, sc, solver, lib, scale)
@@ -316,6 +329,10 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=4, help="CG iterations per step of the CPU arm / cpu_baseline sample")
     ap.add_argument("--mu", type=float, default=100.0)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="solver storage/arithmetic type (reference: f64)")
+    ap.add_argument("--active-set", default="nonzero", choices=["nonzero", "fluid"],
+                    help="rows the CG kernels visit: nonzero (default) = rows with a non-zero coefficient; fluid = every row the reference computes")
+    ap.add_argument("--cg-mode", default="auto", choices=["auto", "kernels", "persistent"],
+                    help="three kernels per iteration from a CUDA graph, one persistent cooperative kernel, or auto by working-set size")
     ap.add_argument("--scene", default="buckling", choices=["buckling", "column"],
                     help="buckling = BASELINE config 4 (default); column = dense-fluid viscous column (config 5 geometry) for kernel studies")
     args = ap.parse_args()

@@ -58,6 +58,21 @@ extern "C" {
                                 (matvecmul / initialize_solver semantics, boundary layer untouched) */
 #define FS_STORE_FLUID 2     /* apply_viscosity semantics: indices 1..g-1 on all axes, fluid faces only */
 
+/* which rows the CG kernels visit (fs_visc3d_set_active_mode).  Both give bit-identical results:
+ *   FS_ACTIVE_FLUID    every row the reference's kernels compute (fluid face, interior; ViscosityCGSolver3D.py:251-258)
+ *   FS_ACTIVE_NONZERO  (default) of those, only rows with at least one non-zero coefficient; an all-zero row is also an
+ *                      all-zero column, its b, q, r, d stay exactly 0 and its x never changes (faces far from any liquid) */
+#define FS_ACTIVE_FLUID 0
+#define FS_ACTIVE_NONZERO 1
+
+/* how the CG iterations are executed (fs_visc3d_set_cg_mode); identical arithmetic:
+ *   FS_CG_KERNELS     three kernels per iteration (K1 apply+d.q, K2 x/r update + r.r, K3 d update), replayed from a CUDA graph
+ *   FS_CG_PERSISTENT  one cooperative launch runs whole iterations: the three kernels become phases separated by grid barriers
+ *   FS_CG_AUTO        (default) persistent while the CG working set is small (launch-latency bound), kernels otherwise */
+#define FS_CG_AUTO 0
+#define FS_CG_KERNELS 1
+#define FS_CG_PERSISTENT 2
+
 /* result of a CG run */
 typedef struct fs_cg_stats {
     int64_t iterations; /* CG iterations executed (reference: number of loop passes) */
@@ -89,6 +104,14 @@ void fs_visc3d_destroy(fs_visc3d* h);
 int fs_visc3d_lattice(const fs_visc3d* h, int* X, int* Y, int* Zp, int64_t* NL);
 /* device pointer of component `comp` (0,1,2) of solver vector `vec` (FS_VEC_*) inside the workspace */
 void* fs_visc3d_vector_ptr(const fs_visc3d* h, int vec, int comp);
+
+/* Select how iterations are launched (FS_CG_*). */
+int fs_visc3d_set_cg_mode(fs_visc3d* h, int mode);
+/* Select the active-row set (FS_ACTIVE_*); takes effect at the next fs_visc3d_pack. */
+int fs_visc3d_set_active_mode(fs_visc3d* h, int mode);
+/* After fs_visc3d_pack: number of active 32-point lattice segments the CG kernels walk, segments in the whole lattice,
+ * and computed rows (any pointer may be NULL). */
+int fs_visc3d_active_info(fs_visc3d* h, int64_t* segments, int64_t* segments_total, int64_t* rows, void* stream);
 
 /* De-interleave the reference's fine-grid inputs into SoA coefficient planes + face masks.
  * vol = lvol / vol_norm (ViscosityCGSolver3D.py:568 uses vol_norm = cell_vol*0.125; pass 1.0 when

@@ -48,6 +48,92 @@ __global__ void cg_state_unlimit_kernel(CgState* st) {
     st->max_iter = 0x7fffffffffffffffLL;
 }
 
+// ---- active-segment list -------------------------------------------------------------------------------------
+__global__ void seg_count_kernel(const uint8_t* act, long long nseg_total, int* block_count) {
+    const long long s = (long long)blockIdx.x * kSegBlock + threadIdx.x;
+    const int n = __syncthreads_count(seg_flag(act, s, nseg_total) ? 1 : 0);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = n;
+}
+
+__global__ void seg_scan_kernel(int* block_count, int nblocks, int* nseg_out) {
+    __shared__ int wtot[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        const int v = i < nblocks ? block_count[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wtot[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const int t = wtot[lane];
+            int ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, ti, o);
+                if (lane >= o) ti += u;
+            }
+            wtot[lane] = ti - t;                 // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int c = carry;
+        if (i < nblocks) block_count[i] = c + wtot[w] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + wtot[w] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nseg_out = carry;
+}
+
+__global__ void seg_write_kernel(const uint8_t* act, long long nseg_total, const int* block_off, int* list) {
+    __shared__ int wsum[kSegBlock / 32];
+    const long long s = (long long)blockIdx.x * kSegBlock + threadIdx.x;
+    const bool f = seg_flag(act, s, nseg_total);
+    const unsigned int m = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    int off = block_off[blockIdx.x];
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    if (f) list[off + __popc(m & ((1u << lane) - 1u))] = (int)s;
+}
+
+int SegList::init(long long npts, void* list_dev, void* scratch_dev) {
+    nseg_total = (npts + kSegPts - 1) / kSegPts;
+    nblocks = (int)((nseg_total + kSegBlock - 1) / kSegBlock);
+    list = (int*)list_dev;
+    block_off = (int*)scratch_dev;
+    nseg_dev = block_off + nblocks + 1;
+    nseg = 0;
+    if (!nseg_pinned) FS_CUDA(cudaHostAlloc((void**)&nseg_pinned, sizeof(int), cudaHostAllocDefault));
+    return FS_OK;
+}
+
+void SegList::destroy() {
+    if (nseg_pinned) cudaFreeHost(nseg_pinned);
+    nseg_pinned = nullptr;
+}
+
+int SegList::build(const uint8_t* act, cudaStream_t s) {
+    seg_count_kernel<<<nblocks, kSegBlock, 0, s>>>(act, nseg_total, block_off);
+    FS_LAUNCH_CHECK();
+    seg_scan_kernel<<<1, 1024, 0, s>>>(block_off, nblocks, nseg_dev);
+    FS_LAUNCH_CHECK();
+    seg_write_kernel<<<nblocks, kSegBlock, 0, s>>>(act, nseg_total, block_off, list);
+    FS_LAUNCH_CHECK();
+    FS_CUDA(cudaMemcpyAsync(nseg_pinned, nseg_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FS_CUDA(cudaStreamSynchronize(s));
+    nseg = *nseg_pinned;
+    return FS_OK;
+}
+
 bool IterGraph::enabled() {
     static int on = -1;
     if (on < 0) {

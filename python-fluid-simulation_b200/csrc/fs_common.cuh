@@ -350,6 +350,276 @@ __global__ void __launch_bounds__(kVecThreads) cg_residual_init_kernel(long long
     }, peers, 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Active-segment lists.  Solver vectors are exactly zero (and x is never changed) on every row the
+// operator does not compute, so the CG kernels only need to visit the rows that are computed.  The
+// lattice / cell array is cut into segments of kSegPts consecutive points; a segment is ACTIVE when
+// any of its points carries a computed row.  The sorted list of active segments is built once per
+// solve (count -> scan -> write, deterministic order) and K1/K2/K3 walk the list instead of the
+// whole array: traffic and time scale with the active set, not with the grid.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSegPts = 32;
+constexpr int kSegBlock = 256;            // segments handled per block by the list-building kernels
+constexpr unsigned int kActCompute = 0x07u;   // bits 0..2: row of component c is computed by this rank
+constexpr unsigned int kActHalo = 0x70u;      // bits 4..6: row is computed by a neighbour slab and mirrored here (multi-GPU)
+
+__device__ __forceinline__ bool seg_flag(const uint8_t* __restrict__ act, long long s, long long nseg_total) {
+    if (s >= nseg_total) return false;
+    const uint4* p = reinterpret_cast<const uint4*>(act + s * kSegPts);
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    return ((a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) & 0x77777777u) != 0u;
+}
+
+__global__ void seg_count_kernel(const uint8_t* act, long long nseg_total, int* block_count);
+// exclusive scan of block_count[0..nblocks) in place; total -> *nseg_out
+__global__ void seg_scan_kernel(int* block_count, int nblocks, int* nseg_out);
+__global__ void seg_write_kernel(const uint8_t* act, long long nseg_total, const int* block_off, int* list);
+
+struct SegList {
+    int* list = nullptr;        // device: active segment ids, ascending
+    int* block_off = nullptr;   // device: nblocks ints (scratch of the scan)
+    int* nseg_dev = nullptr;    // device: number of active segments
+    int* nseg_pinned = nullptr; // host mirror
+    long long nseg_total = 0;   // segments in the whole array
+    int nblocks = 0;
+    int nseg = 0;               // host copy, valid after build()
+    static size_t list_bytes(long long npts) { return (size_t)((npts + kSegPts - 1) / kSegPts) * sizeof(int); }
+    static size_t scratch_bytes(long long npts) {
+        const long long ns = (npts + kSegPts - 1) / kSegPts;
+        return (size_t)((ns + kSegBlock - 1) / kSegBlock + 8) * sizeof(int);
+    }
+    int init(long long npts, void* list_dev, void* scratch_dev);
+    void destroy();
+    // act: one byte per point, readable up to 32*nseg_total bytes.  Blocks until the count is on the host.
+    int build(const uint8_t* act, cudaStream_t s);
+};
+
+// grid size for a list-walking kernel: enough CTAs for the list, at most `cap`; the list length is rounded up to a
+// power of two first so that the launch configuration (and with it the captured iteration graph) changes rarely
+inline int seg_grid(int nseg, int segs_per_block, int cap) {
+    long long n = 1;
+    while (n < nseg) n <<= 1;
+    long long b = (n + segs_per_block - 1) / segs_per_block;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+inline long long seg_level(int nseg) {
+    long long n = 1;
+    while (n < nseg) n <<= 1;
+    return n;
+}
+
+// two consecutive elements per lane (16-byte accesses for fp64, 8-byte for fp32): a half-warp covers one segment
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+// K2 on the active set (same arithmetic as cg_update_xr_kernel).  `ncomp` component arrays of `comp_stride` elements
+// follow each other in x,r,d,q; a point index p of the list addresses element c*comp_stride + p of component c.
+// Returns this thread's share of r.r (owned rows only when DIST).  No __restrict__/__ldg on the vectors: the same body
+// runs inside the persistent whole-iteration kernel, where other CTAs rewrite them between grid barriers.
+template <typename T, bool DIST>
+__device__ __forceinline__ double cg_update_xr_seg_body(int ncomp, long long comp_stride, long long npts, const int* __restrict__ seg, int nseg,
+                                                        T* x, T* r, const T* d, const T* q, T alpha, const PeerHot& hot) {
+    using V = typename Vec2<T>::type;
+    const int hl = threadIdx.x & 15;
+    const long long hw0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const long long nhw = ((long long)gridDim.x * blockDim.x) >> 4;
+    double acc = 0.0;
+    for (int c = 0; c < ncomp; ++c) {
+        const long long base = (long long)c * comp_stride + 2 * hl;
+        long long j = hw0;
+        int sg = j < nseg ? __ldg(seg + j) : 0;
+        while (j < nseg) {
+            const long long p = (long long)sg * kSegPts + 2 * hl;
+            const long long e = base + (long long)sg * kSegPts;
+            j += nhw;
+            sg = j < nseg ? __ldg(seg + j) : 0;           // next segment id requested before this one's data
+            if (p >= npts) continue;                      // tail of the last segment (npts is even)
+            V xv = *reinterpret_cast<const V*>(x + e);
+            V rv = *reinterpret_cast<const V*>(r + e);
+            const V dv = *reinterpret_cast<const V*>(d + e);
+            const V qv = *reinterpret_cast<const V*>(q + e);
+            bool own = true;
+            if (DIST) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) own = own && !(e >= hot.hb[k] && e < hot.he[k]);
+            }
+            xv.x = xv.x + alpha * dv.x; xv.y = xv.y + alpha * dv.y;
+            rv.x = rv.x - alpha * qv.x; rv.y = rv.y - alpha * qv.y;
+            if (own) acc += (double)rv.x * (double)rv.x + (double)rv.y * (double)rv.y;
+            *reinterpret_cast<V*>(x + e) = xv;
+            *reinterpret_cast<V*>(r + e) = rv;
+        }
+    }
+    return acc;
+}
+
+// bookkeeping after the r.r reduction (thread 0 of the finishing block)
+__device__ __forceinline__ void cg_after_rr(CgState* st, double alpha_d, double s) {
+    st->alpha = alpha_d;
+    if (st->dist) { st->red = s; return; }
+    st->delta_old = st->delta;
+    st->delta = s;
+    st->iter += 1;
+    if (s < st->tol2) st->done = 1;
+    else if (st->iter >= st->max_iter || !(s == s)) st->done = 2;  // NaN: the reference would spin to max_iter
+}
+
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kVecThreads) cg_update_xr_seg_kernel(int ncomp, long long comp_stride, long long npts,
+                                                                       const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                       T* x, T* r, const T* d, const T* q, CgState* st, double* partials, int freeze,
+                                                                       PeerInfo* peers, PeerHot hot) {
+    if (*(volatile int*)&st->done) return;
+    const double alpha_d = st->delta / st->dq;
+    const double acc = cg_update_xr_seg_body<T, DIST>(ncomp, comp_stride, npts, seg, *nseg_p, x, r, d, q, (T)alpha_d, hot);
+    grid_sum_finish(acc, partials, &st->counter[1], [=](double s) {
+        if (freeze) return;
+        cg_after_rr(st, alpha_d, s);
+    }, (DIST && !freeze) ? peers : nullptr, 1, false);
+}
+
+// K3 on the active set
+template <typename T>
+__device__ __forceinline__ void cg_update_d_seg_body(int ncomp, long long comp_stride, long long npts, const int* __restrict__ seg, int nseg,
+                                                     T* d, const T* r, T beta) {
+    using V = typename Vec2<T>::type;
+    const int hl = threadIdx.x & 15;
+    const long long hw0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const long long nhw = ((long long)gridDim.x * blockDim.x) >> 4;
+    for (int c = 0; c < ncomp; ++c) {
+        const long long base = (long long)c * comp_stride + 2 * hl;
+        long long j = hw0;
+        int sg = j < nseg ? __ldg(seg + j) : 0;
+        while (j < nseg) {
+            const long long p = (long long)sg * kSegPts + 2 * hl;
+            const long long e = base + (long long)sg * kSegPts;
+            j += nhw;
+            sg = j < nseg ? __ldg(seg + j) : 0;
+            if (p >= npts) continue;
+            V dv = *reinterpret_cast<const V*>(d + e);
+            const V rv = *reinterpret_cast<const V*>(r + e);
+            dv.x = rv.x + beta * dv.x; dv.y = rv.y + beta * dv.y;
+            *reinterpret_cast<V*>(d + e) = dv;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) cg_update_d_seg_kernel(int ncomp, long long comp_stride, long long npts,
+                                                                      const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                      T* d, const T* r, CgState* st) {
+    if (*(volatile int*)&st->done) return;
+    const double beta_d = st->delta / st->delta_old;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->beta = beta_d;
+    cg_update_d_seg_body<T>(ncomp, comp_stride, npts, seg, *nseg_p, d, r, (T)beta_d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grid-wide barrier for the persistent whole-iteration kernels (cooperative launch: every CTA is
+// resident).  grid_reduce_barrier sums one double over the grid: the LAST block to arrive adds the
+// per-block partials in a fixed order, optionally all-reduces over the NVSwitch peers, runs
+// fin(total) in its thread 0 and only then releases the other blocks — one barrier per reduction,
+// and the CG scalars are updated by exactly one thread, as in the multi-kernel path.
+// ---------------------------------------------------------------------------------------------
+struct GridBar { unsigned int count; unsigned int gen; };
+
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
+    unsigned int r;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+    return r;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int r;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+    unsigned int r;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Arrival is an acq_rel atomic (releases this block's writes — bar.sync before it makes that cumulative over the block —
+// and acquires the others' for the last arriver); waiters spin on an acquire load of the generation word.
+__device__ __forceinline__ void grid_barrier(GridBar* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int g = ld_relaxed_gpu(&bar->gen);       // cannot advance before this block has arrived
+        if (atom_add_acq_rel_gpu(&bar->count, 1u) == gridDim.x - 1) {
+            bar->count = 0;
+            st_release_gpu(&bar->gen, g + 1u);
+        } else {
+            while (ld_acquire_gpu(&bar->gen) == g) { }
+        }
+    }
+    __syncthreads();
+}
+
+template <class Fin>
+__device__ __forceinline__ void grid_reduce_barrier(double v, double* partials, GridBar* bar, Fin fin,
+                                                    PeerInfo* peers = nullptr, int kind = 0, bool wrote_peer = false) {
+    __shared__ double sm[32];
+    __shared__ unsigned int s_gen;
+    __shared__ bool s_last;
+    const unsigned int nblocks = gridDim.x;
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) {
+        s_gen = ld_relaxed_gpu(&bar->gen);
+        partials[blockIdx.x] = v;
+        if (wrote_peer) __threadfence_system();               // stores into a peer GPU need system scope
+        s_last = (atom_add_acq_rel_gpu(&bar->count, 1u) == nblocks - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        double s = 0.0;
+        for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) s += __ldcg(partials + i);
+        s = block_sum(s, sm);
+        if (peers && threadIdx.x < 32) {
+            s = __shfl_sync(0xffffffffu, s, 0);
+            s = peer_allreduce_warp(s, peers, kind);
+        }
+        if (threadIdx.x == 0) {
+            bar->count = 0;
+            fin(s);
+            st_release_gpu(&bar->gen, s_gen + 1u);
+        }
+    } else if (threadIdx.x == 0) {
+        while (ld_acquire_gpu(&bar->gen) == s_gen) { }
+    }
+    __syncthreads();
+}
+
+constexpr int kPersistThreads = 512;      // one CTA per SM (128 registers per thread for the operator body)
+
+constexpr int kSegsPerVecBlock = kVecThreads / 16;   // one half-warp per segment
+
+template <typename T>
+int cg_launch_update_xr_seg(int ncomp, long long comp_stride, long long npts, const SegList& sl, T* x, T* r, const T* d, const T* q,
+                            CgState* st, double* partials, cudaStream_t s, int freeze = 0, PeerInfo* peers = nullptr,
+                            const PeerHot* hotp = nullptr) {
+    PeerHot hot;
+    memset(&hot, 0, sizeof(hot));
+    if (hotp) hot = *hotp;
+    const int grid = seg_grid(sl.nseg, kSegsPerVecBlock, kVecGrid);
+    if (peers) cg_update_xr_seg_kernel<T, true><<<grid, kVecThreads, 0, s>>>(ncomp, comp_stride, npts, sl.list, sl.nseg_dev, x, r, d, q, st, partials, freeze, peers, hot);
+    else cg_update_xr_seg_kernel<T, false><<<grid, kVecThreads, 0, s>>>(ncomp, comp_stride, npts, sl.list, sl.nseg_dev, x, r, d, q, st, partials, freeze, nullptr, hot);
+    FS_LAUNCH_CHECK();
+    return FS_OK;
+}
+
+template <typename T>
+int cg_launch_update_d_seg(int ncomp, long long comp_stride, long long npts, const SegList& sl, T* d, const T* r, CgState* st, cudaStream_t s) {
+    const int grid = seg_grid(sl.nseg, kSegsPerVecBlock, kVecGrid);
+    cg_update_d_seg_kernel<T><<<grid, kVecThreads, 0, s>>>(ncomp, comp_stride, npts, sl.list, sl.nseg_dev, d, r, st);
+    FS_LAUNCH_CHECK();
+    return FS_OK;
+}
+
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 inline int vec_grid(long long n, int vec) {
     long long b = (n / vec + kVecThreads - 1) / kVecThreads;
@@ -423,13 +693,14 @@ struct IterGraph {
     cudaGraphExec_t exec = nullptr;
     cudaStream_t cap = nullptr;
     double key = 0.0;
+    long long key2 = 0;     // launch-configuration level (active-set size class); a change re-captures the graph
     int iters = 0;
     bool valid = false;
     static bool enabled();
 
     template <class EnqueueOne>
-    int ensure(double key_, int iters_, EnqueueOne one) {
-        if (valid && key == key_ && iters == iters_) return FS_OK;
+    int ensure(double key_, long long key2_, int iters_, EnqueueOne one) {
+        if (valid && key == key_ && key2 == key2_ && iters == iters_) return FS_OK;
         if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
         valid = false;
         if (!cap) FS_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -446,7 +717,7 @@ struct IterGraph {
         e = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) { exec = nullptr; return fail(FS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
-        key = key_; iters = iters_; valid = true;
+        key = key_; key2 = key2_; iters = iters_; valid = true;
         return FS_OK;
     }
     int launch(cudaStream_t s) {
@@ -463,12 +734,13 @@ struct IterGraph {
 };
 
 constexpr int kCgBatch = 16;
+constexpr int kCgBatchPersistent = 64;   // iterations per launch of a persistent whole-iteration kernel (it stops early when done)
 
 // Enqueue `n` iterations: whole batches of kCgBatch through the graph, the remainder launch by launch.
 template <class EnqueueOne>
-int cg_enqueue_iterations(IterGraph& g, bool use_graph, double key, long long n, EnqueueOne one, cudaStream_t s) {
+int cg_enqueue_iterations(IterGraph& g, bool use_graph, double key, long long n, EnqueueOne one, cudaStream_t s, long long key2 = 0) {
     if (use_graph && IterGraph::enabled() && n >= kCgBatch) {
-        FS_TRY(g.ensure(key, kCgBatch, one));
+        FS_TRY(g.ensure(key, key2, kCgBatch, one));
         while (n >= kCgBatch) { FS_TRY(g.launch(s)); n -= kCgBatch; }
     }
     for (long long k = 0; k < n; ++k) FS_TRY(one(s));

@@ -26,6 +26,7 @@ struct Lat3 {
     int X, Y, Zp;
     long long sx, sy, NL;
     int u_xhi;   // last computed x-plane of u rows: nx-1, or nx-2 when a higher slab owns plane nx-1 (multi-GPU)
+    int has_lo, has_hi;   // multi-GPU: plane 0 / plane nx-1 mirrors rows owned by the lower / higher slab
 };
 
 template <typename T> struct Visc3Dev {
@@ -68,6 +69,8 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
     const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
     auto vol = [&](long long off) { return (T)(lvol[f0 + off] / vol_norm); };
     unsigned int abits = 0;
+    // rows of these planes are computed by a neighbour slab and mirrored here (K2/K3 keep r and d current on them)
+    const bool halo_x = (L.has_lo && x == 0) || (L.has_hi && x == L.nx - 1);
     // faces: fine parities (0,1,1) (1,0,1) (1,1,0)
     {
         const bool in = iy && iz;
@@ -77,6 +80,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
             fluid = sphi[f0 + fy + fz] >= 0.0;
             const bool interior = x >= 1 && x <= L.u_xhi && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
             if (fluid && interior) { v = vol(fy + fz); if (v == v) abits |= 1u; }
+            if (fluid && halo_x && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2) abits |= 0x10u;
         }
         coef[0 * L.NL + i] = v;
         mask[0 * L.NL + i] = fluid;
@@ -89,6 +93,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
             fluid = sphi[f0 + fx + fz] >= 0.0;
             const bool interior = x >= 1 && x <= L.nx - 2 && y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2;
             if (fluid && interior) { v = vol(fx + fz); if (v == v) abits |= 2u; }
+            if (fluid && halo_x && y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2) abits |= 0x20u;
         }
         coef[1 * L.NL + i] = v;
         mask[1 * L.NL + i] = fluid;
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
             fluid = sphi[f0 + fx + fy] >= 0.0;
             const bool interior = x >= 1 && x <= L.nx - 2 && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1;
             if (fluid && interior) { v = vol(fx + fy); if (v == v) abits |= 4u; }
+            if (fluid && halo_x && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1) abits |= 0x40u;
         }
         coef[2 * L.NL + i] = v;
         mask[2 * L.NL + i] = fluid;
@@ -110,6 +116,40 @@ __global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const dou
     coef[5 * L.NL + i] = (iy && inz) ? vol(fy) : T(0);                  // Exz: (0,1,0)
     coef[6 * L.NL + i] = (ix && inz) ? vol(fx) : T(0);                  // Eyz: (1,0,0)
     act[i] = (uint8_t)abits;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Active-set refinement (FS_ACTIVE_NONZERO): a computed row whose seven coefficients (face volume, two cell-centre
+// volumes, four edge volumes) are all zero is an all-zero row AND column of the operator — b, q, r, d are exactly 0
+// there for the whole solve and x never changes (faces far from any liquid) — so it is dropped from the active set.
+// Results are bit-identical; only rows that can carry a non-zero value are visited by the CG kernels.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) visc3d_activity_kernel(Lat3 L, const T* __restrict__ coef /*[7][NL]*/, uint8_t* __restrict__ act) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.NL) return;
+    unsigned int a = act[i];
+    if ((a & kActCompute) == 0u) return;
+    const long long NL = L.NL, sx = L.sx, sy = L.sy;
+    const T* Vc = coef + 3 * NL;
+    const T* Exy = coef + 4 * NL;
+    const T* Exz = coef + 5 * NL;
+    const T* Eyz = coef + 6 * NL;
+    auto nz = [](T v) { return v != T(0); };       // NaN counts as non-zero: it must propagate like in the reference
+    const bool c0 = nz(Vc[i]), exy = nz(Exy[i]), exz = nz(Exz[i]), eyz = nz(Eyz[i]);
+    if (a & 1u) {
+        const bool on = nz(coef[i]) || c0 || nz(Vc[i - sx]) || nz(Exy[i + sy]) || exy || nz(Exz[i + 1]) || exz;
+        if (!on) a &= ~1u;
+    }
+    if (a & 2u) {
+        const bool on = nz(coef[NL + i]) || c0 || nz(Vc[i - sy]) || nz(Exy[i + sx]) || exy || nz(Eyz[i + 1]) || eyz;
+        if (!on) a &= ~2u;
+    }
+    if (a & 4u) {
+        const bool on = nz(coef[2 * NL + i]) || c0 || nz(Vc[i - 1]) || nz(Exz[i + sx]) || exz || nz(Eyz[i + sy]) || eyz;
+        if (!on) a &= ~4u;
+    }
+    act[i] = (uint8_t)a;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -156,37 +196,45 @@ __global__ void __launch_bounds__(kThreads) visc3d_store_kernel(Lat3 L, const T*
 }
 
 // ---------------------------------------------------------------------------------------------
-// extrapolation sweep (extrapolate_kernel :8-39), all three components per launch, ping-pong
+// extrapolation sweep (extrapolate_kernel :8-39), all three components per launch, IN PLACE.
+// The reference ping-pongs full copies of the three velocity arrays and validity masks per sweep
+// (Jacobi).  Here the validity byte carries a generation: 0 = invalid, 1 = valid from the start
+// (sphi >= 0), k+1 = filled by sweep k.  Sweep k treats a neighbour as valid iff 1 <= byte <= k, so
+// a face that is being filled concurrently (byte 0 or k+1) is never read in the same sweep, and a
+// value is only ever written to a face nobody reads during that sweep: identical to Jacobi, without
+// copies — a sweep reads the validity bytes and touches values only next to the fluid/solid interface.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, const T* __restrict__ vin, const uint8_t* __restrict__ valin,
-                                                                      T* __restrict__ vout, uint8_t* __restrict__ valout) {
+__global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, T* v_all, uint8_t* valid_all, int sweep /*1-based*/) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.NL) return;
+    const uint8_t v0 = valid_all[i], v1 = valid_all[L.NL + i], v2 = valid_all[2 * L.NL + i];
+    if (v0 && v1 && v2) return;                       // nothing to fill at this lattice point (the common case)
     int x, y, z;
     lat_decode(L, i, x, y, z);
     const long long st[3] = {L.sx, L.sy, 1};
+    const uint8_t own[3] = {v0, v1, v2};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+        if (own[c]) continue;
         int s0, s1, s2;
         comp_shape(L, c, s0, s1, s2);
-        const T* v = vin + c * L.NL;
-        const uint8_t* va = valin + c * L.NL;
-        T out = v[i];
-        uint8_t ov = va[i];
         const bool interior = x >= 1 && x <= s0 - 2 && y >= 1 && y <= s1 - 2 && z >= 1 && z <= s2 - 2;
-        if (interior && !ov) {
-            T val = T(0);
-            int count = 0;
+        if (!interior) continue;
+        T* v = v_all + c * L.NL;
+        const uint8_t* va = valid_all + c * L.NL;
+        T val = T(0);
+        int count = 0;
 #pragma unroll
-            for (int ax = 0; ax < 3; ++ax) {   // +x,-x,+y,-y,+z,-z  (:19-36)
-                if (va[i + st[ax]]) { val += v[i + st[ax]]; ++count; }
-                if (va[i - st[ax]]) { val += v[i - st[ax]]; ++count; }
-            }
-            if (count > 0) { out = val / (T)count; ov = 1; }
+        for (int ax = 0; ax < 3; ++ax) {   // +x,-x,+y,-y,+z,-z  (:19-36)
+            const unsigned int gp = va[i + st[ax]], gm = va[i - st[ax]];
+            if (gp >= 1u && gp <= (unsigned int)sweep) { val += v[i + st[ax]]; ++count; }
+            if (gm >= 1u && gm <= (unsigned int)sweep) { val += v[i - st[ax]]; ++count; }
         }
-        vout[c * L.NL + i] = out;
-        valout[c * L.NL + i] = ov;
+        if (count > 0) {
+            v[i] = val / (T)count;
+            valid_all[c * L.NL + i] = (uint8_t)(sweep + 1);
+        }
     }
 }
 
@@ -230,96 +278,226 @@ __global__ void __launch_bounds__(kThreads) visc3d_general_kernel(Visc3Dev<T> P,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Start of a solve on the active set: b = RHS(x), q = A x (both with the reference's neighbour masks and
+// association, ViscosityCGSolver3D.py:574-575), d = r = b - q, delta0 = r.r (:577-587) — one pass over the active
+// segments.  Rows outside the active set hold b = q = r = d = 0 (invariant kept by visc3d_clear_kernel).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) visc3d_begin_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ xv, T* __restrict__ b, T* __restrict__ q,
+                                                                T* __restrict__ r, T* __restrict__ d, const int* __restrict__ seg,
+                                                                const int* __restrict__ nseg_p, CgState* st_, double* partials, PeerInfo* peers) {
+    const Lat3& L = P.L;
+    const long long NL = L.NL;
+    const long long st[3] = {L.sx, L.sy, 1};
+    const int nseg = *nseg_p;
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const uint8_t* const* mask = P.mask;
+    auto nb_apply = [&](int comp, long long j) -> T { return mask[comp][j] ? xv[comp * NL + j] : T(0); };
+    auto nb_rhs = [&](int comp, long long j) -> T { return mask[comp][j] ? T(0) : xv[comp * NL + j]; };
+    double acc = 0.0;
+    for (long long k = w0; k < nseg; k += nw) {
+        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+        if (i >= NL) continue;
+        const unsigned int a = (unsigned int)P.act[i] & kActCompute;
+        if (a == 0u) continue;
+        auto row = [&](auto Atag) {
+            constexpr int A = decltype(Atag)::value;
+            if (!(a & (1u << A))) return;
+            const T center = P.coef[A][i];
+            const T own = xv[A * NL + i];
+            const T bb = visc_row<T, 3, A, true, ROW_RHS>(P.coef, i, st, center, own, s, s2, nb_rhs);
+            const T qq = visc_row<T, 3, A, true, ROW_APPLY>(P.coef, i, st, center, own, s, s2, nb_apply);
+            const T rr = bb - qq;
+            b[A * NL + i] = bb; q[A * NL + i] = qq; r[A * NL + i] = rr; d[A * NL + i] = rr;
+            acc += (double)rr * (double)rr;
+        };
+        row(std::integral_constant<int, 0>{});
+        row(std::integral_constant<int, 1>{});
+        row(std::integral_constant<int, 2>{});
+    }
+    grid_sum_finish(acc, partials, &st_->counter[2], [=](double sum) {
+        if (st_->dist) { st_->red = sum; return; }
+        st_->delta = sum;
+        st_->delta0 = sum;
+        st_->delta_old = sum;
+        if (sum < st_->tol2) st_->done = 1;           // `if not self.delta < tol ** 2:` skips the loop
+    }, peers, 1);
+}
+
+// zero r, d, q, b on the segments of the (previous) active list
+template <typename T>
+__global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T* __restrict__ vecs /*[5][3][NL]*/, const int* __restrict__ seg,
+                                                                const int* __restrict__ nseg_p) {
+    const int nseg = *nseg_p;
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long k = w0; k < nseg; k += nw) {
+        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+        if (i >= NL) continue;
+#pragma unroll
+        for (int v = FS_VEC_R; v <= FS_VEC_B; ++v)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) vecs[((long long)v * 3 + c) * NL + i] = T(0);
+    }
+}
+
+// apply_viscosity (:458-470) restricted to the rows the solve can have changed (the computed rows of the active set).
+// Every other fluid face still holds the value that was loaded from the very same caller arrays.
+template <typename T, typename S>
+__global__ void __launch_bounds__(kThreads) visc3d_store_active_kernel(Lat3 L, const T* __restrict__ vec, const uint8_t* __restrict__ act,
+                                                                       const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                       S* __restrict__ a0, S* __restrict__ a1, S* __restrict__ a2) {
+    const int nseg = *nseg_p;
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    S* dst[3] = {a0, a1, a2};
+    for (long long k = w0; k < nseg; k += nw) {
+        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+        if (i >= L.NL) continue;
+        const unsigned int a = (unsigned int)act[i] & kActCompute;
+        if (a == 0u) continue;
+        int x, y, z;
+        lat_decode(L, i, x, y, z);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (!(a & (1u << c))) continue;
+            int s0, s1, s2;
+            comp_shape(L, c, s0, s1, s2);
+            dst[c][((long long)x * s1 + y) * s2 + z] = (S)vec[c * L.NL + i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1: CG-loop apply fused with d.q.  Inside the loop d is exactly zero on every row that is not
-// computed (solid / boundary / padding / other slab), so neighbour masks are not needed (SURVEY A-1)
-// and the row flag rides in the NaN tag of the face volume.
+// computed (solid / boundary / padding / other slab / all-zero row), so neighbour masks are not
+// needed (SURVEY A-1).
 //
-// Persistent grid (kK1BlocksPerSM CTAs per SM, grid-stride over the lattice, z contiguous across the
-// warp).  Per lattice point: the three NaN tags are loaded first; a warp whose 32 points carry no
-// computed row skips the body (the reference's `if sphi < 0: return`, made warp-uniform).  Otherwise
-// the body is branch-free — all 27 neighbour values and 16 coefficients are requested before the first
-// use, one memory-latency period per point instead of one per row — and rows that are not computed
-// select 0.  Loads of discarded lanes may fall outside the lattice; the workspace carries guard bands
-// of one plane + one row + one element around the coefficient and vector regions for exactly that.
-// One block reduction at the very end (fixed-order, deterministic).
+// Persistent grid (kK1BlocksPerSM CTAs per SM).  Each warp walks the sorted list of ACTIVE segments
+// (32 consecutive lattice points, z contiguous across the warp) — the reference's `if sphi < 0:
+// return` turned into "never launched": solid and liquid-free regions cost nothing.  The body is
+// branch-free: all 27 neighbour values, 16 coefficients and the activity byte of a point are
+// requested before the first use (one memory-latency period per segment; the next segment id is
+// prefetched one trip ahead), and rows that are not computed select 0 and are not stored — they
+// hold q == 0 since the masked apply at the start of the solve.  Loads of discarded lanes may fall
+// outside the lattice; the workspace carries guard bands of one plane + one row + one element
+// around the coefficient and vector regions for exactly that.  One block reduction at the very end
+// (fixed order, deterministic).
 // ---------------------------------------------------------------------------------------------
 constexpr int kK1Threads = 256;
+constexpr int kK1SegsPerBlock = kK1Threads / 32;
 // CTAs per SM: the fp64 body keeps 43 loaded values (86 registers) in flight, so it gets 128 registers per thread
 // (2 CTAs/SM); with an 80-register cap (3 CTAs/SM) ptxas split the loads into dependent phases and the dense-scene
 // K1 ran at 0.556 ms instead of 0.357 ms.  fp32 needs half the registers.
 template <typename T> struct K1Occ { static constexpr int value = 2; };
 template <> struct K1Occ<float> { static constexpr int value = 3; };
 
-template <typename T, bool DIST>
-__global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
-                                                                                       CgState* st_, double* partials, PeerInfo* peers, PeerHot hot) {
-    if (*(volatile int*)&st_->done) return;
+// One pass over the active segments: q = A d on computed rows, returns this thread's share of d.q.
+// COHERENT = false: d is read through the read-only path (stand-alone K1: nothing writes d during the launch);
+// COHERENT = true : plain loads (persistent kernel: other CTAs rewrote d before the last grid barrier).
+template <typename T, bool DIST, bool COHERENT>
+__device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T s, T s2, const T* d, T* q, const int* __restrict__ seg, int nseg,
+                                                        const PeerHot& hot, bool& wrote_peer) {
     const Lat3& L = P.L;
     const long long NL = L.NL;
     const long long st[3] = {L.sx, L.sy, 1};
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long NLw = (NL + 31) & ~31LL;       // whole warps take part in every trip (ballot below)
-    const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     double acc = 0.0;
-    bool wrote_peer = false;
-    auto nb = [&](int comp, long long j) -> T { return __ldg(d + comp * NL + j); };
-    // The activity byte of the NEXT trip is requested before this trip's work: in solid regions a trip is a single 1-byte
-    // load, and without the prefetch each warp would have one memory round trip in flight.
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int a_n = i < NL ? __ldg(P.act + i) : 0u;
-    for (; i < NLw; i += stride) {
-        const bool in = i < NL;
-        const unsigned int a = a_n;
+    auto nb = [&](int comp, long long j) -> T { return COHERENT ? d[comp * NL + j] : __ldg(d + comp * NL + j); };
+    int sg_n = w0 < nseg ? __ldg(seg + w0) : 0;
+    for (long long k = w0; k < nseg; k += nw) {
+        const long long i = (long long)sg_n * kSegPts + lane;
         {
-            const long long i2 = i + stride;
-            a_n = i2 < NL ? __ldg(P.act + i2) : 0u;
+            const long long k2 = k + nw;
+            sg_n = k2 < nseg ? __ldg(seg + k2) : 0;
         }
+        const bool in = i < NL;
+        const long long j = in ? i : (NL - 1);
+        const unsigned int a = in ? ((unsigned int)__ldg(P.act + i) & kActCompute) : 0u;
         const bool au = a & 1u, av = a & 2u, aw = a & 4u;
-        T ou = T(0), ov = T(0), ow = T(0);
-        if (__any_sync(0xffffffffu, a != 0u)) {
-            const long long j = in ? i : (NL - 1);
-            const T cu = __ldg(P.coef[0] + j), cv = __ldg(P.coef[1] + j), cw = __ldg(P.coef[2] + j);
-            const T du = nb(0, j), dv = nb(1, j), dw = nb(2, j);
-            const T ru = visc_row<T, 3, 0, false, ROW_APPLY>(P.coef, j, st, cu, du, s, s2, nb);
-            const T rv = visc_row<T, 3, 1, false, ROW_APPLY>(P.coef, j, st, cv, dv, s, s2, nb);
-            const T rw = visc_row<T, 3, 2, false, ROW_APPLY>(P.coef, j, st, cw, dw, s, s2, nb);
-            if (au) { ou = ru; acc += (double)du * (double)ru; }
-            if (av) { ov = rv; acc += (double)dv * (double)rv; }
-            if (aw) { ow = rw; acc += (double)dw * (double)rw; }
-        }
-        // multi-GPU: the halo planes of q (0 and X-2) are written by the NEIGHBOURS' K1 over NVLink — never by this rank
-        const bool halo_plane = DIST && ((hot.has_lo && i < L.sx) ||
-                                         (hot.has_hi && i >= (long long)(L.X - 2) * L.sx && i < (long long)(L.X - 1) * L.sx));
-        // Rows that are not computed hold q == 0 since the masked apply at the start of the solve (which writes 0 on every
-        // interior non-fluid row) and are never written afterwards, so only computed rows are stored — in solid regions
-        // K1 therefore moves one byte per lattice point.
-        if (in && !halo_plane && a != 0u) {
-            if (au) q[i] = ou;
-            if (av) q[NL + i] = ov;
-            if (aw) q[2 * NL + i] = ow;
-            if (DIST) {
-                // multi-GPU: my first / last owned planes are the neighbours' halo planes of q — store them straight
-                // into the peers' memory over NVLink; the all-reduce in this kernel's tail publishes them.
-                const long long lo0 = L.sx, hi0 = (long long)(L.X - 3) * L.sx;
-                if (hot.has_lo && i >= lo0 && i < lo0 + L.sx) {
-                    const long long o = i - lo0;
-                    if (au) reinterpret_cast<T*>(hot.q_lo[0])[o] = ou;
-                    if (av) reinterpret_cast<T*>(hot.q_lo[1])[o] = ov;
-                    if (aw) reinterpret_cast<T*>(hot.q_lo[2])[o] = ow;
-                    wrote_peer = true;
-                }
-                if (hot.has_hi && i >= hi0 && i < hi0 + L.sx) {
-                    const long long o = i - hi0;
-                    if (au) reinterpret_cast<T*>(hot.q_hi[0])[o] = ou;
-                    if (av) reinterpret_cast<T*>(hot.q_hi[1])[o] = ov;
-                    if (aw) reinterpret_cast<T*>(hot.q_hi[2])[o] = ow;
-                    wrote_peer = true;
-                }
+        const T cu = __ldg(P.coef[0] + j), cv = __ldg(P.coef[1] + j), cw = __ldg(P.coef[2] + j);
+        const T du = nb(0, j), dv = nb(1, j), dw = nb(2, j);
+        const T ru = visc_row<T, 3, 0, false, ROW_APPLY>(P.coef, j, st, cu, du, s, s2, nb);
+        const T rv = visc_row<T, 3, 1, false, ROW_APPLY>(P.coef, j, st, cv, dv, s, s2, nb);
+        const T rw = visc_row<T, 3, 2, false, ROW_APPLY>(P.coef, j, st, cw, dw, s, s2, nb);
+        if (au) { q[i] = ru; acc += (double)du * (double)ru; }
+        if (av) { q[NL + i] = rv; acc += (double)dv * (double)rv; }
+        if (aw) { q[2 * NL + i] = rw; acc += (double)dw * (double)rw; }
+        if (DIST && a != 0u) {
+            // multi-GPU: my first / last owned planes are the neighbours' halo planes of q — store them straight
+            // into the peers' memory over NVLink; the all-reduce that follows publishes them.  (The local halo
+            // planes 0 and X-2 carry no computed row: their q is written by the NEIGHBOURS, never by this rank.)
+            const long long lo0 = L.sx, hi0 = (long long)(L.X - 3) * L.sx;
+            if (hot.has_lo && i >= lo0 && i < lo0 + L.sx) {
+                const long long o = i - lo0;
+                if (au) reinterpret_cast<T*>(hot.q_lo[0])[o] = ru;
+                if (av) reinterpret_cast<T*>(hot.q_lo[1])[o] = rv;
+                if (aw) reinterpret_cast<T*>(hot.q_lo[2])[o] = rw;
+                wrote_peer = true;
+            }
+            if (hot.has_hi && i >= hi0 && i < hi0 + L.sx) {
+                const long long o = i - hi0;
+                if (au) reinterpret_cast<T*>(hot.q_hi[0])[o] = ru;
+                if (av) reinterpret_cast<T*>(hot.q_hi[1])[o] = rv;
+                if (aw) reinterpret_cast<T*>(hot.q_hi[2])[o] = rw;
+                wrote_peer = true;
             }
         }
     }
+    return acc;
+}
+
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
+                                                                                       const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                                       CgState* st_, double* partials, PeerInfo* peers, PeerHot hot) {
+    if (*(volatile int*)&st_->done) return;
+    bool wrote_peer = false;
+    const double acc = visc3d_apply_dot_body<T, DIST, false>(P, s, s2, d, q, seg, *nseg_p, hot, wrote_peer);
     const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
     grid_sum_finish(acc, partials, &st_->counter[0], [=](double sum) { st_->dq = sum; }, DIST ? peers : nullptr, 0, block_wrote_peer);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole CG iterations in ONE cooperative launch: K1, K2 and K3 become phases of a persistent kernel
+// (one 512-thread CTA per SM) separated by grid barriers; the two reductions ride on the barriers.
+// No launch gaps and no kernel ramp-up/tail per phase — what bounds an iteration once the active
+// set is small (L2-resident scenes, 64^3, thin multi-GPU slabs).  Same arithmetic, same reduction
+// tree shape (per-thread -> block -> fixed-order sum of block partials), same device-side
+// convergence logic as the three-kernel path; runs up to n_iters iterations and stops early when
+// the state says done.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kernel(Visc3Dev<T> P, T s, T s2, T* x, T* r, T* d, T* q,
+                                                                                  const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                                  CgState* st, double* partials, GridBar* bar, int n_iters,
+                                                                                  PeerInfo* peers, PeerHot hot) {
+    const int nseg = *nseg_p;
+    const long long NL = P.L.NL;
+    for (int it = 0; it < n_iters; ++it) {
+        if (*(volatile int*)&st->done) break;
+        // K1 phase
+        bool wrote_peer = false;
+        double acc = visc3d_apply_dot_body<T, DIST, true>(P, s, s2, d, q, seg, nseg, hot, wrote_peer);
+        const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
+        grid_reduce_barrier(acc, partials, bar, [=](double sum) { st->dq = sum; }, DIST ? peers : nullptr, 0, block_wrote_peer);
+        // K2 phase
+        const double alpha_d = *(volatile double*)&st->delta / *(volatile double*)&st->dq;
+        acc = cg_update_xr_seg_body<T, DIST>(3, NL, NL, seg, nseg, x, r, d, q, (T)alpha_d, hot);
+        grid_reduce_barrier(acc, partials, bar, [=](double sum) { cg_after_rr(st, alpha_d, sum); }, DIST ? peers : nullptr, 1, false);
+        if (*(volatile int*)&st->done) break;
+        // K3 phase
+        const double beta_d = *(volatile double*)&st->delta / *(volatile double*)&st->delta_old;
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->beta = beta_d;
+        cg_update_d_seg_body<T>(3, NL, NL, seg, nseg, d, r, (T)beta_d);
+        grid_barrier(bar);
+    }
 }
 
 }  // namespace fs
@@ -338,7 +516,10 @@ struct fs_visc3d {
     char* coef;      // [7][NL] T
     char* vecs;      // [5][3][NL] T
     uint8_t* mask;   // [3][NL]
-    uint8_t* valid;  // [2][3][NL]
+    uint8_t* valid;  // [3][NL] extrapolation validity generations
+    GridBar* bar;    // grid barrier of the persistent CG kernel
+    int cg_mode;     // FS_CG_AUTO / FS_CG_KERNELS / FS_CG_PERSISTENT
+    bool sparse_clean;   // r,d,q,b are zero outside the segments of the current active list (sparse begin / clear may be used)
     uint8_t* act;    // [NL] computed-row bits
     double* partials;
     CgState* st;
@@ -350,6 +531,9 @@ struct fs_visc3d {
     IterGraph graph; // captured batch of iterations (single GPU and fused multi-GPU transport)
     PeerHot hot;     // by-value copy of the per-point fields of `peers`
     PeerInfo* peers; // device copy; non-null = collectives fused into K1/K2 over peer memory (NVLink), else NCCL per iteration
+    SegList seg;     // sorted list of active 32-point lattice segments (rebuilt by every pack)
+    int active_mode; // FS_ACTIVE_*
+    long long active_rows;   // computed rows of the last pack (host copy, filled lazily)
 };
 
 static Lat3 make_lat3(int nx, int ny, int nz) {
@@ -358,10 +542,11 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     L.X = nx + 1; L.Y = ny + 1; L.Zp = (nz + 1 + 3) / 4 * 4;
     L.sy = L.Zp; L.sx = (long long)L.Y * L.Zp; L.NL = L.sx * L.X;
     L.u_xhi = nx - 1;
+    L.has_lo = 0; L.has_hi = 0;
     return L;
 }
 
-struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, total; int grid_pts; };
+struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, total; int grid_pts; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -375,11 +560,15 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     p += guard;
     o.vecs = p; p = align_up(p + 15 * L.NL * esz, 256) + guard;
     o.mask = p; p = align_up(p + 3 * L.NL, 256);
-    o.valid = p; p = align_up(p + 6 * L.NL, 256);
+    o.valid = p; p = align_up(p + 3 * L.NL, 256);
     o.act = p; p = align_up(p + L.NL + 64, 256);
     size_t np = (size_t)(o.grid_pts > kVecGrid ? o.grid_pts : kVecGrid);
     o.partials = p; p = align_up(p + np * sizeof(double), 256);
     o.st = p; p = align_up(p + sizeof(CgState), 256);
+    // appended after everything the peers address (fs_visc3d_set_peers derives the neighbours' q planes from `vecs`)
+    o.seglist = p; p = align_up(p + SegList::list_bytes(L.NL), 256);
+    o.segscratch = p; p = align_up(p + SegList::scratch_bytes(L.NL), 256);
+    o.bar = p; p = align_up(p + sizeof(GridBar), 256);
     o.total = p;
     return o;
 }
@@ -432,6 +621,7 @@ int fs_visc3d_set_slab(fs_visc3d* h, fs_comm* comm, int has_lo, int has_hi) {
     h->has_lo = has_lo ? 1 : 0;
     h->has_hi = has_hi ? 1 : 0;
     h->L.u_xhi = h->L.nx - 1 - h->has_hi;
+    h->L.has_lo = h->has_lo; h->L.has_hi = h->has_hi;
     h->packed = false;
     h->graph.valid = false;
     return FS_OK;
@@ -488,6 +678,52 @@ int fs_visc3d_peer_error(fs_visc3d* h) {
     return pi.error;
 }
 
+int fs_visc3d_set_cg_mode(fs_visc3d* h, int mode) {
+    if (!h) return fail(FS_ERR_ARG, "null handle");
+    if (mode != FS_CG_AUTO && mode != FS_CG_KERNELS && mode != FS_CG_PERSISTENT) return fail(FS_ERR_ARG, "fs_visc3d_set_cg_mode: bad mode");
+    h->cg_mode = mode;
+    return FS_OK;
+}
+
+int fs_visc3d_set_active_mode(fs_visc3d* h, int mode) {
+    if (!h) return fail(FS_ERR_ARG, "null handle");
+    if (mode != FS_ACTIVE_FLUID && mode != FS_ACTIVE_NONZERO) return fail(FS_ERR_ARG, "fs_visc3d_set_active_mode: bad mode");
+    h->active_mode = mode;
+    h->packed = false;
+    h->graph.valid = false;
+    return FS_OK;
+}
+
+__global__ void visc3d_count_rows_kernel(const uint8_t* act, long long n, unsigned long long* out) {
+    unsigned long long c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        c += __popc((unsigned int)act[i] & fs::kActCompute);
+    c = __reduce_add_sync(0xffffffffu, (unsigned int)c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+int fs_visc3d_active_info(fs_visc3d* h, int64_t* segments, int64_t* segments_total, int64_t* rows, void* stream) {
+    if (!h) return fail(FS_ERR_ARG, "null handle");
+    if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_active_info before fs_visc3d_pack");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (rows) {
+        if (h->active_rows < 0) {       // counted on demand; `partials` is free between solves
+            unsigned long long* tmp = reinterpret_cast<unsigned long long*>(h->partials);
+            FS_CUDA(cudaMemsetAsync(tmp, 0, sizeof(*tmp), s));
+            visc3d_count_rows_kernel<<<kSMs * 4, 256, 0, s>>>(h->act, h->L.NL, tmp);
+            FS_LAUNCH_CHECK();
+            unsigned long long host = 0;
+            FS_CUDA(cudaMemcpyAsync(&host, tmp, sizeof(host), cudaMemcpyDeviceToHost, s));
+            FS_CUDA(cudaStreamSynchronize(s));
+            h->active_rows = (long long)host;
+        }
+        *rows = h->active_rows;
+    }
+    if (segments) *segments = h->seg.nseg;
+    if (segments_total) *segments_total = h->seg.nseg_total;
+    return FS_OK;
+}
+
 size_t fs_visc3d_workspace_bytes(int nx, int ny, int nz, int dtype) {
     if (nx < 1 || ny < 1 || nz < 1 || (dtype != FS_F32 && dtype != FS_F64)) return 0;
     Lat3 L = make_lat3(nx, ny, nz);
@@ -509,15 +745,21 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->coef = h->ws + lay.coef; h->vecs = h->ws + lay.vecs;
     h->mask = (uint8_t*)(h->ws + lay.mask); h->valid = (uint8_t*)(h->ws + lay.valid); h->act = (uint8_t*)(h->ws + lay.act);
     h->partials = (double*)(h->ws + lay.partials); h->st = (CgState*)(h->ws + lay.st);
+    h->bar = (GridBar*)(h->ws + lay.bar);
+    h->cg_mode = FS_CG_AUTO;
+    h->sparse_clean = true;          // the workspace is zeroed below and the list is empty
     h->grid_pts = lay.grid_pts;
     h->packed = false;
     h->comm = nullptr; h->has_lo = 0; h->has_hi = 0; h->peers = nullptr;
+    h->active_mode = FS_ACTIVE_NONZERO; h->active_rows = -1;
     memset(&h->hot, 0, sizeof(h->hot));
     int s = h->cg.init();
     if (s < 0) { delete h; return s; }
+    s = h->seg.init(h->L.NL, h->ws + lay.seglist, h->ws + lay.segscratch);
+    if (s < 0) { h->cg.destroy(); delete h; return s; }
     h->cg.st_dev = h->st; h->cg.partials_dev = h->partials;
     cudaError_t e = cudaMemset(ws, 0, lay.total);     // cp.zeros semantics for every solver vector
-    if (e != cudaSuccess) { h->cg.destroy(); delete h; return fail(FS_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { h->cg.destroy(); h->seg.destroy(); delete h; return fail(FS_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
     *out = h;
     return FS_OK;
 }
@@ -527,6 +769,7 @@ void fs_visc3d_destroy(fs_visc3d* h) {
     if (h->peers) cudaFree(h->peers);
     h->graph.destroy();
     h->cg.destroy();
+    h->seg.destroy();
     delete h;
 }
 
@@ -547,8 +790,26 @@ void* fs_visc3d_vector_ptr(const fs_visc3d* h, int vec, int comp) {
 int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double vol_norm, void* stream) {
     if (!h || !sphi || !lvol) return fail(FS_ERR_ARG, "fs_visc3d_pack: null argument");
     cudaStream_t s = (cudaStream_t)stream;
+    // keep "r, d, q, b are zero outside the active segments": wipe the previous solve's active segments (or everything,
+    // if a dense API call wrote into those vectors since)
+    if (h->sparse_clean) {
+        if (h->seg.nseg > 0) {
+            const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 8);
+            FS_DISPATCH(h, visc3d_clear_kernel<T><<<grid, kThreads, 0, s>>>(h->L.NL, reinterpret_cast<T*>(h->vecs), h->seg.list, h->seg.nseg_dev));
+            FS_LAUNCH_CHECK();
+        }
+    } else {
+        FS_CUDA(cudaMemsetAsync(h->vecs + (size_t)FS_VEC_R * 3 * h->L.NL * h->esz, 0, (size_t)12 * h->L.NL * h->esz, s));
+        h->sparse_clean = true;
+    }
     FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act));
     FS_LAUNCH_CHECK();
+    if (h->active_mode == FS_ACTIVE_NONZERO) {
+        FS_DISPATCH(h, visc3d_activity_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(h->L, reinterpret_cast<const T*>(h->coef), h->act));
+        FS_LAUNCH_CHECK();
+    }
+    FS_TRY(h->seg.build(h->act, s));      // one host sync per solve: the list length sizes the CG launches
+    h->active_rows = -1;
     h->packed = true;
     return FS_OK;
 }
@@ -556,6 +817,7 @@ int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double 
 int fs_visc3d_load(fs_visc3d* h, int vec, const void* vx, const void* vy, const void* vz, int src_dtype, void* stream) {
     if (!h || !vx || !vy || !vz) return fail(FS_ERR_ARG, "fs_visc3d_load: null argument");
     if (vec < 0 || vec >= FS_NUM_VECS) return fail(FS_ERR_ARG, "fs_visc3d_load: bad vector id");
+    if (vec != FS_VEC_X) h->sparse_clean = false;
     cudaStream_t s = (cudaStream_t)stream;
     if (src_dtype == FS_F32) {
         FS_DISPATCH(h, visc3d_load_kernel<T, float><<<h->grid_pts, kThreads, 0, s>>>(h->L, (const float*)vx, (const float*)vy, (const float*)vz, vec_ptr<T>(h, vec)));
@@ -585,25 +847,19 @@ int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_extrapolate: call fs_visc3d_pack first");
     if (vec < 0 || vec >= FS_NUM_VECS) return fail(FS_ERR_ARG, "fs_visc3d_extrapolate: bad vector id");
+    if (sweeps > 250) return fail(FS_ERR_ARG, "fs_visc3d_extrapolate: at most 250 sweeps");
     if (sweeps <= 0) return FS_OK;
+    if (vec != FS_VEC_X) h->sparse_clean = false;
     cudaStream_t s = (cudaStream_t)stream;
-    const int scratch = (vec == FS_VEC_R) ? FS_VEC_D : FS_VEC_R;   // both are fully rewritten at CG start
     const long long NL3 = 3 * h->L.NL;
-    FS_CUDA(cudaMemcpyAsync(h->valid, h->mask, NL3, cudaMemcpyDeviceToDevice, s));   // valid0 = (sphi >= 0)  (:479-481)
-    int cur = 0;
-    for (int k = 0; k < sweeps; ++k) {
-        FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(
-            h->L, vec_ptr<T>(h, cur == 0 ? vec : scratch), h->valid + (size_t)cur * NL3,
-            vec_ptr<T>(h, cur == 0 ? scratch : vec), h->valid + (size_t)(cur ^ 1) * NL3));
+    FS_CUDA(cudaMemcpyAsync(h->valid, h->mask, NL3, cudaMemcpyDeviceToDevice, s));   // generation 1 = (sphi >= 0)  (:479-481)
+    for (int k = 1; k <= sweeps; ++k) {
+        FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k));
         FS_LAUNCH_CHECK();
-        cur ^= 1;
-        if (h->comm) {   // the sweep is Jacobi over the GLOBAL grid: refresh the halo planes of the new values and flags
-            FS_TRY(visc3d_halo_vec(h, cur == 0 ? vec : scratch, s));
-            FS_TRY(visc3d_halo(h, (char*)(h->valid + (size_t)cur * NL3), 1, COMM_U8, s));
+        if (h->comm) {   // the sweep is Jacobi over the GLOBAL grid: refresh the halo planes of the new values and generations
+            FS_TRY(visc3d_halo_vec(h, vec, s));
+            FS_TRY(visc3d_halo(h, (char*)h->valid, 1, COMM_U8, s));
         }
-    }
-    if (cur == 1) {  // result sits in scratch
-        FS_CUDA(cudaMemcpyAsync(h->vecs + (size_t)vec * NL3 * h->esz, h->vecs + (size_t)scratch * NL3 * h->esz, NL3 * h->esz, cudaMemcpyDeviceToDevice, s));
     }
     return FS_OK;
 }
@@ -623,34 +879,33 @@ static int visc3d_general(fs_visc3d* h, double scale, double mu, int src, int ds
 
 int fs_visc3d_rhs(fs_visc3d* h, double scale, double mu, int src_vec, int dst_vec, void* stream) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
+    h->sparse_clean = false;
     return visc3d_general(h, scale, mu, src_vec, dst_vec, ROW_RHS, (cudaStream_t)stream);
 }
 
 int fs_visc3d_apply(fs_visc3d* h, double scale, double mu, int src_vec, int dst_vec, void* stream) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
+    h->sparse_clean = false;
     return visc3d_general(h, scale, mu, src_vec, dst_vec, ROW_APPLY, (cudaStream_t)stream);
 }
 
 static int visc3d_k1(fs_visc3d* h, double sm, cudaStream_t s) {
-    long long want = (h->L.NL + kK1Threads - 1) / kK1Threads;
-    const long long cap = (long long)kSMs * (h->dtype == FS_F32 ? K1Occ<float>::value : K1Occ<double>::value);
-    const int grid = (int)(want < cap ? want : cap);
+    const int cap = kSMs * (h->dtype == FS_F32 ? K1Occ<float>::value : K1Occ<double>::value);
+    const int grid = seg_grid(h->seg.nseg, kK1SegsPerBlock, cap);
     if (h->peers) {
-        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, h->peers, h->hot));
+        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->seg.list, h->seg.nseg_dev, h->st, h->partials, h->peers, h->hot));
     } else {
-        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, nullptr, h->hot));
+        FS_DISPATCH(h, visc3d_apply_dot_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot));
     }
     FS_LAUNCH_CHECK();
     return FS_OK;
 }
 static int visc3d_k2(fs_visc3d* h, cudaStream_t s, int freeze = 0) {
-    const long long n = 3 * h->L.NL;
-    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr<T>(n, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s, freeze, h->peers, h->peers ? &h->hot : nullptr)));
+    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr_seg<T>(3, h->L.NL, h->L.NL, h->seg, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s, freeze, h->peers, h->peers ? &h->hot : nullptr)));
     return FS_OK;
 }
 static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
-    const long long n = 3 * h->L.NL;
-    FS_DISPATCH(h, FS_TRY(cg_launch_update_d<T>(n, vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, s)));
+    FS_DISPATCH(h, FS_TRY(cg_launch_update_d_seg<T>(3, h->L.NL, h->L.NL, h->seg, vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, s)));
     return FS_OK;
 }
 
@@ -677,9 +932,80 @@ static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
 }
 
 // NCCL calls are not captured: graphs are used on a single GPU and with the fused peer-memory transport only
+// Persistent whole-iteration kernel: used when the per-iteration work is small enough that launch gaps and kernel
+// ramp-up/tails matter (FLUIDSOLVER_B200_PERSISTENT=0/1 forces it off/on; default: CG working set <= 256 MB).
+// Not with the NCCL transport (host-launched collectives between the phases).
+static bool visc3d_use_persistent(const fs_visc3d* h) {
+    if (h->comm && !h->peers) return false;
+    if (h->cg_mode == FS_CG_KERNELS) return false;
+    if (h->cg_mode == FS_CG_PERSISTENT) return true;
+    static int mode = -2;
+    if (mode == -2) {
+        const char* e = getenv("FLUIDSOLVER_B200_PERSISTENT");
+        mode = !e ? -1 : (e[0] == '0' ? 0 : 1);
+    }
+    if (mode >= 0) return mode == 1;
+    const double ws = (double)h->seg.nseg * kSegPts * (22.0 * h->esz + 1.0);
+    return ws <= 256e6;
+}
+
+static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
+    const int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, kSMs);
+    while (n > 0) {
+        int ni = (int)(n < (1 << 20) ? n : (1 << 20));
+        cudaError_t e = cudaSuccess;
+        FS_DISPATCH(h, {
+            Visc3Dev<T> P = dev_view<T>(h);
+            T sv = (T)sm, s2v = (T)(2 * sm);
+            T* x = vec_ptr<T>(h, FS_VEC_X); T* r = vec_ptr<T>(h, FS_VEC_R); T* d = vec_ptr<T>(h, FS_VEC_D); T* q = vec_ptr<T>(h, FS_VEC_Q);
+            const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
+            CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
+            PeerInfo* peers = h->peers; PeerHot hot = h->hot;
+            void* args[] = {&P, &sv, &s2v, &x, &r, &d, &q, &seg, &nsegp, &st, &partials, &bar, &ni, &peers, &hot};
+            const void* fn = h->peers ? (const void*)visc3d_cg_persistent_kernel<T, true> : (const void*)visc3d_cg_persistent_kernel<T, false>;
+            e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args, 0, s);
+        });
+        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
+        FS_LAUNCH_CHECK();
+        n -= ni;
+    }
+    return FS_OK;
+}
+
 static int visc3d_iterations(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
+    if (visc3d_use_persistent(h)) return visc3d_persistent(h, sm, n, s);
     const bool graph_ok = !(h->comm && !h->peers);
-    return cg_enqueue_iterations(h->graph, graph_ok, sm, n, [&](cudaStream_t ss) { return visc3d_iteration(h, sm, ss); }, s);
+    return cg_enqueue_iterations(h->graph, graph_ok, sm, n, [&](cudaStream_t ss) { return visc3d_iteration(h, sm, ss); }, s, seg_level(h->seg.nseg));
+}
+
+// Start of a solve on the active set (fs_visc3d_solve): one kernel builds b, q = A x, d = r = b - q and delta0.
+static int visc3d_cg_begin_sparse(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, cudaStream_t s) {
+    const double sm = scale * mu;
+    cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, (h->comm && !h->peers) ? 1 : 0);
+    FS_LAUNCH_CHECK();
+    FS_CUDA(cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s));
+    if (h->peers) {   // belt and braces: the halo planes of q must read as zero until the neighbours store into them
+        for (int c = 0; c < 3; ++c) {
+            char* comp = h->vecs + ((size_t)FS_VEC_Q * 3 + c) * h->L.NL * h->esz;
+            if (h->has_lo) FS_CUDA(cudaMemsetAsync(comp, 0, (size_t)h->L.sx * h->esz, s));
+            if (h->has_hi) FS_CUDA(cudaMemsetAsync(comp + (size_t)(h->L.X - 2) * h->L.sx * h->esz, 0, (size_t)h->L.sx * h->esz, s));
+        }
+    }
+    const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 4);
+    FS_DISPATCH(h, visc3d_begin_kernel<T><<<grid, kThreads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_B),
+                                                                  vec_ptr<T>(h, FS_VEC_Q), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D),
+                                                                  h->seg.list, h->seg.nseg_dev, h->st, h->partials, h->peers));
+    FS_LAUNCH_CHECK();
+    if (h->comm && !h->peers) {
+        FS_TRY(comm_allreduce_sum_f64(h->comm, &h->st->red, 1, s));
+        cg_finish_kernel<<<1, 1, 0, s>>>(h->st, 0);
+        FS_LAUNCH_CHECK();
+    }
+    if (h->peers) {   // one-time: halo rows of r and d (the fused iteration keeps them current from here on)
+        FS_TRY(visc3d_halo_vec(h, FS_VEC_R, s));
+        FS_TRY(visc3d_halo_vec(h, FS_VEC_D, s));
+    }
+    return FS_OK;
 }
 
 static int visc3d_cg_begin(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, cudaStream_t s) {
@@ -713,9 +1039,12 @@ int fs_visc3d_cg(fs_visc3d* h, double scale, double mu, double tol, int64_t max_
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if (max_iter < 0) return fail(FS_ERR_ARG, "fs_visc3d_cg: max_iter < 0");
     cudaStream_t s = (cudaStream_t)stream;
+    h->sparse_clean = false;                      // dense begin: q, r, d are rewritten everywhere
+    FS_CUDA(cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s));
     FS_TRY(visc3d_cg_begin(h, scale, mu, tol, max_iter, s));
     const double sm = scale * mu;
-    return cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter, stats, s);
+    return cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter, stats, s,
+                    visc3d_use_persistent(h) ? kCgBatchPersistent : kCgBatch);
 }
 
 int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void* stream) {
@@ -758,15 +1087,31 @@ int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_
                     void* vx, void* vy, void* vz, int vel_dtype, const double* sphi, const double* lvol,
                     double tol, int64_t max_iter, fs_cg_stats* stats, void* stream) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
+    if (max_iter < 0) return fail(FS_ERR_ARG, "fs_visc3d_solve: max_iter < 0");
+    if (vel_dtype != FS_F32 && vel_dtype != FS_F64) return fail(FS_ERR_ARG, "fs_visc3d_solve: bad velocity dtype");
+    cudaStream_t s = (cudaStream_t)stream;
     const double scale = dt / cell_vol / rho;                                   // :567
-    FS_TRY(fs_visc3d_pack(h, sphi, lvol, cell_vol * 0.125, stream));            // :568
+    const double sm = scale * mu;
+    FS_TRY(fs_visc3d_pack(h, sphi, lvol, cell_vol * 0.125, stream));            // :568 (+ active segment list)
     FS_TRY(fs_visc3d_load(h, FS_VEC_X, vx, vy, vz, vel_dtype, stream));         // :569-571
     FS_TRY(fs_visc3d_extrapolate(h, FS_VEC_X, 3, stream));                      // :573
-    FS_TRY(fs_visc3d_rhs(h, scale, mu, FS_VEC_X, FS_VEC_B, stream));            // :574
-    int status = fs_visc3d_cg(h, scale, mu, tol, max_iter, stats, stream);      // :575-612
+    FS_TRY(visc3d_cg_begin_sparse(h, scale, mu, tol, max_iter, s));             // :574-587 on the active set
+    int status = cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter, stats, s,
+                          visc3d_use_persistent(h) ? kCgBatchPersistent : kCgBatch);   // :588-612
     if (status != FS_OK) return status;                                         // the reference raises before write-back
-    FS_TRY(fs_visc3d_store(h, FS_VEC_X, vx, vy, vz, vel_dtype, FS_STORE_FLUID, stream));   // :613
-    FS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (h->dtype == FS_F64 || vel_dtype == FS_F32) {
+        // :613 — only rows of the active set can differ from what was loaded from these very arrays
+        const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 4);
+        if (vel_dtype == FS_F32) {
+            FS_DISPATCH(h, visc3d_store_active_kernel<T, float><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (float*)vx, (float*)vy, (float*)vz));
+        } else {
+            FS_DISPATCH(h, visc3d_store_active_kernel<T, double><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (double*)vx, (double*)vy, (double*)vz));
+        }
+        FS_LAUNCH_CHECK();
+    } else {   // fp32 solver storage with fp64 caller arrays: every fluid face is rounded through fp32, as before
+        FS_TRY(fs_visc3d_store(h, FS_VEC_X, vx, vy, vz, vel_dtype, FS_STORE_FLUID, stream));
+    }
+    FS_CUDA(cudaStreamSynchronize(s));
     return FS_OK;
 }
 

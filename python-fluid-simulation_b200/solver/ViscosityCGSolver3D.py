@@ -96,6 +96,23 @@ class _Engine:
         return flat.view(X, Y, Zp)[: sh[0], : sh[1], : sh[2]]
 
     # thin wrappers -----------------------------------------------------------------------------
+    def set_active_mode(self, mode):
+        code = {"nonzero": N.ACTIVE_NONZERO, "fluid": N.ACTIVE_FLUID}.get(mode)
+        if code is None:
+            raise ValueError("active_set must be 'nonzero' or 'fluid'")
+        N.check(self.lib.fs_visc3d_set_active_mode(self.h, code), "fs_visc3d_set_active_mode")
+
+    def set_cg_mode(self, mode):
+        code = {"auto": N.CG_AUTO, "kernels": N.CG_KERNELS, "persistent": N.CG_PERSISTENT}.get(mode)
+        if code is None:
+            raise ValueError("cg_mode must be 'auto', 'kernels' or 'persistent'")
+        N.check(self.lib.fs_visc3d_set_cg_mode(self.h, code), "fs_visc3d_set_cg_mode")
+
+    def active_info(self):
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        N.check(self.lib.fs_visc3d_active_info(self.h, a, b, c, A.stream_ptr()), "fs_visc3d_active_info")
+        return a.value, b.value, c.value
+
     def pack(self, sphi, lvol, vol_norm):
         N.check(self.lib.fs_visc3d_pack(self.h, sphi.ptr, lvol.ptr, float(vol_norm), A.stream_ptr()), "fs_visc3d_pack")
 
@@ -198,7 +215,11 @@ def apply_viscosity(gres, vx, vy, vz, out_x, out_y, out_z, sphi, sv, dtype=None)
 class ViscosityCGSolver3D:
     """Implicit variational viscosity step on a 3-D MAC grid, plain CG (reference :532-613)."""
 
-    def __init__(self, gres, bound_size, dtype=torch.float64):
+    def __init__(self, gres, bound_size, dtype=torch.float64, active_set="nonzero", cg_mode="auto"):
+        """``active_set`` (extra, not in the reference): which rows the CG kernels visit — "nonzero" (default; rows
+        with at least one non-zero coefficient) or "fluid" (every row the reference computes).  ``cg_mode``: "auto",
+        "kernels" (three kernels per iteration from a CUDA graph) or "persistent" (one cooperative launch runs whole
+        iterations).  Results are identical up to reduction-order rounding."""
         self.gres = gres
         self._g = A.to_host_ints(gres)
         if len(self._g) != 3:
@@ -207,6 +228,8 @@ class ViscosityCGSolver3D:
         self.cell_vol = float(np.prod(self.cell_size))                                            # :536
         self._code = _DT[dtype]
         self._e = _Engine(self._g, self._code)
+        self._e.set_active_mode(active_set)
+        self._e.set_cg_mode(cg_mode)
         for vec, nm in ((N.VEC_D, "d"), (N.VEC_R, "r"), (N.VEC_Q, "q"), (N.VEC_X, "x"), (N.VEC_B, "b")):
             for c, ax in enumerate("xyz"):
                 setattr(self, f"{nm}_{ax}", self._e.view(vec, c))
@@ -219,6 +242,10 @@ class ViscosityCGSolver3D:
     @property
     def dtype(self):
         return _TORCH[self._code]
+
+    def active_info(self):
+        """(active 32-point segments, segments in the lattice, computed rows) of the last solve's operator."""
+        return self._e.active_info()
 
     def solve(self, dt, mu, rho, vx, vy, vz, sphi, sv, lphi, lvol, tol=1e-3):
         """In-place implicit viscosity update of vx,vy,vz (reference :566-613).

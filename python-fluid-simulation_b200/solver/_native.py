@@ -15,6 +15,8 @@ FS_F32 = 0
 FS_F64 = 1
 VEC_X, VEC_R, VEC_D, VEC_Q, VEC_B = range(5)
 STORE_ALL, STORE_INTERIOR, STORE_FLUID = range(3)
+ACTIVE_FLUID, ACTIVE_NONZERO = range(2)
+CG_AUTO, CG_KERNELS, CG_PERSISTENT = range(3)
 
 
 class CgStats(Structure):
@@ -39,6 +41,9 @@ _SIGS = {
     "fs_visc3d_destroy": (None, [c_void_p]),
     "fs_visc3d_lattice": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
     "fs_visc3d_vector_ptr": (c_void_p, [c_void_p, c_int, c_int]),
+    "fs_visc3d_set_active_mode": (c_int, [c_void_p, c_int]),
+    "fs_visc3d_set_cg_mode": (c_int, [c_void_p, c_int]),
+    "fs_visc3d_active_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), c_void_p]),
     "fs_visc3d_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
     "fs_visc3d_load": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "fs_visc3d_store": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -54,6 +54,22 @@ def plane_cost_from_sphi(sphi, gres, fluid_weight=1.0):
     return 1.0 + fluid_weight * frac
 
 
+def plane_cost_active(sphi, lvol, gres, active_set="nonzero", cg_weight=20.0):
+    """Relative cost of each x-plane of cells with the active-set CG kernels: the once-per-solve passes (pack, load,
+    extrapolation, RHS) stream every plane alike (cost 1), the CG iterations only touch active rows (cg_weight x the
+    plane's active fraction; ~20 for a few hundred iterations on B200).  The active fraction is estimated from the inputs:
+    "fluid": cell centres with sphi >= 0; "nonzero": fine-grid nodes of the plane's three fine layers with lvol != 0."""
+    g = tuple(int(n) for n in gres)
+    if active_set == "fluid":
+        centres = sphi[1::2, 1::2, 1::2][: g[0], : g[1], : g[2]]
+        frac = (centres >= 0).to(torch.float64).mean(dim=(1, 2))
+    else:
+        nz = (lvol != 0).to(torch.float64).mean(dim=(1, 2))          # per fine x-layer
+        frac = (nz[0:-1:2] + nz[1::2] + nz[2::2]) / 3.0
+        frac = torch.clamp(frac * 2.0, max=1.0)                        # one-node dilation of the non-zero set
+    return 1.0 + cg_weight * frac.cpu().numpy()
+
+
 class SlabPartition:
     """x-slabs.  ``[c0, c1)`` = owned cells, ``[e0, e1)`` = extended cells held locally.  With ``plane_cost`` (one
     relative cost per x-plane of cells) the cuts equalise the summed cost instead of the cell count."""
@@ -124,7 +140,7 @@ def get_comm(group=None):
 class SlabViscosityCGSolver3D:
     """Multi-GPU counterpart of ViscosityCGSolver3D: same ``solve()`` argument list, per-rank extended slabs."""
 
-    def __init__(self, gres, bound_size, dtype=torch.float64, group=None, transport=None, partition=None):
+    def __init__(self, gres, bound_size, dtype=torch.float64, group=None, transport=None, partition=None, active_set="nonzero", cg_mode="auto"):
         """partition: a SlabPartition (e.g. cost-balanced); default = equal cell counts.
         transport: "p2p" (default; collectives fused into the kernels over CUDA-IPC peer memory, one NVSwitch box)
         or "nccl" (one NCCL halo exchange + two NCCL all-reduces per iteration; also the fallback if IPC is unavailable)."""
@@ -143,6 +159,8 @@ class SlabViscosityCGSolver3D:
         self._code = _DT[dtype]
         self.transport = transport
         self._e = _Engine(self.part.local_gres, self._code, shared=(transport == "p2p"))
+        self._e.set_active_mode(active_set)
+        self._e.set_cg_mode(cg_mode)
         self._comm = get_comm(group)
         N.check(self._e.lib.fs_visc3d_set_slab(self._e.h, self._comm, int(self.part.has_lo), int(self.part.has_hi)), "fs_visc3d_set_slab")
         self._mapped = []
@@ -256,12 +274,14 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
     g = (n, n, n)
     full = scenes.buckling(n, device="cuda", mu=args.mu)
     balance = os.environ.get("FLUIDSOLVER_B200_BALANCE", "1") != "0"
-    part = SlabPartition(g, world, rank, plane_cost=plane_cost_from_sphi(full["sphi"], g) if balance else None)
+    aset = getattr(args, "active_set", "nonzero")
+    part = SlabPartition(g, world, rank, plane_cost=plane_cost_active(full["sphi"], full["lvol"], g, aset) if balance else None)
     sc = scatter_scene(full, part)
     bound = full["bound_size"]
     del full
     torch.cuda.empty_cache()
-    solver = SlabViscosityCGSolver3D(g, bound, dtype=tdtype, partition=part)
+    solver = SlabViscosityCGSolver3D(g, bound, dtype=tdtype, partition=part, active_set=getattr(args, "active_set", "nonzero"),
+                                     cg_mode=getattr(args, "cg_mode", "auto"))
     config = dict(config, transport=solver.transport, slab_starts=part.starts, balanced=balance)
     solver.max_iter = args.iters
     dev_in = [sc[k] for k in ("vx", "vy", "vz")]
@@ -321,9 +341,9 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
     lib = solver._e.lib
     scale = sc["dt"] / solver.cell_vol / sc["rho"]
     stream = torch.cuda.current_stream().cuda_stream
-    frac_local = (part.e1 - part.e0 + 1) / (n + 1)
-    kbytes = {"K1 visc3d_apply_dot": (2 * F + V7) * esz * frac_local, "K2 cg_update_xr": 6 * F * esz * frac_local,
-              "K3 cg_update_d": 3 * F * esz * frac_local}
+    segs, segs_total, rows = solver._e.active_info()
+    pts = segs * 32
+    kbytes = {"K1 visc3d_apply_dot": pts * (13 * esz + 1), "K2 cg_update_xr": pts * 18 * esz, "K3 cg_update_d": pts * 9 * esz}
     kern = {}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for which, name in ((1, "K1 visc3d_apply_dot"), (2, "K2 cg_update_xr"), (3, "K3 cg_update_d")):
@@ -349,7 +369,9 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
             "gpu_launches": int(tot[2].item()),
             "roofline": {"bound": "hbm", "kernel": dom + " (rank 0 slab)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "per_kernel_ms": kern,
-                         "iteration": {"algorithmic_GB_per_iter": words_iter * esz / 1e9, "achieved_GBps_all_gpus": iter_gbs,
+                         "active_set": {"mode": getattr(args, "active_set", "nonzero"), "segments_rank0": segs, "segments_total_rank0": segs_total,
+                                        "computed_rows_rank0": rows},
+                         "dense_equivalent": {"algorithmic_GB_per_iter": words_iter * esz / 1e9, "achieved_GBps_all_gpus": iter_gbs,
                                        "frac_of_aggregate_peak": iter_gbs / (peak * world)}},
             "clocks": clocks.summary(),
         }

@@ -23,15 +23,18 @@ def main():
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
 
     ok = True
-    cases = [(24, 10.0, torch.float64, None, "nccl"), (24, 10.0, torch.float64, None, "p2p"),
-             (32, 100.0, torch.float64, (37, 24, 28), "p2p"), (32, 100.0, torch.float32, None, "p2p"),
-             (32, 100.0, torch.float64, (37, 24, 28), "nccl")]
-    for N, mu, dtype, g, transport in cases:
+    # (N, mu, dtype, gres, transport, cg_mode, active_set)
+    cases = [(24, 10.0, torch.float64, None, "nccl", "auto", "nonzero"), (24, 10.0, torch.float64, None, "p2p", "persistent", "nonzero"),
+             (24, 10.0, torch.float64, None, "p2p", "kernels", "fluid"),
+             (32, 100.0, torch.float64, (37, 24, 28), "p2p", "persistent", "fluid"), (32, 100.0, torch.float64, (37, 24, 28), "p2p", "kernels", "nonzero"),
+             (32, 100.0, torch.float32, None, "p2p", "auto", "nonzero"),
+             (32, 100.0, torch.float64, (37, 24, 28), "nccl", "auto", "fluid")]
+    for N, mu, dtype, g, transport, cg_mode, aset in cases:
         full = scenes.buckling(N, device="cuda", mu=mu, gres=g)
         gres = full["gres"]
         part = SlabPartition(gres, world, rank)
         sc = scatter_scene(full, part)
-        s = SlabViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype, transport=transport)
+        s = SlabViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype, transport=transport, cg_mode=cg_mode, active_set=aset)
         v = [sc[k].clone() for k in ("vx", "vy", "vz")]
         s.solve(full["dt"], mu, full["rho"], *v, sc["sphi"], None, None, sc["lvol"])
         its = torch.tensor([s.iterations], device="cuda")
@@ -57,7 +60,7 @@ def main():
             shp_ok = all(a.shape == b.shape for a, b in zip(pieces, rv))
             good = same_it and it_ok and shp_ok and max(errs) < 1e-4
             ok = ok and good
-            print(f"[dist_check] {transport} gres={gres} mu={mu} {dtype}: world={world} iters={s.iterations} (single-GPU {ref.iterations}) "
+            print(f"[dist_check] {transport}/{cg_mode}/{aset} gres={gres} mu={mu} {dtype}: world={world} iters={s.iterations} (single-GPU {ref.iterations}) "
                   f"lockstep={same_it} rel_l2={['%.2e' % e for e in errs]} -> {'OK' if good else 'MISMATCH'}", flush=True)
         dist.barrier()
         s.close()

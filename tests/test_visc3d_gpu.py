@@ -86,7 +86,8 @@ def test_solve_vs_reference(tag, dtype):
     sv = torch.zeros(tuple(f["sphi"].shape) + (3,), dtype=torch.float64, device="cuda")
     s.solve(float(f["dt"]), float(f["mu"]), float(f["rho"]), *v, _dev(f["sphi"]), sv, _dev(f["lphi"]), _dev(f["lvol"]), tol=float(f["tol"]))
     it_ref = int(f["iterations"])
-    # fp64 (the default, benchmarked mode) holds the +-2 % iteration bar — in fact it is exact here.  fp32 STORAGE
+    # fp64 (the default, benchmarked mode) holds the +-2 % iteration bar — within one iteration here (the count moves
+    # by one with the reduction order, which differs between the dense, active-set and persistent kernels).  fp32 STORAGE
     # drifts on these tiny near-singular systems (63 vs 61, 103 vs 95 iterations; reproduced bit-for-bit by a NumPy
     # emulation, and caused by the fp32 operator, not by the reductions): it still meets the 1e-4 velocity bar but
     # not the iteration bar, which is why it is opt-in.  See DESIGN.md "Precision".
@@ -104,7 +105,7 @@ def test_solve_vs_reference(tag, dtype):
     # ~2e-6 relative (measured with the oracle), so 1e-4 is the meaningful bar even for the fp64 path; the CG
     # trajectory is only reproducible to reduction-order rounding (SURVEY §8c "Third-party arithmetic").
     if dtype == torch.float64:
-        assert s.iterations == it_ref
+        assert abs(s.iterations - it_ref) <= 1
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
