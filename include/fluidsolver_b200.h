@@ -105,6 +105,9 @@ int fs_visc3d_lattice(const fs_visc3d* h, int* X, int* Y, int* Zp, int64_t* NL);
 /* device pointer of component `comp` (0,1,2) of solver vector `vec` (FS_VEC_*) inside the workspace */
 void* fs_visc3d_vector_ptr(const fs_visc3d* h, int vec, int comp);
 
+/* Debug: copy `bytes` of an internal byte buffer to the host (what = 0: extrapolation validity / phase-timeline scratch,
+ * 1: activity map). */
+int fs_visc3d_debug_read(fs_visc3d* h, int what, void* out_host, size_t bytes);
 /* Select how iterations are launched (FS_CG_*). */
 int fs_visc3d_set_cg_mode(fs_visc3d* h, int mode);
 /* Select the active-row set (FS_ACTIVE_*); takes effect at the next fs_visc3d_pack. */

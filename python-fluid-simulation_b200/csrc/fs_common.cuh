@@ -414,42 +414,48 @@ template <typename T> struct Vec2;
 template <> struct Vec2<float> { using type = float2; };
 template <> struct Vec2<double> { using type = double2; };
 
-// K2 on the active set (same arithmetic as cg_update_xr_kernel).  `ncomp` component arrays of `comp_stride` elements
-// follow each other in x,r,d,q; a point index p of the list addresses element c*comp_stride + p of component c.
+// K2 on the active set (same arithmetic as cg_update_xr_kernel).  NCOMP component arrays of `comp_stride` elements
+// follow each other in x,r,d,q; a point index p of the list addresses element c*comp_stride + p of component c.  A
+// half-warp takes one segment and moves all NCOMP components of it at once (4*NCOMP 16-byte loads in flight per lane).
 // Returns this thread's share of r.r (owned rows only when DIST).  No __restrict__/__ldg on the vectors: the same body
 // runs inside the persistent whole-iteration kernel, where other CTAs rewrite them between grid barriers.
-template <typename T, bool DIST>
-__device__ __forceinline__ double cg_update_xr_seg_body(int ncomp, long long comp_stride, long long npts, const int* __restrict__ seg, int nseg,
+template <typename T, int NCOMP, bool DIST>
+__device__ __forceinline__ double cg_update_xr_seg_body(long long comp_stride, long long npts, const int* __restrict__ seg, int nseg,
                                                         T* x, T* r, const T* d, const T* q, T alpha, const PeerHot& hot) {
     using V = typename Vec2<T>::type;
     const int hl = threadIdx.x & 15;
     const long long hw0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const long long nhw = ((long long)gridDim.x * blockDim.x) >> 4;
     double acc = 0.0;
-    for (int c = 0; c < ncomp; ++c) {
-        const long long base = (long long)c * comp_stride + 2 * hl;
-        long long j = hw0;
-        int sg = j < nseg ? __ldg(seg + j) : 0;
-        while (j < nseg) {
-            const long long p = (long long)sg * kSegPts + 2 * hl;
-            const long long e = base + (long long)sg * kSegPts;
-            j += nhw;
-            sg = j < nseg ? __ldg(seg + j) : 0;           // next segment id requested before this one's data
-            if (p >= npts) continue;                      // tail of the last segment (npts is even)
-            V xv = *reinterpret_cast<const V*>(x + e);
-            V rv = *reinterpret_cast<const V*>(r + e);
-            const V dv = *reinterpret_cast<const V*>(d + e);
-            const V qv = *reinterpret_cast<const V*>(q + e);
+    long long j = hw0;
+    int sg = j < nseg ? __ldg(seg + j) : 0;
+    while (j < nseg) {
+        const long long p = (long long)sg * kSegPts + 2 * hl;
+        j += nhw;
+        sg = j < nseg ? __ldg(seg + j) : 0;           // next segment id requested before this one's data
+        if (p >= npts) continue;                      // tail of the last segment (npts is even)
+        V xv[NCOMP], rv[NCOMP], dv[NCOMP], qv[NCOMP];
+#pragma unroll
+        for (int c = 0; c < NCOMP; ++c) {
+            const long long e = (long long)c * comp_stride + p;
+            xv[c] = *reinterpret_cast<const V*>(x + e);
+            rv[c] = *reinterpret_cast<const V*>(r + e);
+            dv[c] = *reinterpret_cast<const V*>(d + e);
+            qv[c] = *reinterpret_cast<const V*>(q + e);
+        }
+#pragma unroll
+        for (int c = 0; c < NCOMP; ++c) {
+            const long long e = (long long)c * comp_stride + p;
             bool own = true;
             if (DIST) {
 #pragma unroll
                 for (int k = 0; k < 6; ++k) own = own && !(e >= hot.hb[k] && e < hot.he[k]);
             }
-            xv.x = xv.x + alpha * dv.x; xv.y = xv.y + alpha * dv.y;
-            rv.x = rv.x - alpha * qv.x; rv.y = rv.y - alpha * qv.y;
-            if (own) acc += (double)rv.x * (double)rv.x + (double)rv.y * (double)rv.y;
-            *reinterpret_cast<V*>(x + e) = xv;
-            *reinterpret_cast<V*>(r + e) = rv;
+            xv[c].x = xv[c].x + alpha * dv[c].x; xv[c].y = xv[c].y + alpha * dv[c].y;
+            rv[c].x = rv[c].x - alpha * qv[c].x; rv[c].y = rv[c].y - alpha * qv[c].y;
+            if (own) acc += (double)rv[c].x * (double)rv[c].x + (double)rv[c].y * (double)rv[c].y;
+            *reinterpret_cast<V*>(x + e) = xv[c];
+            *reinterpret_cast<V*>(r + e) = rv[c];
         }
     }
     return acc;
@@ -466,14 +472,14 @@ __device__ __forceinline__ void cg_after_rr(CgState* st, double alpha_d, double 
     else if (st->iter >= st->max_iter || !(s == s)) st->done = 2;  // NaN: the reference would spin to max_iter
 }
 
-template <typename T, bool DIST>
-__global__ void __launch_bounds__(kVecThreads) cg_update_xr_seg_kernel(int ncomp, long long comp_stride, long long npts,
+template <typename T, int NCOMP, bool DIST>
+__global__ void __launch_bounds__(kVecThreads) cg_update_xr_seg_kernel(long long comp_stride, long long npts,
                                                                        const int* __restrict__ seg, const int* __restrict__ nseg_p,
                                                                        T* x, T* r, const T* d, const T* q, CgState* st, double* partials, int freeze,
                                                                        PeerInfo* peers, PeerHot hot) {
     if (*(volatile int*)&st->done) return;
     const double alpha_d = st->delta / st->dq;
-    const double acc = cg_update_xr_seg_body<T, DIST>(ncomp, comp_stride, npts, seg, *nseg_p, x, r, d, q, (T)alpha_d, hot);
+    const double acc = cg_update_xr_seg_body<T, NCOMP, DIST>(comp_stride, npts, seg, *nseg_p, x, r, d, q, (T)alpha_d, hot);
     grid_sum_finish(acc, partials, &st->counter[1], [=](double s) {
         if (freeze) return;
         cg_after_rr(st, alpha_d, s);
@@ -481,49 +487,60 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_xr_seg_kernel(int ncomp
 }
 
 // K3 on the active set
-template <typename T>
-__device__ __forceinline__ void cg_update_d_seg_body(int ncomp, long long comp_stride, long long npts, const int* __restrict__ seg, int nseg,
+template <typename T, int NCOMP>
+__device__ __forceinline__ void cg_update_d_seg_body(long long comp_stride, long long npts, const int* __restrict__ seg, int nseg,
                                                      T* d, const T* r, T beta) {
     using V = typename Vec2<T>::type;
     const int hl = threadIdx.x & 15;
     const long long hw0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const long long nhw = ((long long)gridDim.x * blockDim.x) >> 4;
-    for (int c = 0; c < ncomp; ++c) {
-        const long long base = (long long)c * comp_stride + 2 * hl;
-        long long j = hw0;
-        int sg = j < nseg ? __ldg(seg + j) : 0;
-        while (j < nseg) {
-            const long long p = (long long)sg * kSegPts + 2 * hl;
-            const long long e = base + (long long)sg * kSegPts;
-            j += nhw;
-            sg = j < nseg ? __ldg(seg + j) : 0;
-            if (p >= npts) continue;
-            V dv = *reinterpret_cast<const V*>(d + e);
-            const V rv = *reinterpret_cast<const V*>(r + e);
-            dv.x = rv.x + beta * dv.x; dv.y = rv.y + beta * dv.y;
-            *reinterpret_cast<V*>(d + e) = dv;
+    long long j = hw0;
+    int sg = j < nseg ? __ldg(seg + j) : 0;
+    while (j < nseg) {
+        const long long p = (long long)sg * kSegPts + 2 * hl;
+        j += nhw;
+        sg = j < nseg ? __ldg(seg + j) : 0;
+        if (p >= npts) continue;
+        V dv[NCOMP], rv[NCOMP];
+#pragma unroll
+        for (int c = 0; c < NCOMP; ++c) {
+            const long long e = (long long)c * comp_stride + p;
+            dv[c] = *reinterpret_cast<const V*>(d + e);
+            rv[c] = *reinterpret_cast<const V*>(r + e);
+        }
+#pragma unroll
+        for (int c = 0; c < NCOMP; ++c) {
+            const long long e = (long long)c * comp_stride + p;
+            dv[c].x = rv[c].x + beta * dv[c].x; dv[c].y = rv[c].y + beta * dv[c].y;
+            *reinterpret_cast<V*>(d + e) = dv[c];
         }
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kVecThreads) cg_update_d_seg_kernel(int ncomp, long long comp_stride, long long npts,
+template <typename T, int NCOMP>
+__global__ void __launch_bounds__(kVecThreads) cg_update_d_seg_kernel(long long comp_stride, long long npts,
                                                                       const int* __restrict__ seg, const int* __restrict__ nseg_p,
                                                                       T* d, const T* r, CgState* st) {
     if (*(volatile int*)&st->done) return;
     const double beta_d = st->delta / st->delta_old;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->beta = beta_d;
-    cg_update_d_seg_body<T>(ncomp, comp_stride, npts, seg, *nseg_p, d, r, (T)beta_d);
+    cg_update_d_seg_body<T, NCOMP>(comp_stride, npts, seg, *nseg_p, d, r, (T)beta_d);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Grid-wide barrier for the persistent whole-iteration kernels (cooperative launch: every CTA is
-// resident).  grid_reduce_barrier sums one double over the grid: the LAST block to arrive adds the
-// per-block partials in a fixed order, optionally all-reduces over the NVSwitch peers, runs
-// fin(total) in its thread 0 and only then releases the other blocks — one barrier per reduction,
-// and the CG scalars are updated by exactly one thread, as in the multi-kernel path.
+// Grid-wide synchronisation for the persistent whole-iteration kernels (cooperative launch: every
+// CTA is resident).  One monotonically increasing arrival counter (reset by the host before each
+// launch): barrier k is passed when the counter reaches k*gridDim.x, so the last arriver's atomic
+// itself releases everybody — no second flag, no reset on the critical path.
+//   grid_sync        plain barrier
+//   grid_allreduce   sum of one double over the grid, returned to EVERY thread: each block leaves
+//                    its partial (double-buffered by barrier parity), passes the barrier and then
+//                    adds up all partials itself in a fixed order, so all blocks obtain the same
+//                    bits and keep the CG scalars in registers — no global state on the critical path.
+// Arrival is an acq_rel atomic (releases this block's writes — bar.sync before it makes that
+// cumulative over the block); waiters spin on an acquire load.
 // ---------------------------------------------------------------------------------------------
-struct GridBar { unsigned int count; unsigned int gen; };
+struct GridBar { unsigned int count; unsigned int flag; double gsum[2]; };
 
 __device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
     unsigned int r;
@@ -535,87 +552,104 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
     return r;
 }
-__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
-    unsigned int r;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
-    return r;
-}
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Arrival is an acq_rel atomic (releases this block's writes — bar.sync before it makes that cumulative over the block —
-// and acquires the others' for the last arriver); waiters spin on an acquire load of the generation word.
-__device__ __forceinline__ void grid_barrier(GridBar* bar) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int g = ld_relaxed_gpu(&bar->gen);       // cannot advance before this block has arrived
-        if (atom_add_acq_rel_gpu(&bar->count, 1u) == gridDim.x - 1) {
-            bar->count = 0;
-            st_release_gpu(&bar->gen, g + 1u);
-        } else {
-            while (ld_acquire_gpu(&bar->gen) == g) { }
+struct GridSync {
+    GridBar* bar;
+    unsigned int passed;     // barriers passed so far in this launch (identical in every thread of the grid)
+    __device__ __forceinline__ void arrive_and_wait(bool system_scope) {   // thread 0 of the block only
+        ++passed;
+        const unsigned int target = passed * gridDim.x;
+        if (system_scope) __threadfence_system();                          // stores into a peer GPU need system scope
+        if (atom_add_acq_rel_gpu(&bar->count, 1u) + 1u < target) {
+            while (ld_acquire_gpu(&bar->count) < target) { }
         }
     }
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) arrive_and_wait(false);
+        else ++passed;
+        __syncthreads();
+    }
+};
+
+// every thread of the block gets the block total; fixed order => identical bits in every block that sums the same values
+__device__ __forceinline__ double block_sum_all(double v, double* sm /*>=32 doubles*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
     __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    double t = lane < nwarps ? sm[lane] : 0.0;
+    return warp_sum(t);
 }
 
-template <class Fin>
-__device__ __forceinline__ void grid_reduce_barrier(double v, double* partials, GridBar* bar, Fin fin,
-                                                    PeerInfo* peers = nullptr, int kind = 0, bool wrote_peer = false) {
+__device__ __forceinline__ double grid_allreduce(double v, double* partials /*2*gridDim.x*/, GridSync& gs,
+                                                 PeerInfo* peers = nullptr, int kind = 0, bool wrote_peer = false) {
     __shared__ double sm[32];
-    __shared__ unsigned int s_gen;
-    __shared__ bool s_last;
     const unsigned int nblocks = gridDim.x;
+    double* slot = partials + (size_t)(gs.passed & 1u) * nblocks;
     v = block_sum(v, sm);
     if (threadIdx.x == 0) {
-        s_gen = ld_relaxed_gpu(&bar->gen);
-        partials[blockIdx.x] = v;
-        if (wrote_peer) __threadfence_system();               // stores into a peer GPU need system scope
-        s_last = (atom_add_acq_rel_gpu(&bar->count, 1u) == nblocks - 1);
+        slot[blockIdx.x] = v;
+        gs.arrive_and_wait(wrote_peer);
+    } else {
+        ++gs.passed;
     }
     __syncthreads();
-    if (s_last) {
-        double s = 0.0;
-        for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) s += __ldcg(partials + i);
-        s = block_sum(s, sm);
-        if (peers && threadIdx.x < 32) {
-            s = __shfl_sync(0xffffffffu, s, 0);
-            s = peer_allreduce_warp(s, peers, kind);
+    double s = 0.0;
+    for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) s += __ldcg(slot + i);
+    s = block_sum_all(s, sm);
+    if (peers) {
+        // multi-GPU: block 0 all-reduces the local sum over the NVSwitch peers and publishes the result; the other
+        // blocks wait for it (flag = index of the barrier it belongs to)
+        __shared__ double s_glob;
+        const unsigned int tag = gs.passed;
+        if (blockIdx.x == 0) {
+            if (threadIdx.x < 32) {
+                const double g = peer_allreduce_warp(s, peers, kind);
+                if (threadIdx.x == 0) {
+                    gs.bar->gsum[tag & 1u] = g;
+                    st_release_gpu(&gs.bar->flag, tag);
+                    s_glob = g;
+                }
+            }
+        } else if (threadIdx.x == 0) {
+            while (ld_acquire_gpu(&gs.bar->flag) < tag) { }
+            s_glob = *(volatile double*)&gs.bar->gsum[tag & 1u];
         }
-        if (threadIdx.x == 0) {
-            bar->count = 0;
-            fin(s);
-            st_release_gpu(&bar->gen, s_gen + 1u);
-        }
-    } else if (threadIdx.x == 0) {
-        while (ld_acquire_gpu(&bar->gen) == s_gen) { }
+        __syncthreads();
+        s = s_glob;
+        __syncthreads();
     }
-    __syncthreads();
+    return s;
 }
 
 constexpr int kPersistThreads = 512;      // one CTA per SM (128 registers per thread for the operator body)
 
 constexpr int kSegsPerVecBlock = kVecThreads / 16;   // one half-warp per segment
 
-template <typename T>
-int cg_launch_update_xr_seg(int ncomp, long long comp_stride, long long npts, const SegList& sl, T* x, T* r, const T* d, const T* q,
+template <typename T, int NCOMP>
+int cg_launch_update_xr_seg(long long comp_stride, long long npts, const SegList& sl, T* x, T* r, const T* d, const T* q,
                             CgState* st, double* partials, cudaStream_t s, int freeze = 0, PeerInfo* peers = nullptr,
                             const PeerHot* hotp = nullptr) {
     PeerHot hot;
     memset(&hot, 0, sizeof(hot));
     if (hotp) hot = *hotp;
     const int grid = seg_grid(sl.nseg, kSegsPerVecBlock, kVecGrid);
-    if (peers) cg_update_xr_seg_kernel<T, true><<<grid, kVecThreads, 0, s>>>(ncomp, comp_stride, npts, sl.list, sl.nseg_dev, x, r, d, q, st, partials, freeze, peers, hot);
-    else cg_update_xr_seg_kernel<T, false><<<grid, kVecThreads, 0, s>>>(ncomp, comp_stride, npts, sl.list, sl.nseg_dev, x, r, d, q, st, partials, freeze, nullptr, hot);
+    if (peers) cg_update_xr_seg_kernel<T, NCOMP, true><<<grid, kVecThreads, 0, s>>>(comp_stride, npts, sl.list, sl.nseg_dev, x, r, d, q, st, partials, freeze, peers, hot);
+    else cg_update_xr_seg_kernel<T, NCOMP, false><<<grid, kVecThreads, 0, s>>>(comp_stride, npts, sl.list, sl.nseg_dev, x, r, d, q, st, partials, freeze, nullptr, hot);
     FS_LAUNCH_CHECK();
     return FS_OK;
 }
 
-template <typename T>
-int cg_launch_update_d_seg(int ncomp, long long comp_stride, long long npts, const SegList& sl, T* d, const T* r, CgState* st, cudaStream_t s) {
+template <typename T, int NCOMP>
+int cg_launch_update_d_seg(long long comp_stride, long long npts, const SegList& sl, T* d, const T* r, CgState* st, cudaStream_t s) {
     const int grid = seg_grid(sl.nseg, kSegsPerVecBlock, kVecGrid);
-    cg_update_d_seg_kernel<T><<<grid, kVecThreads, 0, s>>>(ncomp, comp_stride, npts, sl.list, sl.nseg_dev, d, r, st);
+    cg_update_d_seg_kernel<T, NCOMP><<<grid, kVecThreads, 0, s>>>(comp_stride, npts, sl.list, sl.nseg_dev, d, r, st);
     FS_LAUNCH_CHECK();
     return FS_OK;
 }

@@ -37,6 +37,15 @@ template <typename T> struct Visc3Dev {
 };
 
 __device__ __forceinline__ void lat_decode(const Lat3& L, long long i, int& x, int& y, int& z) {
+    if (L.NL < 0x7fffffffLL) {                       // 32-bit divisions (the common case) are several times cheaper
+        const unsigned int u = (unsigned int)i, zp = (unsigned int)L.Zp, yy = (unsigned int)L.Y;
+        const unsigned int t = u / zp;
+        z = (int)(u - t * zp);
+        const unsigned int xx = t / yy;
+        y = (int)(t - xx * yy);
+        x = (int)xx;
+        return;
+    }
     z = (int)(i % L.Zp);
     long long t = i / L.Zp;
     y = (int)(t % L.Y);
@@ -53,123 +62,125 @@ __device__ __forceinline__ void comp_shape(const Lat3& L, int c, int& s0, int& s
 constexpr int kThreads = 256;
 
 // ---------------------------------------------------------------------------------------------
-// pack: fine-grid (2n+1)^3 fp64 sphi / lvol  ->  lattice coefficient planes + face masks
+// pack: fine-grid (2n+1)^3 fp64 sphi / lvol  ->  lattice coefficient planes + face masks + activity map.
+// One block per lattice row (x,y); threads run along z (no per-thread index division).
+//
+// Activity map (1 byte per lattice point): bit c = row of component c is COMPUTED by this rank — fluid face
+// (sphi >= 0), interior, owned — and, with FS_ACTIVE_NONZERO, at least one of its seven coefficients (face volume, two
+// cell-centre volumes, four edge volumes = the fine node of the face and its six fine-grid neighbours) is non-zero.
+// A row whose coefficients are all zero is an all-zero row AND column of the operator: b, q, r, d are exactly 0 there
+// for the whole solve and x never changes (faces far from any liquid), so dropping it changes no result bit.
+// Bits 4..6: the row is computed by a neighbour slab and mirrored here (multi-GPU halo planes).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kThreads) visc3d_pack_kernel(Lat3 L, const double* __restrict__ sphi, const double* __restrict__ lvol,
-                                                               double vol_norm, T* __restrict__ coef /*[7][NL]*/, uint8_t* __restrict__ mask /*[3][NL]*/,
-                                                               uint8_t* __restrict__ act /*[NL + 32]*/) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.NL) return;
-    int x, y, z;
-    lat_decode(L, i, x, y, z);
+__global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const double* __restrict__ sphi, const double* __restrict__ lvol,
+                                                          double vol_norm, T* __restrict__ coef /*[7][NL]*/, uint8_t* __restrict__ mask /*[3][NL]*/,
+                                                          uint8_t* __restrict__ act /*[NL + 64]*/, int nonzero_only) {
+    const int row = blockIdx.x;                      // x*Y + y
+    const int x = row / L.Y, y = row - x * L.Y;
     const long long fz = 1, fy = 2LL * L.nz + 1, fx = fy * (2LL * L.ny + 1);
-    const long long f0 = 2LL * x * fx + 2LL * y * fy + 2LL * z * fz;  // fine node (2x,2y,2z)
-    const bool ix = x < L.nx, iy = y < L.ny, iz = z < L.nz, inz = z <= L.nz;
+    const long long frow = 2LL * x * fx + 2LL * y * fy;
+    const bool ix = x < L.nx, iy = y < L.ny;
     const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
-    auto vol = [&](long long off) { return (T)(lvol[f0 + off] / vol_norm); };
-    unsigned int abits = 0;
     // rows of these planes are computed by a neighbour slab and mirrored here (K2/K3 keep r and d current on them)
     const bool halo_x = (L.has_lo && x == 0) || (L.has_hi && x == L.nx - 1);
-    // faces: fine parities (0,1,1) (1,0,1) (1,1,0)
-    {
-        const bool in = iy && iz;
-        bool fluid = false;
-        T v = nan;
-        if (in) {
-            fluid = sphi[f0 + fy + fz] >= 0.0;
-            const bool interior = x >= 1 && x <= L.u_xhi && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
-            if (fluid && interior) { v = vol(fy + fz); if (v == v) abits |= 1u; }
-            if (fluid && halo_x && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2) abits |= 0x10u;
+    for (int z = threadIdx.x; z < L.Zp; z += blockDim.x) {
+        const long long i = (long long)row * L.Zp + z;
+        const long long f0 = frow + 2LL * z;         // fine node (2x,2y,2z)
+        const bool iz = z < L.nz, inz = z <= L.nz;
+        // vol = lvol / vol_norm (:568); the division is skipped for the (very common) exact zeros, whose quotient is the same zero
+        auto vol = [&](long long off) { const double l = lvol[f0 + off]; return l == 0.0 ? (T)l : (T)(l / vol_norm); };
+        auto nz = [](T v) { return v != T(0); };     // NaN counts as non-zero: it must propagate like in the reference
+        const T vc = (ix && iy && iz) ? vol(fx + fy + fz) : T(0);   // cell centre (1,1,1)
+        const T exy = (iz) ? vol(fz) : T(0);                        // Exy: (0,0,1)
+        const T exz = (iy && inz) ? vol(fy) : T(0);                 // Exz: (0,1,0)
+        const T eyz = (ix && inz) ? vol(fx) : T(0);                 // Eyz: (1,0,0)
+        unsigned int abits = 0;
+        // faces: fine parities (0,1,1) (1,0,1) (1,1,0)
+        {
+            bool fluid = false;
+            T v = nan;
+            if (iy && iz) {
+                fluid = sphi[f0 + fy + fz] >= 0.0;
+                const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
+                if (fluid && yz && x >= 1 && x <= L.u_xhi) {
+                    v = vol(fy + fz);
+                    if (v == v) {
+                        bool on = true;
+                        if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(exz) || nz(vol(fy + fz - fx)) || nz(vol(fy + fz + fy)) || nz(vol(fy + fz + fz));
+                        if (on) abits |= 1u;
+                    }
+                }
+                if (fluid && halo_x && yz) abits |= 0x10u;
+            }
+            coef[0 * L.NL + i] = v;
+            mask[0 * L.NL + i] = fluid;
         }
-        coef[0 * L.NL + i] = v;
-        mask[0 * L.NL + i] = fluid;
-    }
-    {
-        const bool in = ix && iz;
-        bool fluid = false;
-        T v = nan;
-        if (in) {
-            fluid = sphi[f0 + fx + fz] >= 0.0;
-            const bool interior = x >= 1 && x <= L.nx - 2 && y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2;
-            if (fluid && interior) { v = vol(fx + fz); if (v == v) abits |= 2u; }
-            if (fluid && halo_x && y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2) abits |= 0x20u;
+        {
+            bool fluid = false;
+            T v = nan;
+            if (ix && iz) {
+                fluid = sphi[f0 + fx + fz] >= 0.0;
+                const bool yz = y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2;
+                if (fluid && yz && x >= 1 && x <= L.nx - 2) {
+                    v = vol(fx + fz);
+                    if (v == v) {
+                        bool on = true;
+                        if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(eyz) || nz(vol(fx + fz + fx)) || nz(vol(fx + fz - fy)) || nz(vol(fx + fz + fz));
+                        if (on) abits |= 2u;
+                    }
+                }
+                if (fluid && halo_x && yz) abits |= 0x20u;
+            }
+            coef[1 * L.NL + i] = v;
+            mask[1 * L.NL + i] = fluid;
         }
-        coef[1 * L.NL + i] = v;
-        mask[1 * L.NL + i] = fluid;
-    }
-    {
-        const bool in = ix && iy && inz;
-        bool fluid = false;
-        T v = nan;
-        if (in) {
-            fluid = sphi[f0 + fx + fy] >= 0.0;
-            const bool interior = x >= 1 && x <= L.nx - 2 && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1;
-            if (fluid && interior) { v = vol(fx + fy); if (v == v) abits |= 4u; }
-            if (fluid && halo_x && y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1) abits |= 0x40u;
+        {
+            bool fluid = false;
+            T v = nan;
+            if (ix && iy && inz) {
+                fluid = sphi[f0 + fx + fy] >= 0.0;
+                const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1;
+                if (fluid && yz && x >= 1 && x <= L.nx - 2) {
+                    v = vol(fx + fy);
+                    if (v == v) {
+                        bool on = true;
+                        if (nonzero_only) on = nz(v) || nz(vc) || nz(exz) || nz(eyz) || nz(vol(fx + fy + fx)) || nz(vol(fx + fy + fy)) || nz(vol(fx + fy - fz));
+                        if (on) abits |= 4u;
+                    }
+                }
+                if (fluid && halo_x && yz) abits |= 0x40u;
+            }
+            coef[2 * L.NL + i] = v;
+            mask[2 * L.NL + i] = fluid;
         }
-        coef[2 * L.NL + i] = v;
-        mask[2 * L.NL + i] = fluid;
+        coef[3 * L.NL + i] = vc;
+        coef[4 * L.NL + i] = exy;
+        coef[5 * L.NL + i] = exz;
+        coef[6 * L.NL + i] = eyz;
+        act[i] = (uint8_t)abits;
     }
-    coef[3 * L.NL + i] = (ix && iy && iz) ? vol(fx + fy + fz) : T(0);   // cell centre (1,1,1)
-    coef[4 * L.NL + i] = (iz) ? vol(fz) : T(0);                         // Exy: (0,0,1)
-    coef[5 * L.NL + i] = (iy && inz) ? vol(fy) : T(0);                  // Exz: (0,1,0)
-    coef[6 * L.NL + i] = (ix && inz) ? vol(fx) : T(0);                  // Eyz: (1,0,0)
-    act[i] = (uint8_t)abits;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Active-set refinement (FS_ACTIVE_NONZERO): a computed row whose seven coefficients (face volume, two cell-centre
-// volumes, four edge volumes) are all zero is an all-zero row AND column of the operator — b, q, r, d are exactly 0
-// there for the whole solve and x never changes (faces far from any liquid) — so it is dropped from the active set.
-// Results are bit-identical; only rows that can carry a non-zero value are visited by the CG kernels.
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kThreads) visc3d_activity_kernel(Lat3 L, const T* __restrict__ coef /*[7][NL]*/, uint8_t* __restrict__ act) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.NL) return;
-    unsigned int a = act[i];
-    if ((a & kActCompute) == 0u) return;
-    const long long NL = L.NL, sx = L.sx, sy = L.sy;
-    const T* Vc = coef + 3 * NL;
-    const T* Exy = coef + 4 * NL;
-    const T* Exz = coef + 5 * NL;
-    const T* Eyz = coef + 6 * NL;
-    auto nz = [](T v) { return v != T(0); };       // NaN counts as non-zero: it must propagate like in the reference
-    const bool c0 = nz(Vc[i]), exy = nz(Exy[i]), exz = nz(Exz[i]), eyz = nz(Eyz[i]);
-    if (a & 1u) {
-        const bool on = nz(coef[i]) || c0 || nz(Vc[i - sx]) || nz(Exy[i + sy]) || exy || nz(Exz[i + 1]) || exz;
-        if (!on) a &= ~1u;
-    }
-    if (a & 2u) {
-        const bool on = nz(coef[NL + i]) || c0 || nz(Vc[i - sy]) || nz(Exy[i + sx]) || exy || nz(Eyz[i + 1]) || eyz;
-        if (!on) a &= ~2u;
-    }
-    if (a & 4u) {
-        const bool on = nz(coef[2 * NL + i]) || c0 || nz(Vc[i - 1]) || nz(Exz[i + sx]) || exz || nz(Eyz[i + sy]) || eyz;
-        if (!on) a &= ~4u;
-    }
-    act[i] = (uint8_t)a;
 }
 
 // ---------------------------------------------------------------------------------------------
 // load / store between the caller's dense MAC arrays and lattice vectors
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename S>
-__global__ void __launch_bounds__(kThreads) visc3d_load_kernel(Lat3 L, const S* __restrict__ a0, const S* __restrict__ a1, const S* __restrict__ a2,
-                                                               T* __restrict__ vec /*[3][NL]*/) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.NL) return;
-    int x, y, z;
-    lat_decode(L, i, x, y, z);
+__global__ void __launch_bounds__(512) visc3d_load_kernel(Lat3 L, const S* __restrict__ a0, const S* __restrict__ a1, const S* __restrict__ a2,
+                                                          T* __restrict__ vec /*[3][NL]*/) {
+    const int row = blockIdx.x;                      // x*Y + y, one block per lattice row
+    const int x = row / L.Y, y = row - x * L.Y;
     const S* src[3] = {a0, a1, a2};
+    for (int z = threadIdx.x; z < L.Zp; z += blockDim.x) {
+        const long long i = (long long)row * L.Zp + z;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        int s0, s1, s2;
-        comp_shape(L, c, s0, s1, s2);
-        T v = T(0);
-        if (x < s0 && y < s1 && z < s2) v = (T)src[c][((long long)x * s1 + y) * s2 + z];
-        vec[c * L.NL + i] = v;
+        for (int c = 0; c < 3; ++c) {
+            int s0, s1, s2;
+            comp_shape(L, c, s0, s1, s2);
+            T v = T(0);
+            if (x < s0 && y < s1 && z < s2) v = (T)src[c][((long long)x * s1 + y) * s2 + z];
+            vec[c * L.NL + i] = v;
+        }
     }
 }
 
@@ -204,36 +215,129 @@ __global__ void __launch_bounds__(kThreads) visc3d_store_kernel(Lat3 L, const T*
 // value is only ever written to a face nobody reads during that sweep: identical to Jacobi, without
 // copies — a sweep reads the validity bytes and touches values only next to the fluid/solid interface.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool bytes_all_nonzero(uint32_t w) {
+    return ((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u) == 0x80808080u;
+}
+
+// Work lists of the extrapolation: the faces filled by sweep k are the only places next to which sweep k+1 can fill
+// anything, so sweep 1 (a full pass) records them and the later sweeps only look around them.
+struct ExtrapWork {
+    unsigned int* list[2];      // flat face ids c*NL + i, ping-pong between sweeps
+    unsigned int* count;        // [0..1] entries of list[k], [2] overflow flag
+    unsigned int cap;           // 0 = lists disabled (full passes only)
+};
+
+__device__ __forceinline__ void extrap_push(const ExtrapWork& W, int which, unsigned int face) {
+    if (W.cap == 0u) return;
+    const unsigned int k = atomicAdd(W.count + which, 1u);
+    if (k < W.cap) W.list[which][k] = face;
+    else W.count[2] = 1u;                          // overflow: the next sweep falls back to a full pass
+}
+
+// fill face (c,i) if it is invalid, interior and has a neighbour that was valid before this sweep (:12-38)
 template <typename T>
-__global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, T* v_all, uint8_t* valid_all, int sweep /*1-based*/) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.NL) return;
-    const uint8_t v0 = valid_all[i], v1 = valid_all[L.NL + i], v2 = valid_all[2 * L.NL + i];
-    if (v0 && v1 && v2) return;                       // nothing to fill at this lattice point (the common case)
-    int x, y, z;
-    lat_decode(L, i, x, y, z);
-    const long long st[3] = {L.sx, L.sy, 1};
-    const uint8_t own[3] = {v0, v1, v2};
+__device__ __forceinline__ bool extrap_try_fill(const Lat3& L, T* v_all, uint8_t* valid_all, int c, long long i, int x, int y, int z, unsigned int sw) {
+    int s0, s1, s2;
+    comp_shape(L, c, s0, s1, s2);
+    if (!(x >= 1 && x <= s0 - 2 && y >= 1 && y <= s1 - 2 && z >= 1 && z <= s2 - 2)) return false;
+    T* v = v_all + c * L.NL;
+    uint8_t* va = valid_all + c * L.NL;
+    if (va[i] != 0) return false;
+    auto ok = [&](unsigned int g) { return g >= 1u && g <= sw; };
+    T val = T(0);
+    int count = 0;                                 // +x,-x,+y,-y,+z,-z
+    if (ok(va[i + L.sx])) { val += v[i + L.sx]; ++count; }
+    if (ok(va[i - L.sx])) { val += v[i - L.sx]; ++count; }
+    if (ok(va[i + L.sy])) { val += v[i + L.sy]; ++count; }
+    if (ok(va[i - L.sy])) { val += v[i - L.sy]; ++count; }
+    if (ok(va[i + 1])) { val += v[i + 1]; ++count; }
+    if (ok(va[i - 1])) { val += v[i - 1]; ++count; }
+    if (count == 0) return false;
+    v[i] = val / (T)count;
+    va[i] = (uint8_t)(sw + 1u);
+    return true;
+}
+
+// Full pass.  One thread per 4 z-consecutive lattice points (Zp % 4 == 0): the validity bytes are read as words, a group
+// whose twelve bytes are all valid (fluid regions) exits after three loads, and the index decode and the neighbour
+// words are only touched where something may have to be filled.  Grid-stride, so the same kernel serves as the
+// fall-back of the list-driven sweeps (`only_if_overflow`).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, T* v_all, uint8_t* valid_all, int sweep /*1-based*/, ExtrapWork W,
+                                                                      int push_to /*list to record fills in, -1 = none*/, int only_if_overflow) {
+    if (only_if_overflow && (W.cap == 0u || W.count[2] == 0u)) return;
+    const unsigned int sw = (unsigned int)sweep;
+    const long long ngroups = L.NL / 4;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (long long)gridDim.x * blockDim.x) {
+        const long long i4 = g * 4;
+        uint32_t own[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        if (own[c]) continue;
-        int s0, s1, s2;
-        comp_shape(L, c, s0, s1, s2);
-        const bool interior = x >= 1 && x <= s0 - 2 && y >= 1 && y <= s1 - 2 && z >= 1 && z <= s2 - 2;
-        if (!interior) continue;
-        T* v = v_all + c * L.NL;
-        const uint8_t* va = valid_all + c * L.NL;
-        T val = T(0);
-        int count = 0;
+        for (int c = 0; c < 3; ++c) own[c] = *reinterpret_cast<const uint32_t*>(valid_all + c * L.NL + i4);
+        if (bytes_all_nonzero(own[0]) && bytes_all_nonzero(own[1]) && bytes_all_nonzero(own[2])) continue;
+        int x, y, z0;
+        lat_decode(L, i4, x, y, z0);
 #pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {   // +x,-x,+y,-y,+z,-z  (:19-36)
-            const unsigned int gp = va[i + st[ax]], gm = va[i - st[ax]];
-            if (gp >= 1u && gp <= (unsigned int)sweep) { val += v[i + st[ax]]; ++count; }
-            if (gm >= 1u && gm <= (unsigned int)sweep) { val += v[i - st[ax]]; ++count; }
+        for (int c = 0; c < 3; ++c) {
+            if (bytes_all_nonzero(own[c])) continue;
+            int s0, s1, s2;
+            comp_shape(L, c, s0, s1, s2);
+            if (!(x >= 1 && x <= s0 - 2 && y >= 1 && y <= s1 - 2)) continue;
+            T* v = v_all + c * L.NL;
+            uint8_t* va = valid_all + c * L.NL;
+            const uint32_t xp = *reinterpret_cast<const uint32_t*>(va + i4 + L.sx), xm = *reinterpret_cast<const uint32_t*>(va + i4 - L.sx);
+            const uint32_t yp = *reinterpret_cast<const uint32_t*>(va + i4 + L.sy), ym = *reinterpret_cast<const uint32_t*>(va + i4 - L.sy);
+            const unsigned int zl = z0 > 0 ? va[i4 - 1] : 0u;
+            const unsigned int zr = z0 + 4 < L.Zp ? va[i4 + 4] : 0u;
+            auto ok = [&](unsigned int gg) { return gg >= 1u && gg <= sw; };
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int z = z0 + k;
+                if (((own[c] >> (8 * k)) & 0xffu) != 0u || !(z >= 1 && z <= s2 - 2)) continue;
+                const long long i = i4 + k;
+                const unsigned int gxp = (xp >> (8 * k)) & 0xffu, gxm = (xm >> (8 * k)) & 0xffu;
+                const unsigned int gyp = (yp >> (8 * k)) & 0xffu, gym = (ym >> (8 * k)) & 0xffu;
+                const unsigned int gzp = k < 3 ? (own[c] >> (8 * (k < 3 ? k + 1 : 0))) & 0xffu : zr;
+                const unsigned int gzm = k > 0 ? (own[c] >> (8 * (k > 0 ? k - 1 : 0))) & 0xffu : zl;
+                T val = T(0);
+                int count = 0;                            // +x,-x,+y,-y,+z,-z  (:19-36)
+                if (ok(gxp)) { val += v[i + L.sx]; ++count; }
+                if (ok(gxm)) { val += v[i - L.sx]; ++count; }
+                if (ok(gyp)) { val += v[i + L.sy]; ++count; }
+                if (ok(gym)) { val += v[i - L.sy]; ++count; }
+                if (ok(gzp)) { val += v[i + 1]; ++count; }
+                if (ok(gzm)) { val += v[i - 1]; ++count; }
+                if (count > 0) {
+                    v[i] = val / (T)count;
+                    va[i] = (uint8_t)(sweep + 1);
+                    if (push_to >= 0) extrap_push(W, push_to, (unsigned int)(c * L.NL + i));
+                }
+            }
         }
-        if (count > 0) {
-            v[i] = val / (T)count;
-            valid_all[c * L.NL + i] = (uint8_t)(sweep + 1);
+    }
+}
+
+// List-driven sweep k >= 2: only the six same-component neighbours of the faces filled by sweep k-1 can be filled now.
+// Two entries may target the same face: both compute the same value from the same (final) inputs, so the race is benign.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) visc3d_extrapolate_list_kernel(Lat3 L, T* v_all, uint8_t* valid_all, int sweep, ExtrapWork W,
+                                                                           int from, int push_to) {
+    if (W.count[2] != 0u) return;                  // overflowed: the full-pass fall-back does this sweep
+    const unsigned int n = W.count[from];
+    const unsigned int sw = (unsigned int)sweep;
+    const long long off[6] = {L.sx, -L.sx, L.sy, -L.sy, 1, -1};
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const unsigned int face = W.list[from][e];
+        const int c = (int)(face / (unsigned int)L.NL);
+        const long long i = (long long)(face - (unsigned int)c * (unsigned int)L.NL);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const long long j = i + off[k];
+            if (j < 0 || j >= L.NL) continue;
+            if (valid_all[c * L.NL + j] != 0) continue;
+            int x, y, z;
+            lat_decode(L, j, x, y, z);
+            if (extrap_try_fill<T>(L, v_all, valid_all, c, j, x, y, z, sw) && push_to >= 0)
+                extrap_push(W, push_to, (unsigned int)(c * L.NL + j));
         }
     }
 }
@@ -477,26 +581,54 @@ template <typename T, bool DIST>
 __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kernel(Visc3Dev<T> P, T s, T s2, T* x, T* r, T* d, T* q,
                                                                                   const int* __restrict__ seg, const int* __restrict__ nseg_p,
                                                                                   CgState* st, double* partials, GridBar* bar, int n_iters,
-                                                                                  PeerInfo* peers, PeerHot hot) {
+                                                                                  PeerInfo* peers, PeerHot hot, unsigned long long* prof) {
     const int nseg = *nseg_p;
     const long long NL = P.L.NL;
-    for (int it = 0; it < n_iters; ++it) {
-        if (*(volatile int*)&st->done) break;
-        // K1 phase
+    // The CG scalars live in registers, replicated in every thread of the grid: each block derives them from the same
+    // per-block partials in the same order, so they stay bit-identical everywhere and nothing global is read in the loop.
+    double delta = st->delta, delta_old = st->delta_old, dq = st->dq, alpha_d = st->alpha, beta_d = st->beta;
+    const double tol2 = st->tol2;
+    long long iter = st->iter;
+    const long long max_iter = st->max_iter;
+    int done = st->done;
+    GridSync gs{bar, 0u};
+    // optional phase timeline (FLUIDSOLVER_B200_PROFILE): block 0 stamps the global timer after every phase / barrier
+    const bool stamp = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    int np = 0;
+    auto tick = [&]() {
+        if (stamp && np < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); prof[np++] = t; }
+    };
+    for (int it = 0; it < n_iters && !done; ++it) {
+        tick();
+        // K1 phase: q = A d, d.q
         bool wrote_peer = false;
         double acc = visc3d_apply_dot_body<T, DIST, true>(P, s, s2, d, q, seg, nseg, hot, wrote_peer);
         const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
-        grid_reduce_barrier(acc, partials, bar, [=](double sum) { st->dq = sum; }, DIST ? peers : nullptr, 0, block_wrote_peer);
-        // K2 phase
-        const double alpha_d = *(volatile double*)&st->delta / *(volatile double*)&st->dq;
-        acc = cg_update_xr_seg_body<T, DIST>(3, NL, NL, seg, nseg, x, r, d, q, (T)alpha_d, hot);
-        grid_reduce_barrier(acc, partials, bar, [=](double sum) { cg_after_rr(st, alpha_d, sum); }, DIST ? peers : nullptr, 1, false);
-        if (*(volatile int*)&st->done) break;
-        // K3 phase
-        const double beta_d = *(volatile double*)&st->delta / *(volatile double*)&st->delta_old;
-        if (blockIdx.x == 0 && threadIdx.x == 0) st->beta = beta_d;
-        cg_update_d_seg_body<T>(3, NL, NL, seg, nseg, d, r, (T)beta_d);
-        grid_barrier(bar);
+        tick();
+        dq = grid_allreduce(acc, partials, gs, DIST ? peers : nullptr, 0, block_wrote_peer);
+        tick();
+        // K2 phase: x += alpha d, r -= alpha q, r.r
+        alpha_d = delta / dq;
+        acc = cg_update_xr_seg_body<T, 3, DIST>(NL, NL, seg, nseg, x, r, d, q, (T)alpha_d, hot);
+        tick();
+        const double rr = grid_allreduce(acc, partials, gs, DIST ? peers : nullptr, 1, false);
+        tick();
+        delta_old = delta;
+        delta = rr;
+        iter += 1;
+        if (rr < tol2) done = 1;
+        else if (iter >= max_iter || !(rr == rr)) done = 2;      // NaN: the reference would spin to max_iter
+        if (done) break;
+        // K3 phase: d = r + beta d
+        beta_d = delta / delta_old;
+        cg_update_d_seg_body<T, 3>(NL, NL, seg, nseg, d, r, (T)beta_d);
+        tick();
+        gs.sync();
+        tick();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->delta = delta; st->delta_old = delta_old; st->dq = dq; st->alpha = alpha_d; st->beta = beta_d;
+        st->iter = iter; st->done = done;
     }
 }
 
@@ -518,6 +650,7 @@ struct fs_visc3d {
     uint8_t* mask;   // [3][NL]
     uint8_t* valid;  // [3][NL] extrapolation validity generations
     GridBar* bar;    // grid barrier of the persistent CG kernel
+    ExtrapWork work; // extrapolation work lists
     int cg_mode;     // FS_CG_AUTO / FS_CG_KERNELS / FS_CG_PERSISTENT
     bool sparse_clean;   // r,d,q,b are zero outside the segments of the current active list (sparse begin / clear may be used)
     uint8_t* act;    // [NL] computed-row bits
@@ -536,6 +669,12 @@ struct fs_visc3d {
     long long active_rows;   // computed rows of the last pack (host copy, filled lazily)
 };
 
+// threads of the one-block-per-lattice-row kernels: a whole number of warps covering the row once, at most 512
+static int row_block(const Lat3& L) {
+    int b = (L.Zp + 31) / 32 * 32;
+    return b < 512 ? b : 512;
+}
+
 static Lat3 make_lat3(int nx, int ny, int nz) {
     Lat3 L;
     L.nx = nx; L.ny = ny; L.nz = nz;
@@ -546,7 +685,7 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     return L;
 }
 
-struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, total; int grid_pts; };
+struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, total; int grid_pts; unsigned int wcap; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -569,6 +708,10 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     o.seglist = p; p = align_up(p + SegList::list_bytes(L.NL), 256);
     o.segscratch = p; p = align_up(p + SegList::scratch_bytes(L.NL), 256);
     o.bar = p; p = align_up(p + sizeof(GridBar), 256);
+    // extrapolation work lists: 2 x NL/2 face ids (a sweep that fills more falls back to full passes); needs 3*NL < 2^32
+    o.wcap = (3 * L.NL < 0xffffffffLL) ? (unsigned int)(L.NL / 2 + 1024) : 0u;
+    o.wlist = p; p = align_up(p + (size_t)2 * o.wcap * sizeof(unsigned int), 256);
+    o.wcount = p; p = align_up(p + 4 * sizeof(unsigned int), 256);
     o.total = p;
     return o;
 }
@@ -671,6 +814,13 @@ int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int h
     return FS_OK;
 }
 
+int fs_visc3d_debug_read(fs_visc3d* h, int what, void* out, size_t bytes) {
+    if (!h || !out) return fail(FS_ERR_ARG, "null argument");
+    const void* src = what == 0 ? (const void*)h->valid : (const void*)h->act;
+    FS_CUDA(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    return FS_OK;
+}
+
 int fs_visc3d_peer_error(fs_visc3d* h) {
     if (!h || !h->peers) return 0;
     PeerInfo pi;
@@ -746,6 +896,14 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->mask = (uint8_t*)(h->ws + lay.mask); h->valid = (uint8_t*)(h->ws + lay.valid); h->act = (uint8_t*)(h->ws + lay.act);
     h->partials = (double*)(h->ws + lay.partials); h->st = (CgState*)(h->ws + lay.st);
     h->bar = (GridBar*)(h->ws + lay.bar);
+    h->work.cap = lay.wcap;
+    if (const char* e = getenv("FLUIDSOLVER_B200_EXTRAP_CAP")) {   // test hook: tiny lists force the overflow fall-back
+        const long long c = atoll(e);
+        if (c >= 0 && c < (long long)lay.wcap) h->work.cap = (unsigned int)c;
+    }
+    h->work.list[0] = (unsigned int*)(h->ws + lay.wlist);
+    h->work.list[1] = h->work.list[0] + lay.wcap;
+    h->work.count = (unsigned int*)(h->ws + lay.wcount);
     h->cg_mode = FS_CG_AUTO;
     h->sparse_clean = true;          // the workspace is zeroed below and the list is empty
     h->grid_pts = lay.grid_pts;
@@ -802,12 +960,9 @@ int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double 
         FS_CUDA(cudaMemsetAsync(h->vecs + (size_t)FS_VEC_R * 3 * h->L.NL * h->esz, 0, (size_t)12 * h->L.NL * h->esz, s));
         h->sparse_clean = true;
     }
-    FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act));
+    FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act,
+                                                                                      h->active_mode == FS_ACTIVE_NONZERO ? 1 : 0));
     FS_LAUNCH_CHECK();
-    if (h->active_mode == FS_ACTIVE_NONZERO) {
-        FS_DISPATCH(h, visc3d_activity_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(h->L, reinterpret_cast<const T*>(h->coef), h->act));
-        FS_LAUNCH_CHECK();
-    }
     FS_TRY(h->seg.build(h->act, s));      // one host sync per solve: the list length sizes the CG launches
     h->active_rows = -1;
     h->packed = true;
@@ -820,9 +975,9 @@ int fs_visc3d_load(fs_visc3d* h, int vec, const void* vx, const void* vy, const 
     if (vec != FS_VEC_X) h->sparse_clean = false;
     cudaStream_t s = (cudaStream_t)stream;
     if (src_dtype == FS_F32) {
-        FS_DISPATCH(h, visc3d_load_kernel<T, float><<<h->grid_pts, kThreads, 0, s>>>(h->L, (const float*)vx, (const float*)vy, (const float*)vz, vec_ptr<T>(h, vec)));
+        FS_DISPATCH(h, visc3d_load_kernel<T, float><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, (const float*)vx, (const float*)vy, (const float*)vz, vec_ptr<T>(h, vec)));
     } else if (src_dtype == FS_F64) {
-        FS_DISPATCH(h, visc3d_load_kernel<T, double><<<h->grid_pts, kThreads, 0, s>>>(h->L, (const double*)vx, (const double*)vy, (const double*)vz, vec_ptr<T>(h, vec)));
+        FS_DISPATCH(h, visc3d_load_kernel<T, double><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, (const double*)vx, (const double*)vy, (const double*)vz, vec_ptr<T>(h, vec)));
     } else return fail(FS_ERR_ARG, "fs_visc3d_load: bad dtype");
     FS_LAUNCH_CHECK();
     return FS_OK;
@@ -853,9 +1008,25 @@ int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const long long NL3 = 3 * h->L.NL;
     FS_CUDA(cudaMemcpyAsync(h->valid, h->mask, NL3, cudaMemcpyDeviceToDevice, s));   // generation 1 = (sphi >= 0)  (:479-481)
+    // single GPU: sweep 1 is a full pass that records what it filled, later sweeps only look around those faces.
+    // Multi-GPU slabs always run full passes (the neighbours' fills arrive through the halo exchange, not the list).
+    ExtrapWork W = h->work;
+    if (h->comm) W.cap = 0u;
+    if (W.cap) FS_CUDA(cudaMemsetAsync(W.count, 0, 4 * sizeof(unsigned int), s));
+    const int full_grid = (int)((h->L.NL / 4 + kThreads - 1) / kThreads);
     for (int k = 1; k <= sweeps; ++k) {
-        FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<h->grid_pts, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k));
-        FS_LAUNCH_CHECK();
+        const int push_to = (W.cap && k < sweeps) ? ((k - 1) & 1) : -1;
+        if (k == 1 || !W.cap) {
+            FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<full_grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, push_to, 0));
+            FS_LAUNCH_CHECK();
+        } else {
+            const int from = (k - 2) & 1;
+            if (push_to >= 0) FS_CUDA(cudaMemsetAsync(W.count + push_to, 0, sizeof(unsigned int), s));
+            FS_DISPATCH(h, visc3d_extrapolate_list_kernel<T><<<kSMs * 4, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, from, push_to));
+            FS_LAUNCH_CHECK();
+            FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<kSMs * 8, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, -1, 1));   // only if a list overflowed
+            FS_LAUNCH_CHECK();
+        }
         if (h->comm) {   // the sweep is Jacobi over the GLOBAL grid: refresh the halo planes of the new values and generations
             FS_TRY(visc3d_halo_vec(h, vec, s));
             FS_TRY(visc3d_halo(h, (char*)h->valid, 1, COMM_U8, s));
@@ -901,11 +1072,11 @@ static int visc3d_k1(fs_visc3d* h, double sm, cudaStream_t s) {
     return FS_OK;
 }
 static int visc3d_k2(fs_visc3d* h, cudaStream_t s, int freeze = 0) {
-    FS_DISPATCH(h, FS_TRY(cg_launch_update_xr_seg<T>(3, h->L.NL, h->L.NL, h->seg, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s, freeze, h->peers, h->peers ? &h->hot : nullptr)));
+    FS_DISPATCH(h, FS_TRY((cg_launch_update_xr_seg<T, 3>(h->L.NL, h->L.NL, h->seg, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R), vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), h->st, h->partials, s, freeze, h->peers, h->peers ? &h->hot : nullptr))));
     return FS_OK;
 }
 static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
-    FS_DISPATCH(h, FS_TRY(cg_launch_update_d_seg<T>(3, h->L.NL, h->L.NL, h->seg, vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, s)));
+    FS_DISPATCH(h, FS_TRY((cg_launch_update_d_seg<T, 3>(h->L.NL, h->L.NL, h->seg, vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, s))));
     return FS_OK;
 }
 
@@ -950,10 +1121,13 @@ static bool visc3d_use_persistent(const fs_visc3d* h) {
 }
 
 static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
-    const int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, kSMs);
+    int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, kSMs);
+    if (const char* e = getenv("FLUIDSOLVER_B200_PERSIST_GRID")) { const int g = atoi(e); if (g >= 1 && g <= kSMs) grid = g; }
+    unsigned long long* prof = getenv("FLUIDSOLVER_B200_PROFILE") ? reinterpret_cast<unsigned long long*>(h->valid) : nullptr;   // scratch between solves
     while (n > 0) {
         int ni = (int)(n < (1 << 20) ? n : (1 << 20));
-        cudaError_t e = cudaSuccess;
+        cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);     // arrival counter / flag count from zero in every launch
+        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
         FS_DISPATCH(h, {
             Visc3Dev<T> P = dev_view<T>(h);
             T sv = (T)sm, s2v = (T)(2 * sm);
@@ -961,7 +1135,7 @@ static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t 
             const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
             CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
             PeerInfo* peers = h->peers; PeerHot hot = h->hot;
-            void* args[] = {&P, &sv, &s2v, &x, &r, &d, &q, &seg, &nsegp, &st, &partials, &bar, &ni, &peers, &hot};
+            void* args[] = {&P, &sv, &s2v, &x, &r, &d, &q, &seg, &nsegp, &st, &partials, &bar, &ni, &peers, &hot, &prof};
             const void* fn = h->peers ? (const void*)visc3d_cg_persistent_kernel<T, true> : (const void*)visc3d_cg_persistent_kernel<T, false>;
             e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args, 0, s);
         });

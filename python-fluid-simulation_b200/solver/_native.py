@@ -43,6 +43,7 @@ _SIGS = {
     "fs_visc3d_vector_ptr": (c_void_p, [c_void_p, c_int, c_int]),
     "fs_visc3d_set_active_mode": (c_int, [c_void_p, c_int]),
     "fs_visc3d_set_cg_mode": (c_int, [c_void_p, c_int]),
+    "fs_visc3d_debug_read": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     "fs_visc3d_active_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), c_void_p]),
     "fs_visc3d_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
     "fs_visc3d_load": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

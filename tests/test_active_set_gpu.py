@@ -150,3 +150,41 @@ def test_fixed_window_persistent_counts_iterations():
         with pytest.raises(ValueError, match="Failed to converge!"):
             s.solve(sc["dt"], 100.0, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"], tol=0.0)
         assert s.iterations == 150
+
+
+@pytest.mark.parametrize("cap", ["0", "7", None])
+def test_extrapolation_worklists_and_overflow_fallback(cap, monkeypatch):
+    """Sweeps >= 2 of the extrapolation are driven by the list of faces the previous sweep filled; a list that overflows
+    (cap=7) or is disabled (cap=0) falls back to full passes.  All three must reproduce the reference bit for bit."""
+    from solver import ViscosityCGSolver3D as V
+    if cap is None:
+        monkeypatch.delenv("FLUIDSOLVER_B200_EXTRAP_CAP", raising=False)
+    else:
+        monkeypatch.setenv("FLUIDSOLVER_B200_EXTRAP_CAP", cap)
+    V._engines.clear()
+    f = load_golden("visc3d_kernels_6x7x8")
+    g = tuple(int(n) for n in f["gres"])
+    v = [torch.as_tensor(f[k]).cuda() for k in ("vx", "vy", "vz")]
+    V.extrapolate(g, 3, *v, torch.as_tensor(f["sphi"]).cuda(), dtype=torch.float64)
+    for o, n in zip(v, "xyz"):
+        assert np.array_equal(o.cpu().numpy(), f["e" + n])
+    # a larger random case: all variants agree with each other (compared against the cap=None run through a module cache)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    g2 = (19, 14, 23)
+    sphi = torch.randn(tuple(2 * n + 1 for n in g2), dtype=torch.float64, device="cuda", generator=gen) - 0.8
+    vel = [torch.randn(sh, dtype=torch.float64, device="cuda", generator=gen) for sh in ((20, 14, 23), (19, 15, 23), (19, 14, 24))]
+    for sweeps in (1, 2, 5):
+        out = [a.clone() for a in vel]
+        V.extrapolate(g2, sweeps, *out, sphi, dtype=torch.float64)
+        key = ("extrap", sweeps)
+        if key not in _EXTRAP_CACHE:                        # the NumPy oracle (Jacobi with full copies), once per sweep count
+            from oracle import numpy_oracle as O
+            ref = [a.cpu().numpy().copy() for a in vel]
+            O.visc3d_extrapolate(g2, sweeps, *ref, sphi.cpu().numpy())
+            _EXTRAP_CACHE[key] = ref
+        for a, b in zip(out, _EXTRAP_CACHE[key]):
+            assert np.array_equal(a.cpu().numpy(), b)
+    V._engines.clear()
+
+
+_EXTRAP_CACHE = {}
