@@ -151,6 +151,11 @@ def workload_config(args, n, where):
 # ------------------------------------------------------------------------------------------------------------
 
 def run_native(args):
+    # keep stdout to the one JSON line: anything the native libraries print (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    args._json_out = os.fdopen(json_fd, "w")
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -283,7 +288,7 @@ def run_native(args):
                 "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=args._json_out, flush=True)
     return 0
 
 

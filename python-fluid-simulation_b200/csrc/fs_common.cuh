@@ -587,9 +587,73 @@ __device__ __forceinline__ double block_sum_all(double v, double* sm /*>=32 doub
     return warp_sum(t);
 }
 
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// Multi-GPU part of grid_allreduce: `local` is this rank's sum (known to every block).  Block 0 publishes it to every
+// rank's mailbox (its own included); warp 0 of EVERY block then collects the N rank sums from the local mailbox and adds
+// them in rank order, so no second hop through a flag is needed and every block of every rank obtains the same bits.
+// Mailbox words are LL-style (4 data bytes + 4-byte sequence number); the polling loads are relaxed and one acquire
+// fence follows, so the q halo rows a neighbour stored before publishing are visible afterwards.  seq = sequence number of this reduction (the same
+// in every block; the caller keeps the running count).  Bounded spin: a dead peer yields NaN and P->error = 1.
+__device__ __forceinline__ double peer_allreduce_block(double local, PeerInfo* P, int kind, unsigned int seq, double* sm_bcast) {
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        const int n = P->nranks, me = P->rank;
+        const int slot = ((kind * 2 + (int)(seq & 1u)) * kMaxRanks);
+        if (blockIdx.x == 0) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(local);
+            const unsigned long long w0 = ((unsigned long long)seq << 32) | (bits & 0xffffffffull);
+            const unsigned long long w1 = ((unsigned long long)seq << 32) | (bits >> 32);
+            fence_acq_rel_sys();                       // everything this rank did (peer stores, halo reads) is ordered before
+            if (lane < n) {
+                unsigned long long* dst = P->mbox[lane] + (slot + me) * 2;
+                st_relaxed_sys_u64(dst, w0);
+                st_relaxed_sys_u64(dst + 1, w1);
+            }
+        }
+        double v = 0.0;
+        bool ok = true;
+        if (lane < n) {
+            const unsigned long long* src = P->mbox[me] + (slot + lane) * 2;
+            unsigned long long a, b;
+            const long long t0 = clock64();
+            for (;;) {
+                a = ld_relaxed_sys_u64(src);
+                b = ld_relaxed_sys_u64(src + 1);
+                if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
+                if (clock64() - t0 > 20000000000LL) { ok = false; break; }     // ~10 s: a peer died; bail out instead of hanging
+            }
+            v = __longlong_as_double((long long)(((b & 0xffffffffull) << 32) | (a & 0xffffffffull)));
+        }
+        fence_acq_rel_sys();                           // acquire: what the peers stored before publishing is visible from here on
+        double sum = 0.0;
+        if (!__all_sync(0xffffffffu, ok)) {
+            if (lane == 0) P->error = 1;
+            sum = __longlong_as_double(0x7ff8000000000000LL);
+        } else {
+            for (int r = 0; r < n; ++r) sum += __shfl_sync(0xffffffffu, v, r);        // fixed rank order
+        }
+        if (lane == 0) *sm_bcast = sum;
+    }
+    __syncthreads();
+    const double out = *sm_bcast;
+    __syncthreads();
+    return out;
+}
+
+// seq: when `peers` is given, the sequence number of this cross-GPU reduction (see peer_allreduce_block)
 __device__ __forceinline__ double grid_allreduce(double v, double* partials /*2*gridDim.x*/, GridSync& gs,
-                                                 PeerInfo* peers = nullptr, int kind = 0, bool wrote_peer = false) {
+                                                 PeerInfo* peers = nullptr, int kind = 0, bool wrote_peer = false, unsigned int seq = 0) {
     __shared__ double sm[32];
+    __shared__ double s_glob;
     const unsigned int nblocks = gridDim.x;
     double* slot = partials + (size_t)(gs.passed & 1u) * nblocks;
     v = block_sum(v, sm);
@@ -603,28 +667,7 @@ __device__ __forceinline__ double grid_allreduce(double v, double* partials /*2*
     double s = 0.0;
     for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) s += __ldcg(slot + i);
     s = block_sum_all(s, sm);
-    if (peers) {
-        // multi-GPU: block 0 all-reduces the local sum over the NVSwitch peers and publishes the result; the other
-        // blocks wait for it (flag = index of the barrier it belongs to)
-        __shared__ double s_glob;
-        const unsigned int tag = gs.passed;
-        if (blockIdx.x == 0) {
-            if (threadIdx.x < 32) {
-                const double g = peer_allreduce_warp(s, peers, kind);
-                if (threadIdx.x == 0) {
-                    gs.bar->gsum[tag & 1u] = g;
-                    st_release_gpu(&gs.bar->flag, tag);
-                    s_glob = g;
-                }
-            }
-        } else if (threadIdx.x == 0) {
-            while (ld_acquire_gpu(&gs.bar->flag) < tag) { }
-            s_glob = *(volatile double*)&gs.bar->gsum[tag & 1u];
-        }
-        __syncthreads();
-        s = s_glob;
-        __syncthreads();
-    }
+    if (peers) s = peer_allreduce_block(s, peers, kind, seq, &s_glob);
     return s;
 }
 

@@ -592,6 +592,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
     const long long max_iter = st->max_iter;
     int done = st->done;
     GridSync gs{bar, 0u};
+    // multi-GPU: running sequence numbers of the two cross-GPU reductions (every block keeps its own copy; block 0 writes
+    // them back at the end so that the next launch — persistent or three-kernel — continues the count)
+    unsigned int seq0 = 0, seq1 = 0;
+    if (DIST) { seq0 = peers->seq[0]; seq1 = peers->seq[1]; }
     // optional phase timeline (FLUIDSOLVER_B200_PROFILE): block 0 stamps the global timer after every phase / barrier
     const bool stamp = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     int np = 0;
@@ -605,13 +609,15 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
         double acc = visc3d_apply_dot_body<T, DIST, true>(P, s, s2, d, q, seg, nseg, hot, wrote_peer);
         const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
         tick();
-        dq = grid_allreduce(acc, partials, gs, DIST ? peers : nullptr, 0, block_wrote_peer);
+        if (DIST) ++seq0;
+        dq = grid_allreduce(acc, partials, gs, DIST ? peers : nullptr, 0, block_wrote_peer, seq0);
         tick();
         // K2 phase: x += alpha d, r -= alpha q, r.r
         alpha_d = delta / dq;
         acc = cg_update_xr_seg_body<T, 3, DIST>(NL, NL, seg, nseg, x, r, d, q, (T)alpha_d, hot);
         tick();
-        const double rr = grid_allreduce(acc, partials, gs, DIST ? peers : nullptr, 1, false);
+        if (DIST) ++seq1;
+        const double rr = grid_allreduce(acc, partials, gs, DIST ? peers : nullptr, 1, false, seq1);
         tick();
         delta_old = delta;
         delta = rr;
@@ -629,6 +635,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->delta = delta; st->delta_old = delta_old; st->dq = dq; st->alpha = alpha_d; st->beta = beta_d;
         st->iter = iter; st->done = done;
+        if (DIST) { peers->seq[0] = seq0; peers->seq[1] = seq1; }
     }
 }
 

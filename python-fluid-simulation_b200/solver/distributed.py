@@ -14,6 +14,7 @@ The per-rank arrays passed to ``solve()`` are the extended slabs, cut from globa
 import ctypes
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -375,7 +376,7 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
                                        "frac_of_aggregate_peak": iter_gbs / (peak * world)}},
             "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=getattr(args, "_json_out", None) or sys.stdout, flush=True)
     solver.close()
     dist.barrier()
     dist.destroy_process_group()
