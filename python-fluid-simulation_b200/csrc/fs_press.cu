@@ -8,6 +8,7 @@
 // the fastest axis contiguous, so no repacking is needed — one thread per cell with the fastest axis on
 // threadIdx.x gives coalesced 8-byte accesses.  All arithmetic follows the reference's association with
 // explicit round-to-nearest intrinsics (no FMA contraction), so fp64 results are bit-identical to it.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "fs_common.cuh"
@@ -119,6 +120,120 @@ __global__ void __launch_bounds__(kPT) press_apply_kernel(Grid<D> g, const doubl
         out[i] = res;
     }
     if (CG) grid_sum_finish(acc, partials, &st->counter[0], [=](double s) { st->dq = s; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Active-set CG for the pressure system.  Rows that the operator computes are the interior cells with lphi < 0; on
+// every other cell b = q = r = d = 0 and x stays 0 for the whole solve.  One byte per cell marks the computed rows, the
+// sorted list of active 32-cell segments is built once per solve (fs_common: SegList) and a persistent cooperative
+// kernel runs whole iterations on it: apply + d.q, x/r update + r.r, d update as phases separated by grid barriers,
+// the CG scalars replicated in registers (same structure as visc3d_cg_persistent_kernel).  Arithmetic and association
+// are those of press_apply_kernel / cg_update_*; only the set of visited cells and the reduction order differ.
+// ---------------------------------------------------------------------------------------------
+template <int D> __device__ __forceinline__ void decode_fast(const Grid<D>& g, long long i, int* c) {
+    if (g.ncells < 0x7fffffffLL) {
+        unsigned int u = (unsigned int)i;
+#pragma unroll
+        for (int a = D - 1; a >= 0; --a) {
+            const unsigned int n = (unsigned int)g.n[a];
+            const unsigned int t = u / n;
+            c[a] = (int)(u - t * n);
+            u = t;
+        }
+        return;
+    }
+    decode<D>(g, i, c);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kPT) press_activity_kernel(Grid<D> g, const double* __restrict__ lphi, uint8_t* __restrict__ act) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.ncells) return;
+    int c[D];
+    decode_fast<D>(g, i, c);
+    act[i] = (interior<D>(g, c) && lphi[i] < 0) ? 1 : 0;
+}
+
+// one pass over the active segments: out = A v on computed rows (a warp per 32-cell segment), returns this thread's share of v.out
+template <int D>
+__device__ __forceinline__ double press_apply_seg_body(const Grid<D>& g, const double* v, double* out, const PressW<D>& W,
+                                                       const double* __restrict__ lphi, const int* __restrict__ seg, int nseg) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    int sg_n = w0 < nseg ? __ldg(seg + w0) : 0;
+    for (long long k = w0; k < nseg; k += nw) {
+        const long long i = (long long)sg_n * kSegPts + lane;
+        {
+            const long long k2 = k + nw;
+            sg_n = k2 < nseg ? __ldg(seg + k2) : 0;
+        }
+        if (i >= g.ncells) continue;
+        int c[D];
+        decode_fast<D>(g, i, c);
+        if (!interior<D>(g, c)) continue;
+        const double phi = __ldg(lphi + i);
+        if (!(phi < 0)) continue;                       // not computed: out holds 0 since the start of the solve
+        double val = 0.0, diag = 0.0;
+        const double vc = v[i];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+#pragma unroll
+            for (int sgn = 1; sgn >= -1; sgn -= 2) {          // +a then -a
+                const long long j = i + sgn * g.cs[a];
+                const double nphi = __ldg(lphi + j);
+                const double w = __ldg(W.w[a] + face_idx<D>(g, a, c, sgn > 0 ? 1 : 0));
+                if (nphi < 0) {
+                    val = __dsub_rn(val, __dmul_rn(w, v[j]));
+                    diag = __dadd_rn(diag, w);
+                } else {
+                    const double frac = fmin(1.0, fmax(0.01, phi / __dsub_rn(phi, nphi)));
+                    diag = __dadd_rn(diag, w / frac);
+                }
+            }
+        }
+        const double res = __dadd_rn(val, __dmul_rn(diag, vc));
+        acc += vc * res;
+        out[i] = res;
+    }
+    return acc;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kPersistThreads, 1) press_cg_persistent_kernel(Grid<D> g, double* x, double* r, double* d, double* q, PressW<D> W,
+                                                                                 const double* __restrict__ lphi, const int* __restrict__ seg,
+                                                                                 const int* __restrict__ nseg_p, CgState* st, double* partials,
+                                                                                 GridBar* bar, int n_iters) {
+    const int nseg = *nseg_p;
+    double delta = st->delta, delta_old = st->delta_old, dq = st->dq, alpha_d = st->alpha, beta_d = st->beta;
+    const double tol2 = st->tol2;
+    long long iter = st->iter;
+    const long long max_iter = st->max_iter;
+    int done = st->done;
+    GridSync gs{bar, 0u};
+    PeerHot hot;                                     // unused (single GPU)
+    hot.has_lo = hot.has_hi = 0;
+    for (int it = 0; it < n_iters && !done; ++it) {
+        double acc = press_apply_seg_body<D>(g, d, q, W, lphi, seg, nseg);
+        dq = grid_allreduce(acc, partials, gs);
+        alpha_d = delta / dq;
+        acc = cg_update_xr_seg_body<double, 1, false>(g.ncells, g.ncells, seg, nseg, x, r, d, q, alpha_d, hot);
+        const double rr = grid_allreduce(acc, partials, gs);
+        delta_old = delta;
+        delta = rr;
+        iter += 1;
+        if (rr < tol2) done = 1;
+        else if (iter >= max_iter || !(rr == rr)) done = 2;
+        if (done) break;
+        beta_d = delta / delta_old;
+        cg_update_d_seg_body<double, 1>(g.ncells, g.ncells, seg, nseg, d, r, beta_d);
+        gs.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->delta = delta; st->delta_old = delta_old; st->dq = dq; st->alpha = alpha_d; st->beta = beta_d;
+        st->iter = iter; st->done = done;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -251,14 +366,26 @@ struct fs_press {
     int grid;
     IterGraph graph;
     const void* gkey[9];   // pointer set the captured graph was built for
+    uint8_t* act;          // computed-row flag per cell
+    SegList seg;           // active 32-cell segments of the current solve
+    GridBar* bar;
+    bool use_list;         // the current solve iterates on the active list with the persistent kernel
 };
 
-static size_t press_ws(long long ncells, size_t* off_st) {
+struct PressLayout { size_t st, act, seglist, segscratch, bar, total; };
+
+static PressLayout press_layout(long long ncells) {
+    PressLayout o;
     int grid = (int)((ncells + kPT - 1) / kPT);
     size_t np = (size_t)(grid > kVecGrid ? grid : kVecGrid);
     size_t p = align_up(np * sizeof(double), 256);
-    if (off_st) *off_st = p;
-    return p + align_up(sizeof(CgState), 256);
+    o.st = p; p += align_up(sizeof(CgState), 256);
+    o.act = p; p = align_up(p + (size_t)ncells + 64, 256);
+    o.seglist = p; p = align_up(p + SegList::list_bytes(ncells), 256);
+    o.segscratch = p; p = align_up(p + SegList::scratch_bytes(ncells), 256);
+    o.bar = p; p = align_up(p + sizeof(GridBar), 256);
+    o.total = p;
+    return o;
 }
 
 template <int D> static PressW<D> mkW(const double* wx, const double* wy, const double* wz) {
@@ -304,8 +431,57 @@ static int press_iteration(fs_press* h, double* x, double* d, double* r, double*
     return FS_OK;
 }
 
+// Build the computed-row map and the active segment list of this solve; decide whether the iterations run on the list
+// (persistent kernel; FLUIDSOLVER_B200_PERSISTENT=0/1 forces off/on, default: active working set <= 256 MB) or on the
+// dense three-kernel path.  The list kernels use 16-byte accesses: an odd cell count or unaligned arrays stay dense.
+static int press_prepare_list(fs_press* h, const double* x, const double* d, const double* r, const double* q, const double* lphi, cudaStream_t s) {
+    h->use_list = false;
+    static int mode = -2;
+    if (mode == -2) {
+        const char* e = getenv("FLUIDSOLVER_B200_PERSISTENT");
+        mode = !e ? -1 : (e[0] == '0' ? 0 : 1);
+    }
+    if (mode == 0) return FS_OK;
+    if ((h->ncells & 1) || !aligned16(x) || !aligned16(d) || !aligned16(r) || !aligned16(q)) return FS_OK;
+    if (h->nz > 0) press_activity_kernel<3><<<h->grid, kPT, 0, s>>>(make_grid<3>(h->nx, h->ny, h->nz), lphi, h->act);
+    else press_activity_kernel<2><<<h->grid, kPT, 0, s>>>(make_grid<2>(h->nx, h->ny, 0), lphi, h->act);
+    FS_LAUNCH_CHECK();
+    FS_TRY(h->seg.build(h->act, s));
+    const double ws = (double)h->seg.nseg * kSegPts * 80.0;     // x,r,d,q,lphi + weights, 8 bytes each
+    h->use_list = (mode == 1) || ws <= 256e6;
+    return FS_OK;
+}
+
+static int press_persistent(fs_press* h, double* x, double* d, double* r, double* q, const double* wx, const double* wy, const double* wz,
+                            const double* lphi, long long n, cudaStream_t s) {
+    const int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, kSMs);
+    while (n > 0) {
+        int ni = (int)(n < (1 << 20) ? n : (1 << 20));
+        cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);
+        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+        const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
+        CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
+        if (h->nz > 0) {
+            Grid<3> g = make_grid<3>(h->nx, h->ny, h->nz);
+            PressW<3> W = mkW<3>(wx, wy, wz);
+            void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni};
+            e = cudaLaunchCooperativeKernel((const void*)press_cg_persistent_kernel<3>, dim3(grid), dim3(kPersistThreads), args, 0, s);
+        } else {
+            Grid<2> g = make_grid<2>(h->nx, h->ny, 0);
+            PressW<2> W = mkW<2>(wx, wy, nullptr);
+            void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni};
+            e = cudaLaunchCooperativeKernel((const void*)press_cg_persistent_kernel<2>, dim3(grid), dim3(kPersistThreads), args, 0, s);
+        }
+        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
+        FS_LAUNCH_CHECK();
+        n -= ni;
+    }
+    return FS_OK;
+}
+
 static int press_iterations(fs_press* h, double* x, double* d, double* r, double* q, const double* wx, const double* wy, const double* wz,
                             const double* lphi, long long n, cudaStream_t s) {
+    if (h->use_list) return press_persistent(h, x, d, r, q, wx, wy, wz, lphi, n, s);
     const void* ptrs[9] = {x, d, r, q, wx, wy, wz, lphi, nullptr};
     if (!press_same_ptrs(h, ptrs)) {                      // the graph bakes the array pointers in
         h->graph.valid = false;
@@ -318,7 +494,7 @@ extern "C" {
 
 size_t fs_press_workspace_bytes(int nx, int ny, int nz) {
     if (nx < 1 || ny < 1 || nz < 0) return 0;
-    return press_ws((long long)nx * ny * (nz > 0 ? nz : 1), nullptr);
+    return press_layout((long long)nx * ny * (nz > 0 ? nz : 1)).total;
 }
 
 int fs_press_create(fs_press** out, int nx, int ny, int nz, void* ws, size_t ws_bytes) {
@@ -328,18 +504,23 @@ int fs_press_create(fs_press** out, int nx, int ny, int nz, void* ws, size_t ws_
     fs_press* h = new fs_press();
     h->nx = nx; h->ny = ny; h->nz = nz;
     h->ncells = (long long)nx * ny * (nz > 0 ? nz : 1);
-    size_t off_st;
-    size_t need = press_ws(h->ncells, &off_st);
+    const PressLayout lay = press_layout(h->ncells);
+    const size_t need = lay.total;
     if (ws_bytes < need) { delete h; return fail(FS_ERR_ARG, "fs_press_create: workspace too small"); }
     h->partials = (double*)ws;
-    h->st = (CgState*)((char*)ws + off_st);
+    h->st = (CgState*)((char*)ws + lay.st);
+    h->act = (uint8_t*)((char*)ws + lay.act);
+    h->bar = (GridBar*)((char*)ws + lay.bar);
+    h->use_list = false;
     h->grid = (int)((h->ncells + kPT - 1) / kPT);
     for (int k = 0; k < 9; ++k) h->gkey[k] = nullptr;
     int s = h->cg.init();
     if (s < 0) { delete h; return s; }
+    s = h->seg.init(h->ncells, (char*)ws + lay.seglist, (char*)ws + lay.segscratch);
+    if (s < 0) { h->cg.destroy(); delete h; return s; }
     h->cg.st_dev = h->st; h->cg.partials_dev = h->partials;
     cudaError_t e = cudaMemset(ws, 0, need);
-    if (e != cudaSuccess) { h->cg.destroy(); delete h; return fail(FS_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { h->cg.destroy(); h->seg.destroy(); delete h; return fail(FS_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
     *out = h;
     return FS_OK;
 }
@@ -348,6 +529,7 @@ void fs_press_destroy(fs_press* h) {
     if (!h) return;
     h->graph.destroy();
     h->cg.destroy();
+    h->seg.destroy();
     delete h;
 }
 
@@ -407,8 +589,9 @@ int fs_press_cg(fs_press* h, double* x, double* d, double* r, double* q, const d
     FS_CUDA(cudaMemsetAsync(x, 0, h->ncells * sizeof(double), s));                       // self.x *= 0.0   (:198)
     FS_TRY(press_apply_launch(h, x, q, wx, wy, wz, lphi, false, s));                     // q = A x         (:201)
     FS_TRY((cg_launch_residual_init<double>(h->ncells, b, q, d, r, h->st, h->partials, s)));   // d = b - q ; r = d ; delta (:202-204)
+    FS_TRY(press_prepare_list(h, x, d, r, q, lphi, s));
     return cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return press_iterations(h, x, d, r, q, wx, wy, wz, lphi, nb, ss); },
-                    (long long)max_iter, stats, s);
+                    (long long)max_iter, stats, s, h->use_list ? kCgBatchPersistent : kCgBatch);
 }
 
 int fs_press_cg_enqueue(fs_press* h, double* x, double* d, double* r, double* q,
@@ -416,6 +599,7 @@ int fs_press_cg_enqueue(fs_press* h, double* x, double* d, double* r, double* q,
     if (!h || !x || !d || !r || !q || !wx || !wy || !lphi || (h->nz > 0 && !wz)) return fail(FS_ERR_ARG, "fs_press_cg_enqueue: null argument");
     cg_state_unlimit_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->st);
     FS_LAUNCH_CHECK();
+    FS_TRY(press_prepare_list(h, x, d, r, q, lphi, (cudaStream_t)stream));
     return press_iterations(h, x, d, r, q, wx, wy, wz, lphi, n, (cudaStream_t)stream);
 }
 
