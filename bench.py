@@ -241,17 +241,27 @@ def run_native(args):
     e2e_value = args.iters * e2e_steps / (e2e_ms * 1e-3)
     del host
 
-    # ---- per-kernel timing for the roofline -----------------------------------------------------------------
+    # ---- roofline: the CG window alone, and each kernel of the iteration alone --------------------------------
     scale = sc["dt"] / solver.cell_vol / sc["rho"]
     stream = torch.cuda.current_stream().cuda_stream
-    kern = {}
-    # bytes per launch: the kernels walk the active 32-point lattice segments only, so the unit is the lattice
-    # point of an active segment: K1 reads d (3) + coefficients (7) and writes q (3) = 13 words + 1 activity byte;
-    # K2 reads x,d,r,q and writes x,r = 18 words; K3 reads r,d and writes d = 9 words (3 components per point)
+    # bytes: the kernels walk the ACTIVE 32-point lattice segments only, so the unit is the lattice point of an
+    # active segment: K1 reads d (3) + coefficients (7) and writes q (3) = 13 words + 1 activity byte; K2 reads x,d,r,q and
+    # writes x,r = 18 words; K3 reads r,d and writes d = 9 words (3 components per point)
     segs, segs_total, rows = solver.active_info()
     pts = segs * 32
     kbytes = {"K1 visc3d_apply_dot": pts * (13 * esz + 1), "K2 cg_update_xr": pts * 18 * esz, "K3 cg_update_d": pts * 9 * esz}
+    iter_bytes = sum(kbytes.values())
     working_set = pts * (22 * esz + 1)
+    persistent = N.check(lib.fs_visc3d_cg_mode_in_use(solver._e.h), "mode") == N.CG_PERSISTENT
+    N.check(lib.fs_visc3d_cg_enqueue(solver._e.h, scale, args.mu, 64, stream), "warm")
+    torch.cuda.synchronize()
+    win = 512 if persistent else 192
+    ev0.record()
+    N.check(lib.fs_visc3d_cg_enqueue(solver._e.h, scale, args.mu, win, stream), "window")
+    ev1.record()
+    torch.cuda.synchronize()
+    iter_ms = ev0.elapsed_time(ev1) / win
+    kern = {}
     reps = 30
     for which, name in ((1, "K1 visc3d_apply_dot"), (2, "K2 cg_update_xr"), (3, "K3 cg_update_d")):
         N.check(lib.fs_visc3d_kernel_enqueue(solver._e.h, which, scale, args.mu, 3, stream), "warm")
@@ -261,19 +271,34 @@ def run_native(args):
         ev1.record()
         torch.cuda.synchronize()
         kern[name] = ev0.elapsed_time(ev1) / reps
-    dom = max(kern, key=kern.get)
-    achieved = kbytes[dom] / (kern[dom] * 1e-3) / 1e9
+    if persistent:
+        # the iteration runs as ONE persistent kernel (K1, K2, K3 are its phases): that kernel is the dominant one of the step
+        dom = "visc3d_cg_persistent_kernel (K1+K2+K3 phases of one cooperative launch per 64 iterations)"
+        achieved = iter_bytes / (iter_ms * 1e-3) / 1e9
+        dom_share = iter_ms * args.iters / (ms / args.steps)
+    else:
+        dom = max(kern, key=kern.get)
+        achieved = kbytes[dom] / (kern[dom] * 1e-3) / 1e9
+        dom_share = kern[dom] * args.iters / (ms / args.steps)
     iter_gbs = words_iter * esz * value / 1e9
+    traffic = None
+    try:                                              # dram bytes per launch from the committed ncu --set full capture, if any
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(args.scene + ":" + args.active_set + ":" + ("persistent" if persistent else dom.split()[0]))
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "per_kernel_ms": kern, "per_kernel_GBps": {k: kbytes[k] / (kern[k] * 1e-3) / 1e9 for k in kern},
+                "traffic": traffic, "peak_source": peak_src, "share_of_step": dom_share,
+                "cg_iteration_us": iter_ms * 1e3, "cg_iteration_bytes": iter_bytes, "setup_ms_per_step": ms / args.steps - iter_ms * args.iters,
+                "per_kernel_ms_standalone": kern, "per_kernel_GBps_standalone": {k: kbytes[k] / (kern[k] * 1e-3) / 1e9 for k in kern},
                 "bytes_per_launch": kbytes,
-                "cg_mode": args.cg_mode,
+                "cg_mode": "persistent" if persistent else "kernels",
                 "active_set": {"mode": args.active_set, "segments": segs, "segments_total": segs_total, "computed_rows": rows,
                                "faces": F, "row_fraction": rows / F, "cg_working_set_MB": working_set / 1e6,
                                "l2_resident": working_set < 100e6},
-                "note": "bytes = lattice points of ACTIVE segments x words per point; when the CG working set is L2-resident the "
-                        "achieved figure is L2, not HBM, bandwidth (see --scene column for the HBM-bound dense case)",
+                "note": "bytes = lattice points of ACTIVE segments x words per point (13+18+9 words per iteration); when the CG working set "
+                        "is L2-resident the achieved figure is L2, not HBM, traffic (see --scene column / --active-set fluid for the "
+                        "HBM-bound regimes)",
                 "dense_equivalent": {"algorithmic_GB_per_iter": words_iter * esz / 1e9, "achieved_GBps": iter_gbs, "frac": iter_gbs / peak,
                                      "formula": "(11F+V7) words/iter if every face row were streamed, SURVEY §8d"}}
 

@@ -110,6 +110,8 @@ void* fs_visc3d_vector_ptr(const fs_visc3d* h, int vec, int comp);
 int fs_visc3d_debug_read(fs_visc3d* h, int what, void* out_host, size_t bytes);
 /* Select how iterations are launched (FS_CG_*). */
 int fs_visc3d_set_cg_mode(fs_visc3d* h, int mode);
+/* After fs_visc3d_pack: the mode FS_CG_AUTO resolves to for the current active set (FS_CG_KERNELS or FS_CG_PERSISTENT). */
+int fs_visc3d_cg_mode_in_use(fs_visc3d* h);
 /* Select the active-row set (FS_ACTIVE_*); takes effect at the next fs_visc3d_pack. */
 int fs_visc3d_set_active_mode(fs_visc3d* h, int mode);
 /* After fs_visc3d_pack: number of active 32-point lattice segments the CG kernels walk, segments in the whole lattice,
@@ -219,6 +221,12 @@ typedef struct fs_press fs_press;
 size_t fs_press_workspace_bytes(int nx, int ny, int nz);
 int fs_press_create(fs_press** out, int nx, int ny, int nz, void* workspace_dev, size_t workspace_bytes);
 void fs_press_destroy(fs_press* h);
+/* Operator the handle's apply / CG use: the pressure Poisson operator (default) or the density (volume-conservation)
+ * operator of DensityCGSolver3D.py:117-204 — same 7-point ghost-fluid stencil with UNIT diagonal contributions and the
+ * reference's -z quirk (the -z off-diagonal term reads wz[x,y,z+1]).  Same CG driver, same CGSolverBuffer arrays. */
+#define FS_OP_PRESSURE 0
+#define FS_OP_DENSITY 1
+int fs_press_set_operator(fs_press* h, int op);
 /* initialize_solver (PressureCGSolver3D.py:155-159): weighted divergence RHS into b */
 int fs_press_rhs(fs_press* h, const double* cell_size3, const void* vx_dev, const void* vy_dev, const void* vz_dev, int vel_dtype,
                  const double* sv_dev, const double* lphi_dev, double* b_dev,
@@ -237,6 +245,28 @@ int fs_press_cg(fs_press* h, double* x_dev, double* d_dev, double* r_dev, double
 int fs_press_cg_enqueue(fs_press* h, double* x_dev, double* d_dev, double* r_dev, double* q_dev,
                         const double* wx_dev, const double* wy_dev, const double* wz_dev, const double* lphi_dev,
                         int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Density (volume-conservation) solve  (DensityCGSolver3D, SURVEY "next" row f-1) — the kernels around the CG;
+ * the operator apply and the CG itself are fs_press_apply / fs_press_cg on a handle set to FS_OP_DENSITY.
+ * Cells (nx,ny,nz), faces (+1 on their own axis), fine grid (2n+1)^3: fp64, reference layout.  Particles: px (P,3) and
+ * pm (P), FS_F32 or FS_F64.  bound_min3 / cell_size3 / grid_bias3 are HOST arrays of three doubles.
+ * ---------------------------------------------------------------------------------------- */
+/* initialize_density (DensityCGSolver3D.py:8-36, :250-255): gm += w*pm, gvol += w*pvol (trilinear, fp64 atomics) */
+int fs_dens3d_scatter(int nx, int ny, int nz, const double* bound_min3, const double* cell_size3, const void* px_dev, int px_dtype,
+                      const void* pm_dev, int pm_dtype, int64_t num_particles, double pvol, double* gm_dev, double* gvol_dev, void* stream);
+/* fix_volume (:38-92, :257-264): in place on gvol, interior cells */
+int fs_dens3d_fix_volume(int nx, int ny, int nz, const double* cell_size3, double* gvol_dev, const double* sphi_dev, const double* lphi_dev,
+                         const double* wx_dev, const double* wy_dev, const double* wz_dev, void* stream);
+/* initialize_solver (:94-125, :266-272): b on interior cells (0 on non-fluid ones), boundary layer untouched */
+int fs_dens3d_rhs(int nx, int ny, int nz, double rho0, double dt, const double* cell_size3, const double* gm_dev, const double* gvol_dev,
+                  const double* lphi_dev, const double* wx_dev, const double* wy_dev, const double* wz_dev, double* b_dev, void* stream);
+/* compute_displacement (:206-219, :280-284): dx,dy,dz[x,y,z] for x,y,z in 1..g-1 */
+int fs_dens3d_displacement(int nx, int ny, int nz, double dt, const double* cell_size3, double* dx_dev, double* dy_dev, double* dz_dev,
+                           const double* pv_dev, const double* lphi_dev, void* stream);
+/* apply_displacement (:221-248, :286-291): px[:,axis] += trilinear gather of d (shape s0,s1,s2) */
+int fs_dens3d_gather(void* px_dev, int px_dtype, int64_t num_particles, const double* d_dev, int s0, int s1, int s2,
+                     const double* bound_min3, const double* cell_size3, const double* grid_bias3, int axis, void* stream);
 
 #ifdef __cplusplus
 }

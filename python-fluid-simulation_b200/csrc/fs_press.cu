@@ -83,7 +83,12 @@ __device__ __forceinline__ double edge_in_fraction(double l, double r) {
 // deterministic block reduction at the very end (a reduction per 256 cells made the first version barrier-bound).
 constexpr int kPressBlocksPerSM = 6;
 
-template <int D, bool CG>
+// OP selects the operator: OP_PRESSURE = PressureCGSolver*.matvecmul_kernel (diagonal weighted by the face fractions);
+// OP_DENSITY = DensityCGSolver3D.matvecmul_kernel (:117-194): unit diagonal contributions, and the -z off-diagonal term
+// reads wz[x,y,z+1] (not wz[x,y,z]) exactly as the reference does (:184).
+enum { OP_PRESSURE = 0, OP_DENSITY = 1 };
+
+template <int D, bool CG, int OP>
 __global__ void __launch_bounds__(kPT) press_apply_kernel(Grid<D> g, const double* __restrict__ v, double* __restrict__ out, PressW<D> W,
                                                           const double* __restrict__ lphi, CgState* st, double* partials) {
     if (CG) { if (*(volatile int*)&st->done) return; }
@@ -104,13 +109,15 @@ __global__ void __launch_bounds__(kPT) press_apply_kernel(Grid<D> g, const doubl
                 for (int sgn = 1; sgn >= -1; sgn -= 2) {          // +a then -a
                     const long long j = i + sgn * g.cs[a];
                     const double nphi = __ldg(lphi + j);
-                    const double w = __ldg(W.w[a] + face_idx<D>(g, a, c, sgn > 0 ? 1 : 0));
+                    const int foff = (sgn > 0 || (OP == OP_DENSITY && a == D - 1)) ? 1 : 0;
+                    const double w = __ldg(W.w[a] + face_idx<D>(g, a, c, foff));
+                    const double dw = (OP == OP_DENSITY) ? 1.0 : w;
                     if (nphi < 0) {
                         val = __dsub_rn(val, __dmul_rn(w, __ldg(v + j)));
-                        diag = __dadd_rn(diag, w);
+                        diag = __dadd_rn(diag, dw);
                     } else {
                         const double frac = fmin(1.0, fmax(0.01, phi / __dsub_rn(phi, nphi)));
-                        diag = __dadd_rn(diag, w / frac);
+                        diag = __dadd_rn(diag, dw / frac);
                     }
                 }
             }
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(kPT) press_activity_kernel(Grid<D> g, const do
 }
 
 // one pass over the active segments: out = A v on computed rows (a warp per 32-cell segment), returns this thread's share of v.out
-template <int D>
+template <int D, int OP>
 __device__ __forceinline__ double press_apply_seg_body(const Grid<D>& g, const double* v, double* out, const PressW<D>& W,
                                                        const double* __restrict__ lphi, const int* __restrict__ seg, int nseg) {
     const int lane = threadIdx.x & 31;
@@ -183,13 +190,15 @@ __device__ __forceinline__ double press_apply_seg_body(const Grid<D>& g, const d
             for (int sgn = 1; sgn >= -1; sgn -= 2) {          // +a then -a
                 const long long j = i + sgn * g.cs[a];
                 const double nphi = __ldg(lphi + j);
-                const double w = __ldg(W.w[a] + face_idx<D>(g, a, c, sgn > 0 ? 1 : 0));
+                const int foff = (sgn > 0 || (OP == OP_DENSITY && a == D - 1)) ? 1 : 0;
+                const double w = __ldg(W.w[a] + face_idx<D>(g, a, c, foff));
+                const double dw = (OP == OP_DENSITY) ? 1.0 : w;
                 if (nphi < 0) {
                     val = __dsub_rn(val, __dmul_rn(w, v[j]));
-                    diag = __dadd_rn(diag, w);
+                    diag = __dadd_rn(diag, dw);
                 } else {
                     const double frac = fmin(1.0, fmax(0.01, phi / __dsub_rn(phi, nphi)));
-                    diag = __dadd_rn(diag, w / frac);
+                    diag = __dadd_rn(diag, dw / frac);
                 }
             }
         }
@@ -200,7 +209,7 @@ __device__ __forceinline__ double press_apply_seg_body(const Grid<D>& g, const d
     return acc;
 }
 
-template <int D>
+template <int D, int OP>
 __global__ void __launch_bounds__(kPersistThreads, 1) press_cg_persistent_kernel(Grid<D> g, double* x, double* r, double* d, double* q, PressW<D> W,
                                                                                  const double* __restrict__ lphi, const int* __restrict__ seg,
                                                                                  const int* __restrict__ nseg_p, CgState* st, double* partials,
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) press_cg_persistent_kernel
     PeerHot hot;                                     // unused (single GPU)
     hot.has_lo = hot.has_hi = 0;
     for (int it = 0; it < n_iters && !done; ++it) {
-        double acc = press_apply_seg_body<D>(g, d, q, W, lphi, seg, nseg);
+        double acc = press_apply_seg_body<D, OP>(g, d, q, W, lphi, seg, nseg);
         dq = grid_allreduce(acc, partials, gs);
         alpha_d = delta / dq;
         acc = cg_update_xr_seg_body<double, 1, false>(g.ncells, g.ncells, seg, nseg, x, r, d, q, alpha_d, hot);
@@ -370,6 +379,7 @@ struct fs_press {
     SegList seg;           // active 32-cell segments of the current solve
     GridBar* bar;
     bool use_list;         // the current solve iterates on the active list with the persistent kernel
+    int op;                // OP_PRESSURE / OP_DENSITY
 };
 
 struct PressLayout { size_t st, act, seglist, segscratch, bar, total; };
@@ -407,12 +417,17 @@ static int press_apply_launch(fs_press* h, const double* v, double* out, const d
     const int pg = h->grid < kSMs * kPressBlocksPerSM ? h->grid : kSMs * kPressBlocksPerSM;
     if (h->nz > 0) {
         auto g = make_grid<3>(h->nx, h->ny, h->nz);
-        if (cg) press_apply_kernel<3, true><<<pg, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
-        else press_apply_kernel<3, false><<<pg, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
+        if (h->op == OP_DENSITY) {
+            if (cg) press_apply_kernel<3, true, OP_DENSITY><<<pg, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
+            else press_apply_kernel<3, false, OP_DENSITY><<<pg, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
+        } else {
+            if (cg) press_apply_kernel<3, true, OP_PRESSURE><<<pg, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
+            else press_apply_kernel<3, false, OP_PRESSURE><<<pg, kPT, 0, s>>>(g, v, out, mkW<3>(wx, wy, wz), lphi, h->st, h->partials);
+        }
     } else {
         auto g = make_grid<2>(h->nx, h->ny, 0);
-        if (cg) press_apply_kernel<2, true><<<pg, kPT, 0, s>>>(g, v, out, mkW<2>(wx, wy, nullptr), lphi, h->st, h->partials);
-        else press_apply_kernel<2, false><<<pg, kPT, 0, s>>>(g, v, out, mkW<2>(wx, wy, nullptr), lphi, h->st, h->partials);
+        if (cg) press_apply_kernel<2, true, OP_PRESSURE><<<pg, kPT, 0, s>>>(g, v, out, mkW<2>(wx, wy, nullptr), lphi, h->st, h->partials);
+        else press_apply_kernel<2, false, OP_PRESSURE><<<pg, kPT, 0, s>>>(g, v, out, mkW<2>(wx, wy, nullptr), lphi, h->st, h->partials);
     }
     FS_LAUNCH_CHECK();
     return FS_OK;
@@ -465,12 +480,13 @@ static int press_persistent(fs_press* h, double* x, double* d, double* r, double
             Grid<3> g = make_grid<3>(h->nx, h->ny, h->nz);
             PressW<3> W = mkW<3>(wx, wy, wz);
             void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni};
-            e = cudaLaunchCooperativeKernel((const void*)press_cg_persistent_kernel<3>, dim3(grid), dim3(kPersistThreads), args, 0, s);
+            const void* fn = h->op == OP_DENSITY ? (const void*)press_cg_persistent_kernel<3, OP_DENSITY> : (const void*)press_cg_persistent_kernel<3, OP_PRESSURE>;
+            e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args, 0, s);
         } else {
             Grid<2> g = make_grid<2>(h->nx, h->ny, 0);
             PressW<2> W = mkW<2>(wx, wy, nullptr);
             void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni};
-            e = cudaLaunchCooperativeKernel((const void*)press_cg_persistent_kernel<2>, dim3(grid), dim3(kPersistThreads), args, 0, s);
+            e = cudaLaunchCooperativeKernel((const void*)press_cg_persistent_kernel<2, OP_PRESSURE>, dim3(grid), dim3(kPersistThreads), args, 0, s);
         }
         if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
         FS_LAUNCH_CHECK();
@@ -531,6 +547,15 @@ void fs_press_destroy(fs_press* h) {
     h->cg.destroy();
     h->seg.destroy();
     delete h;
+}
+
+int fs_press_set_operator(fs_press* h, int op) {
+    if (!h) return fail(FS_ERR_ARG, "null handle");
+    if (op != FS_OP_PRESSURE && op != FS_OP_DENSITY) return fail(FS_ERR_ARG, "fs_press_set_operator: bad operator");
+    if (op == FS_OP_DENSITY && h->nz == 0) return fail(FS_ERR_ARG, "fs_press_set_operator: the density operator is 3-D only");
+    h->op = op;
+    h->graph.valid = false;
+    return FS_OK;
 }
 
 int fs_press_apply(fs_press* h, const double* v, double* out, const double* wx, const double* wy, const double* wz, const double* lphi, void* stream) {

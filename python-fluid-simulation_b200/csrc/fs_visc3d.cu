@@ -763,6 +763,8 @@ static int visc3d_halo_vec(fs_visc3d* h, int vec, cudaStream_t s) {
 
 extern "C" {
 
+static bool visc3d_use_persistent(const fs_visc3d* h);
+
 int fs_visc3d_set_slab(fs_visc3d* h, fs_comm* comm, int has_lo, int has_hi) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if ((has_lo || has_hi) && !comm) return fail(FS_ERR_ARG, "fs_visc3d_set_slab: neighbours need a communicator");
@@ -840,6 +842,12 @@ int fs_visc3d_set_cg_mode(fs_visc3d* h, int mode) {
     if (mode != FS_CG_AUTO && mode != FS_CG_KERNELS && mode != FS_CG_PERSISTENT) return fail(FS_ERR_ARG, "fs_visc3d_set_cg_mode: bad mode");
     h->cg_mode = mode;
     return FS_OK;
+}
+
+int fs_visc3d_cg_mode_in_use(fs_visc3d* h) {
+    if (!h) return fail(FS_ERR_ARG, "null handle");
+    if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_cg_mode_in_use before fs_visc3d_pack");
+    return visc3d_use_persistent(h) ? FS_CG_PERSISTENT : FS_CG_KERNELS;
 }
 
 int fs_visc3d_set_active_mode(fs_visc3d* h, int mode) {

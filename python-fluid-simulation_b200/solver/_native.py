@@ -17,6 +17,7 @@ VEC_X, VEC_R, VEC_D, VEC_Q, VEC_B = range(5)
 STORE_ALL, STORE_INTERIOR, STORE_FLUID = range(3)
 ACTIVE_FLUID, ACTIVE_NONZERO = range(2)
 CG_AUTO, CG_KERNELS, CG_PERSISTENT = range(3)
+OP_PRESSURE, OP_DENSITY = range(2)
 
 
 class CgStats(Structure):
@@ -43,6 +44,7 @@ _SIGS = {
     "fs_visc3d_vector_ptr": (c_void_p, [c_void_p, c_int, c_int]),
     "fs_visc3d_set_active_mode": (c_int, [c_void_p, c_int]),
     "fs_visc3d_set_cg_mode": (c_int, [c_void_p, c_int]),
+    "fs_visc3d_cg_mode_in_use": (c_int, [c_void_p]),
     "fs_visc3d_debug_read": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     "fs_visc3d_active_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), c_void_p]),
     "fs_visc3d_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
@@ -92,6 +94,7 @@ _SIGS = {
     "fs_press_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "fs_press_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_size_t]),
     "fs_press_destroy": (None, [c_void_p]),
+    "fs_press_set_operator": (c_int, [c_void_p, c_int]),
     "fs_press_rhs": (c_int, [c_void_p, POINTER(c_double), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "fs_press_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -101,6 +104,15 @@ _SIGS = {
                             c_double, c_int64, POINTER(CgStats), c_void_p]),
     "fs_press_cg_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int64, c_void_p]),
+    # density solver (DensityCGSolver3D)
+    "fs_dens3d_scatter": (c_int, [c_int, c_int, c_int, POINTER(c_double), POINTER(c_double), c_void_p, c_int, c_void_p, c_int, c_int64, c_double,
+                                  c_void_p, c_void_p, c_void_p]),
+    "fs_dens3d_fix_volume": (c_int, [c_int, c_int, c_int, POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fs_dens3d_rhs": (c_int, [c_int, c_int, c_int, c_double, c_double, POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p]),
+    "fs_dens3d_displacement": (c_int, [c_int, c_int, c_int, c_double, POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fs_dens3d_gather": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_double),
+                                 c_int, c_void_p]),
 }
 
 _lib = None

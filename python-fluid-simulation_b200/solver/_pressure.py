@@ -19,9 +19,10 @@ def fine_shape(g):
 class Engine:
     """One native fs_press handle (+ its small device workspace) per grid resolution."""
 
-    def __init__(self, g):
+    def __init__(self, g, op="pressure"):
         self.lib = N.load()
         self.g = tuple(g)
+        self.op = op
         nz = self.g[2] if len(self.g) == 3 else 0
         self.dims = (self.g[0], self.g[1], nz)
         nbytes = self.lib.fs_press_workspace_bytes(*self.dims)
@@ -31,6 +32,8 @@ class Engine:
         h = ctypes.c_void_p()
         N.check(self.lib.fs_press_create(ctypes.byref(h), *self.dims, self.ws.data_ptr(), nbytes), "fs_press_create")
         self.h = h
+        if op != "pressure":       # the density solver shares the CG machinery with a different operator (fs_press_set_operator)
+            N.check(self.lib.fs_press_set_operator(h, {"density": N.OP_DENSITY}[op]), "fs_press_set_operator")
 
     def __del__(self):
         try:
@@ -44,13 +47,13 @@ class Engine:
 _engines = {}
 
 
-def engine(g):
-    key = (tuple(g), torch.cuda.current_device())
+def engine(g, op="pressure"):
+    key = (tuple(g), op, torch.cuda.current_device())
     e = _engines.get(key)
     if e is None:
         if len(_engines) > 8:
             _engines.clear()
-        e = _engines[key] = Engine(g)
+        e = _engines[key] = Engine(g, op)
     return e
 
 
