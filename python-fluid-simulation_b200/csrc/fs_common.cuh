@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_d_seg_kernel(long long 
 // Arrival is an acq_rel atomic (releases this block's writes — bar.sync before it makes that
 // cumulative over the block); waiters spin on an acquire load.
 // ---------------------------------------------------------------------------------------------
-struct GridBar { unsigned int count; unsigned int flag; double gsum[2]; };
+struct GridBar { unsigned int count; unsigned int pad; unsigned long long result_ll[8]; };
 
 __device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
     unsigned int r;
@@ -556,13 +556,15 @@ __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) 
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 struct GridSync {
     GridBar* bar;
     unsigned int passed;     // barriers passed so far in this launch (identical in every thread of the grid)
     __device__ __forceinline__ void arrive_and_wait(bool system_scope) {   // thread 0 of the block only
         ++passed;
         const unsigned int target = passed * gridDim.x;
-        if (system_scope) __threadfence_system();                          // stores into a peer GPU need system scope
+        if (system_scope) fence_acq_rel_sys();                             // stores into a peer GPU need system scope
         if (atom_add_acq_rel_gpu(&bar->count, 1u) + 1u < target) {
             while (ld_acquire_gpu(&bar->count) < target) { }
         }
@@ -595,20 +597,34 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
-// Multi-GPU part of grid_allreduce: `local` is this rank's sum (known to every block).  Block 0 publishes it to every
-// rank's mailbox (its own included); warp 0 of EVERY block then collects the N rank sums from the local mailbox and adds
-// them in rank order, so no second hop through a flag is needed and every block of every rank obtains the same bits.
-// Mailbox words are LL-style (4 data bytes + 4-byte sequence number); the polling loads are relaxed and one acquire
-// fence follows, so the q halo rows a neighbour stored before publishing are visible afterwards.  seq = sequence number of this reduction (the same
-// in every block; the caller keeps the running count).  Bounded spin: a dead peer yields NaN and P->error = 1.
-__device__ __forceinline__ double peer_allreduce_block(double local, PeerInfo* P, int kind, unsigned int seq, double* sm_bcast) {
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Multi-GPU part of grid_allreduce: `local` is this rank's sum (known to every block).  Warp 0 of block 0 publishes it
+// to every rank's mailbox (its own included), collects the N rank sums from the local mailbox, adds them in rank order
+// and republishes the total in a local LL-style word pair that the other blocks poll: only N lanes of one warp spin at
+// system scope on the mailbox line the NVLink writes land in (every block polling it made the reduction slower with
+// every added rank), the other 147 blocks spin on a private line at GPU scope.  Mailbox and result words carry 4 data
+// bytes + a 4-byte sequence number, so no separate flag round trip is needed; one acquire fence after the spin makes
+// the q halo rows a neighbour stored before publishing visible.  seq = sequence number of this reduction (the same in
+// every block; the caller keeps the running count).  Bounded spin: a dead peer yields NaN and P->error = 1.
+__device__ __forceinline__ double peer_allreduce_block(double local, PeerInfo* P, int kind, unsigned int seq, double* sm_bcast,
+                                                       unsigned long long* result_ll /*[2 kinds][2 parities][2 words], local*/) {
     const int lane = threadIdx.x & 31;
+    unsigned long long* res = result_ll + ((kind & 1) * 2 + (int)(seq & 1u)) * 2;     // per kind and parity: tags of the two kinds coincide
     if (threadIdx.x < 32) {
-        const int n = P->nranks, me = P->rank;
-        const int slot = ((kind * 2 + (int)(seq & 1u)) * kMaxRanks);
+        double sum = 0.0;
         if (blockIdx.x == 0) {
+            const int n = P->nranks, me = P->rank;
+            const int slot = ((kind * 2 + (int)(seq & 1u)) * kMaxRanks);
             const unsigned long long bits = (unsigned long long)__double_as_longlong(local);
             const unsigned long long w0 = ((unsigned long long)seq << 32) | (bits & 0xffffffffull);
             const unsigned long long w1 = ((unsigned long long)seq << 32) | (bits >> 32);
@@ -618,28 +634,43 @@ __device__ __forceinline__ double peer_allreduce_block(double local, PeerInfo* P
                 st_relaxed_sys_u64(dst, w0);
                 st_relaxed_sys_u64(dst + 1, w1);
             }
-        }
-        double v = 0.0;
-        bool ok = true;
-        if (lane < n) {
-            const unsigned long long* src = P->mbox[me] + (slot + lane) * 2;
+            double v = 0.0;
+            bool ok = true;
+            if (lane < n) {
+                const unsigned long long* src = P->mbox[me] + (slot + lane) * 2;
+                unsigned long long a, b;
+                const long long t0 = clock64();
+                for (;;) {
+                    a = ld_relaxed_sys_u64(src);
+                    b = ld_relaxed_sys_u64(src + 1);
+                    if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
+                    if (clock64() - t0 > 20000000000LL) { ok = false; break; }     // ~10 s: a peer died; bail out instead of hanging
+                }
+                v = __longlong_as_double((long long)(((b & 0xffffffffull) << 32) | (a & 0xffffffffull)));
+            }
+            fence_acq_rel_sys();                       // acquire what the peers stored before publishing; release it to the local blocks
+            if (!__all_sync(0xffffffffu, ok)) {
+                if (lane == 0) P->error = 1;
+                sum = __longlong_as_double(0x7ff8000000000000LL);
+            } else {
+                for (int r = 0; r < n; ++r) sum += __shfl_sync(0xffffffffu, v, r);        // fixed rank order
+            }
+            if (lane == 0) {
+                const unsigned long long sb = (unsigned long long)__double_as_longlong(sum);
+                st_relaxed_gpu_u64(res, ((unsigned long long)seq << 32) | (sb & 0xffffffffull));
+                st_relaxed_gpu_u64(res + 1, ((unsigned long long)seq << 32) | (sb >> 32));
+            }
+        } else if (lane == 0) {
             unsigned long long a, b;
             const long long t0 = clock64();
             for (;;) {
-                a = ld_relaxed_sys_u64(src);
-                b = ld_relaxed_sys_u64(src + 1);
+                a = ld_relaxed_gpu_u64(res);
+                b = ld_relaxed_gpu_u64(res + 1);
                 if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
-                if (clock64() - t0 > 20000000000LL) { ok = false; break; }     // ~10 s: a peer died; bail out instead of hanging
+                if (clock64() - t0 > 40000000000LL) { a = 0; b = 0x7ff80000ull; break; }   // block 0 gave up: NaN
             }
-            v = __longlong_as_double((long long)(((b & 0xffffffffull) << 32) | (a & 0xffffffffull)));
-        }
-        fence_acq_rel_sys();                           // acquire: what the peers stored before publishing is visible from here on
-        double sum = 0.0;
-        if (!__all_sync(0xffffffffu, ok)) {
-            if (lane == 0) P->error = 1;
-            sum = __longlong_as_double(0x7ff8000000000000LL);
-        } else {
-            for (int r = 0; r < n; ++r) sum += __shfl_sync(0xffffffffu, v, r);        // fixed rank order
+            fence_acq_rel_gpu();
+            sum = __longlong_as_double((long long)(((b & 0xffffffffull) << 32) | (a & 0xffffffffull)));
         }
         if (lane == 0) *sm_bcast = sum;
     }
@@ -667,7 +698,7 @@ __device__ __forceinline__ double grid_allreduce(double v, double* partials /*2*
     double s = 0.0;
     for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) s += __ldcg(slot + i);
     s = block_sum_all(s, sm);
-    if (peers) s = peer_allreduce_block(s, peers, kind, seq, &s_glob);
+    if (peers) s = peer_allreduce_block(s, peers, kind, seq, &s_glob, gs.bar->result_ll);
     return s;
 }
 

@@ -188,3 +188,44 @@ def test_extrapolation_worklists_and_overflow_fallback(cap, monkeypatch):
 
 
 _EXTRAP_CACHE = {}
+
+
+@pytest.mark.parametrize("N,mu", [(128, 100.0), (256, 100.0)])
+def test_true_residual_at_full_size(N, mu):
+    """Size-independent end-to-end property at BASELINE.json's full size: after solve() on the benchmark scene, the TRUE
+    residual b - A x — recomputed with the dense masked operator kernel (fs_visc3d_apply: one thread per lattice point, no
+    lists, no persistent kernel) — matches the recursively updated residual the CG stopped on, and x is untouched outside
+    the active set.  This ties the active-set / persistent path to the dense operator on 50 million faces."""
+    import ctypes
+    import scenes
+    from solver import _native as N_
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    sc = scenes.buckling(N, device="cuda", mu=mu)
+    s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
+    v = [sc[k].clone() for k in ("vx", "vy", "vz")]
+    s.solve(sc["dt"], mu, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"], tol=1e-3)
+    assert s.delta < 1e-6 and s.iterations > 50
+    segs, total, rows = s.active_info()
+    assert 0 < segs < total
+    lib, e = N_.load(), s._e
+    scale = sc["dt"] / s.cell_vol / sc["rho"]
+    b = [a.clone() for a in (s.b_x, s.b_y, s.b_z)]
+    r = [a.clone() for a in (s.r_x, s.r_y, s.r_z)]
+    x = [a.clone() for a in (s.x_x, s.x_y, s.x_z)]
+    N_.check(lib.fs_visc3d_apply(e.h, scale, mu, N_.VEC_X, N_.VEC_Q, 0), "apply")       # q = A x, dense masked kernel
+    torch.cuda.synchronize()
+    true_rr = 0.0
+    rec_rr = 0.0
+    bnorm = 0.0
+    for bb, rr, qq in zip(b, r, (s.q_x, s.q_y, s.q_z)):
+        t = bb - qq
+        true_rr += float((t * t).sum())
+        rec_rr += float((rr * rr).sum())
+        bnorm += float((bb * bb).sum())
+        assert float((t - rr).abs().max()) < 1e-7 * max(1.0, float(bb.abs().max()))
+    assert abs(rec_rr - s.delta) <= 1e-9 * max(s.delta, 1e-300)
+    assert true_rr < 4.0 * s.delta + 1e-10 * bnorm
+    # rows outside the active set: the solution equals the (extrapolated) start value, i.e. the caller's arrays are unchanged
+    changed = sum(int((a != b0).sum()) for a, b0 in zip(v, (sc["vx"], sc["vy"], sc["vz"])))
+    assert 0 < changed <= rows
+    del x
