@@ -119,9 +119,13 @@ int SegList::init(long long npts, void* list_dev, void* scratch_dev) {
 void SegList::destroy() {
     if (nseg_pinned) cudaFreeHost(nseg_pinned);
     nseg_pinned = nullptr;
+    if (ready) cudaEventDestroy(ready);
+    ready = nullptr;
+    pending = false;
 }
 
-int SegList::build(const uint8_t* act, cudaStream_t s) {
+int SegList::enqueue(const uint8_t* act, cudaStream_t s) {
+    if (!ready) FS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     seg_count_kernel<<<nblocks, kSegBlock, 0, s>>>(act, nseg_total, block_off);
     FS_LAUNCH_CHECK();
     seg_scan_kernel<<<1, 1024, 0, s>>>(block_off, nblocks, nseg_dev);
@@ -129,9 +133,22 @@ int SegList::build(const uint8_t* act, cudaStream_t s) {
     seg_write_kernel<<<nblocks, kSegBlock, 0, s>>>(act, nseg_total, block_off, list);
     FS_LAUNCH_CHECK();
     FS_CUDA(cudaMemcpyAsync(nseg_pinned, nseg_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
-    FS_CUDA(cudaStreamSynchronize(s));
+    FS_CUDA(cudaEventRecord(ready, s));
+    pending = true;
+    return FS_OK;
+}
+
+int SegList::finish() {
+    if (!pending) return FS_OK;
+    FS_CUDA(cudaEventSynchronize(ready));
+    pending = false;
     nseg = *nseg_pinned;
     return FS_OK;
+}
+
+int SegList::build(const uint8_t* act, cudaStream_t s) {
+    FS_TRY(enqueue(act, s));
+    return finish();
 }
 
 bool IterGraph::enabled() {

@@ -390,8 +390,14 @@ struct SegList {
     }
     int init(long long npts, void* list_dev, void* scratch_dev);
     void destroy();
-    // act: one byte per point, readable up to 32*nseg_total bytes.  Blocks until the count is on the host.
+    // act: one byte per point, readable up to 32*nseg_total bytes.  build() = enqueue() + finish().
+    // enqueue() launches the three list kernels and the async read-back of the count; finish() blocks until the count
+    // is on the host.  Independent work enqueued in between hides the host round trip.
+    int enqueue(const uint8_t* act, cudaStream_t s);
+    int finish();
     int build(const uint8_t* act, cudaStream_t s);
+    cudaEvent_t ready = nullptr;
+    bool pending = false;
 };
 
 // grid size for a list-walking kernel: enough CTAs for the list, at most `cap`; the list length is rounded up to a

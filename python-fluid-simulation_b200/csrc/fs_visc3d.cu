@@ -847,6 +847,7 @@ int fs_visc3d_set_cg_mode(fs_visc3d* h, int mode) {
 int fs_visc3d_cg_mode_in_use(fs_visc3d* h) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_cg_mode_in_use before fs_visc3d_pack");
+    FS_TRY(h->seg.finish());
     return visc3d_use_persistent(h) ? FS_CG_PERSISTENT : FS_CG_KERNELS;
 }
 
@@ -870,6 +871,7 @@ __global__ void visc3d_count_rows_kernel(const uint8_t* act, long long n, unsign
 int fs_visc3d_active_info(fs_visc3d* h, int64_t* segments, int64_t* segments_total, int64_t* rows, void* stream) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_active_info before fs_visc3d_pack");
+    FS_TRY(h->seg.finish());
     cudaStream_t s = (cudaStream_t)stream;
     if (rows) {
         if (h->active_rows < 0) {       // counted on demand; `partials` is free between solves
@@ -963,6 +965,7 @@ void* fs_visc3d_vector_ptr(const fs_visc3d* h, int vec, int comp) {
 int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double vol_norm, void* stream) {
     if (!h || !sphi || !lvol) return fail(FS_ERR_ARG, "fs_visc3d_pack: null argument");
     cudaStream_t s = (cudaStream_t)stream;
+    FS_TRY(h->seg.finish());              // (a previous pack whose list length was never consumed)
     // keep "r, d, q, b are zero outside the active segments": wipe the previous solve's active segments (or everything,
     // if a dense API call wrote into those vectors since)
     if (h->sparse_clean) {
@@ -978,7 +981,7 @@ int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double 
     FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act,
                                                                                       h->active_mode == FS_ACTIVE_NONZERO ? 1 : 0));
     FS_LAUNCH_CHECK();
-    FS_TRY(h->seg.build(h->act, s));      // one host sync per solve: the list length sizes the CG launches
+    FS_TRY(h->seg.enqueue(h->act, s));    // the list length (read back asynchronously) sizes the CG launches: see visc3d_list_ready
     h->active_rows = -1;
     h->packed = true;
     return FS_OK;
@@ -1169,6 +1172,7 @@ static int visc3d_iterations(fs_visc3d* h, double sm, long long n, cudaStream_t 
 
 // Start of a solve on the active set (fs_visc3d_solve): one kernel builds b, q = A x, d = r = b - q and delta0.
 static int visc3d_cg_begin_sparse(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, cudaStream_t s) {
+    FS_TRY(h->seg.finish());                      // list length: enqueued by pack, needed from here on for the launch sizes
     const double sm = scale * mu;
     cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, (h->comm && !h->peers) ? 1 : 0);
     FS_LAUNCH_CHECK();
@@ -1198,6 +1202,7 @@ static int visc3d_cg_begin_sparse(fs_visc3d* h, double scale, double mu, double 
 }
 
 static int visc3d_cg_begin(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, cudaStream_t s) {
+    FS_TRY(h->seg.finish());
     const long long n = 3 * h->L.NL;
     cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, (h->comm && !h->peers) ? 1 : 0);
     FS_LAUNCH_CHECK();
@@ -1239,6 +1244,7 @@ int fs_visc3d_cg(fs_visc3d* h, double scale, double mu, double tol, int64_t max_
 int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void* stream) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_cg_enqueue before fs_visc3d_pack");
+    FS_TRY(h->seg.finish());
     const double sm = scale * mu;
     cg_state_unlimit_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->st);
     FS_LAUNCH_CHECK();
@@ -1248,6 +1254,7 @@ int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void*
 int fs_visc3d_kernel_enqueue(fs_visc3d* h, int which, double scale, double mu, int64_t n, void* stream) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_kernel_enqueue before fs_visc3d_pack");
+    FS_TRY(h->seg.finish());
     if (which < 1 || which > 3) return fail(FS_ERR_ARG, "fs_visc3d_kernel_enqueue: which must be 1, 2 or 3");
     cudaStream_t s = (cudaStream_t)stream;
     const double sm = scale * mu;
