@@ -143,6 +143,9 @@ def workload_config(args, n, where):
                         if where != "cpu" else f"buckling-{n}^3 high-viscosity (mu={args.mu:g}), ViscosityCGSolver3D CG iterations",
             "grid": [n, n, n], "mu": args.mu, "dt": 1.0 / 300, "rho": 1000.0, "iters_per_step": args.iters if where != "cpu" else args.ref_iters,
             "partition": f"x-slabs over {args.gpus} GPU(s)" if args.gpus > 1 else "single GPU",
+            "active_set": getattr(args, "active_set", "nonzero") + " (the CG kernels visit only rows with a non-zero operator row; same iterates, "
+                          "iteration counts and velocities as the dense loop: tests/test_active_set_gpu.py)"
+                          if getattr(args, "active_set", "nonzero") == "nonzero" else "fluid (every row the reference's kernels compute)",
             "l2": "working set >> L2 (inputs larger than L2, no explicit flush)"}
 
 

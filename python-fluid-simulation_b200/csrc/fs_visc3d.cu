@@ -6,13 +6,19 @@
 // shared by every array so a single flat index i=(x*Y+y)*Zp+z addresses the u,v,w faces, the cell
 // centre and the three low edges that belong to lattice point (x,y,z); neighbours are i+-1, i+-Zp,
 // i+-Y*Zp for every array alike.
-//   coef[0..2]  Vu,Vv,Vw   face liquid-volume fraction; NaN on rows the operator never computes
-//                          (solid faces, the frozen boundary layer, lattice padding)
+//   coef[0..2]  Vu,Vv,Vw   face liquid-volume fraction (NaN where the row is never computed)
 //   coef[3]     Vc         cell-centre volume
 //   coef[4..6]  Exy,Exz,Eyz edge-centred volumes
 //   mask[0..2]  fluid flag of each face (sphi >= 0), bytes; used by the masked apply / RHS /
 //                          extrapolation / write-back only — never inside the CG loop
-//   vec[v][c]   X,R,D,Q,B  solver vectors, 3 components each, NL elements per component
+//   act         1 byte per lattice point: bit c = row of component c is computed (bits 4..6: by a neighbour slab)
+//   seg list    sorted ids of the active 32-point segments (any act bit set): what K1/K2/K3 walk
+//   vec[v][c]   X,R,D,Q,B  solver vectors, 3 components each, NL elements per component;
+//                          R,D,Q,B are exactly zero outside the active segments (invariant kept by pack)
+//
+// One solve:  pack (+ activity map, segment list) -> load -> 3 in-place extrapolation sweeps -> begin (b, q=Ax, r=d=b-q,
+// delta0 on the active set) -> CG iterations (one persistent cooperative kernel, or K1/K2/K3 from a CUDA graph for
+// HBM-sized active sets) -> write-back of the active rows.
 #include <type_traits>
 
 #include "fs_comm.cuh"

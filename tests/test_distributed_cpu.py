@@ -97,3 +97,45 @@ def test_scatter_and_halos_world2_gloo():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_active_set_plane_cost():
+    """plane_cost_active: planes without liquid (non-zero mode) / without fluid (fluid mode) cost 1, the others more, and the
+    balanced cuts give the liquid planes to more ranks than an equal split would."""
+    import scenes
+    from solver.distributed import SlabPartition, balanced_starts, plane_cost_active
+    sc = scenes.buckling(32)
+    g = sc["gres"]
+    for mode in ("nonzero", "fluid"):
+        cost = plane_cost_active(sc["sphi"], sc["lvol"], g, mode)
+        assert cost.shape == (g[0],) and cost.min() >= 1.0 and cost.max() > 1.0
+        centres = sc["sphi"][1::2, 1::2, 1::2]
+        outside = (centres >= 0).sum(dim=(1, 2)).numpy() == 0                      # planes entirely inside the solid
+        if mode == "fluid":
+            assert np.all(cost[outside] == 1.0)
+        nz_planes = (sc["lvol"] != 0).sum(dim=(1, 2)).numpy()
+        no_liquid = (nz_planes[0:-1:2] + nz_planes[1::2] + nz_planes[2::2]) == 0
+        if mode == "nonzero":
+            assert np.all(cost[no_liquid] == 1.0) and np.all(cost[~no_liquid] > 1.0)
+        starts = balanced_starts(cost, 4)
+        parts = [SlabPartition(g, 4, r, plane_cost=cost) for r in range(4)]
+        assert [p.c0 for p in parts] + [g[0]] == starts
+        sums = [cost[a:b].sum() for a, b in zip(starts, starts[1:])]
+        eq = [cost[a:b].sum() for a, b in zip(range(0, 32, 8), range(8, 40, 8))]
+        assert max(sums) <= max(eq) + 1e-9
+
+
+def test_density_module_surface_without_gpu():
+    """The drop-in module exposes the reference's names (DensityCGSolver3D.py:250-291, :283) and refuses to run without CUDA."""
+    import inspect
+    from solver import DensityCGSolver3D as Dn
+    for name in ("initialize_density", "fix_volume", "initialize_solver", "matvecmul", "compute_displacement", "apply_displacement",
+                 "DensityCGSolver3D", "compute_solid_frac", "edge_in_fraction"):
+        assert hasattr(Dn, name), name
+    sig = inspect.signature(Dn.DensityCGSolver3D.solve)
+    assert list(sig.parameters)[1:] == ["rho0", "dt", "px", "pm", "pvol", "vx", "vy", "vz", "sphi", "sv", "lphi", "lvol", "wx", "wy", "wz", "tol"]
+    assert sig.parameters["tol"].default == 1e-3 and sig.parameters["wx"].default is None
+    assert list(inspect.signature(Dn.DensityCGSolver3D.__init__).parameters)[1:] == ["buf", "gres", "bound_min", "bound_size"]
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            Dn.DensityCGSolver3D(None, (8, 8, 8), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
