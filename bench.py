@@ -364,7 +364,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="solver storage/arithmetic type (reference: f64)")
     ap.add_argument("--active-set", default="nonzero", choices=["nonzero", "fluid"],
                     help="rows the CG kernels visit: nonzero (default) = rows with a non-zero coefficient; fluid = every row the reference computes")
-    ap.add_argument("--cg-mode", default="auto", choices=["auto", "kernels", "persistent"],
+    ap.add_argument("--cg-mode", default="auto", choices=["auto", "kernels", "persistent", "persistent_fold"],
                     help="three kernels per iteration from a CUDA graph, one persistent cooperative kernel, or auto by working-set size")
     ap.add_argument("--scene", default="buckling", choices=["buckling", "column"],
                     help="buckling = BASELINE config 4 (default); column = dense-fluid viscous column (config 5 geometry) for kernel studies")

@@ -72,6 +72,7 @@ extern "C" {
 #define FS_CG_AUTO 0
 #define FS_CG_KERNELS 1
 #define FS_CG_PERSISTENT 2
+#define FS_CG_PERSISTENT_FOLD 3 /* persistent, with the d update folded into the next apply phase (two grid barriers per iteration) */
 
 /* result of a CG run */
 typedef struct fs_cg_stats {

@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(kThreads) visc3d_begin_kernel(Visc3Dev<T> P, T
 
 // zero r, d, q, b on the segments of the (previous) active list
 template <typename T>
-__global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T* __restrict__ vecs /*[5][3][NL]*/, const int* __restrict__ seg,
-                                                                const int* __restrict__ nseg_p) {
+__global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T* __restrict__ vecs /*[5][3][NL]*/, T* __restrict__ d2 /*[3][NL]*/,
+                                                                const int* __restrict__ seg, const int* __restrict__ nseg_p) {
     const int nseg = *nseg_p;
     const int lane = threadIdx.x & 31;
     const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -451,6 +451,8 @@ __global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T*
         for (int v = FS_VEC_R; v <= FS_VEC_B; ++v)
 #pragma unroll
             for (int c = 0; c < 3; ++c) vecs[((long long)v * 3 + c) * NL + i] = T(0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d2[(long long)c * NL + i] = T(0);
     }
 }
 
@@ -498,6 +500,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_store_active_kernel(Lat3 L, c
 // around the coefficient and vector regions for exactly that.  One block reduction at the very end
 // (fixed order, deterministic).
 // ---------------------------------------------------------------------------------------------
+constexpr bool kFoldByDefault = false;   // FS_CG_AUTO: fold K3 into K1 inside the persistent kernel
 constexpr int kK1Threads = 256;
 constexpr int kK1SegsPerBlock = kK1Threads / 32;
 // CTAs per SM: the fp64 body keeps 43 loaded values (86 registers) in flight, so it gets 128 registers per thread
@@ -563,6 +566,82 @@ __device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T 
     return acc;
 }
 
+// K3 folded into K1 (persistent kernel only): the search direction of this iteration, d_new = r + beta d_old, is formed
+// on the fly for the point itself AND for its 26 stencil neighbours from r and d_old, stored for the point (all three
+// components of every point of the segment, computed row or not — mirrored halo rows included), and q = A d_new follows
+// as usual.  d_old must stay intact while other CTAs read it, so d ping-pongs between two buffers.  This removes the
+// separate d-update phase and its grid barrier from every iteration.
+template <typename T, bool DIST>
+__device__ __forceinline__ double visc3d_apply_dot_fold_body(const Visc3Dev<T>& P, T s, T s2, const T* dold, const T* r, T beta, T* dnew, T* q,
+                                                             const int* __restrict__ seg, int nseg, const PeerHot& hot, bool& wrote_peer) {
+    const Lat3& L = P.L;
+    const long long NL = L.NL;
+    const long long st[3] = {L.sx, L.sy, 1};
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    auto nb = [&](int comp, long long j) -> T { return r[comp * NL + j] + beta * dold[comp * NL + j]; };
+    int sg_n = w0 < nseg ? __ldg(seg + w0) : 0;
+    for (long long k = w0; k < nseg; k += nw) {
+        const long long i = (long long)sg_n * kSegPts + lane;
+        {
+            const long long k2 = k + nw;
+            sg_n = k2 < nseg ? __ldg(seg + k2) : 0;
+        }
+        const bool in = i < NL;
+        const long long j = in ? i : (NL - 1);
+        const unsigned int a = in ? ((unsigned int)__ldg(P.act + i) & kActCompute) : 0u;
+        const bool au = a & 1u, av = a & 2u, aw = a & 4u;
+        const T cu = __ldg(P.coef[0] + j), cv = __ldg(P.coef[1] + j), cw = __ldg(P.coef[2] + j);
+        const T du = nb(0, j), dv = nb(1, j), dw = nb(2, j);
+        if (in) { dnew[i] = du; dnew[NL + i] = dv; dnew[2 * NL + i] = dw; }
+        const T ru = visc_row<T, 3, 0, false, ROW_APPLY>(P.coef, j, st, cu, du, s, s2, nb);
+        const T rv = visc_row<T, 3, 1, false, ROW_APPLY>(P.coef, j, st, cv, dv, s, s2, nb);
+        const T rw = visc_row<T, 3, 2, false, ROW_APPLY>(P.coef, j, st, cw, dw, s, s2, nb);
+        if (au) { q[i] = ru; acc += (double)du * (double)ru; }
+        if (av) { q[NL + i] = rv; acc += (double)dv * (double)rv; }
+        if (aw) { q[2 * NL + i] = rw; acc += (double)dw * (double)rw; }
+        if (DIST && a != 0u) {
+            const long long lo0 = L.sx, hi0 = (long long)(L.X - 3) * L.sx;
+            if (hot.has_lo && i >= lo0 && i < lo0 + L.sx) {
+                const long long o = i - lo0;
+                if (au) reinterpret_cast<T*>(hot.q_lo[0])[o] = ru;
+                if (av) reinterpret_cast<T*>(hot.q_lo[1])[o] = rv;
+                if (aw) reinterpret_cast<T*>(hot.q_lo[2])[o] = rw;
+                wrote_peer = true;
+            }
+            if (hot.has_hi && i >= hi0 && i < hi0 + L.sx) {
+                const long long o = i - hi0;
+                if (au) reinterpret_cast<T*>(hot.q_hi[0])[o] = ru;
+                if (av) reinterpret_cast<T*>(hot.q_hi[1])[o] = rv;
+                if (aw) reinterpret_cast<T*>(hot.q_hi[2])[o] = rw;
+                wrote_peer = true;
+            }
+        }
+    }
+    return acc;
+}
+
+// end of a folded launch: dst = r + beta * src (pending d update) or dst = src (beta_valid == false), own segments
+template <typename T>
+__device__ __forceinline__ void visc3d_fold_finish_body(long long NL, const int* __restrict__ seg, int nseg, T* dst, const T* src, const T* r,
+                                                        T beta, bool apply_beta) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long k = w0; k < nseg; k += nw) {
+        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+        if (i >= NL) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const long long e = c * NL + i;
+            const T v = src[e];
+            dst[e] = apply_beta ? (r[e] + beta * v) : v;
+        }
+    }
+}
+
 template <typename T, bool DIST>
 __global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ d, T* __restrict__ q,
                                                                                        const int* __restrict__ seg, const int* __restrict__ nseg_p,
@@ -583,8 +662,8 @@ __global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot_
 // convergence logic as the three-kernel path; runs up to n_iters iterations and stops early when
 // the state says done.
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool DIST>
-__global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kernel(Visc3Dev<T> P, T s, T s2, T* x, T* r, T* d, T* q,
+template <typename T, bool DIST, bool FOLD>
+__global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kernel(Visc3Dev<T> P, T s, T s2, T* x, T* r, T* d, T* q, T* d2,
                                                                                   const int* __restrict__ seg, const int* __restrict__ nseg_p,
                                                                                   CgState* st, double* partials, GridBar* bar, int n_iters,
                                                                                   PeerInfo* peers, PeerHot hot, unsigned long long* prof) {
@@ -608,11 +687,20 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
     auto tick = [&]() {
         if (stamp && np < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); prof[np++] = t; }
     };
+    T* cur = d;                 // buffer holding the search direction of the current iteration
+    T* nxt = d2;                // FOLD: the other buffer of the ping-pong
+    bool have_beta = false;     // FOLD: a d update (beta_d) is pending
     for (int it = 0; it < n_iters && !done; ++it) {
         tick();
-        // K1 phase: q = A d, d.q
+        // K1 phase: q = A d, d.q   (FOLD, from the second iteration of a launch on: d = r + beta d_old formed on the fly)
         bool wrote_peer = false;
-        double acc = visc3d_apply_dot_body<T, DIST, true>(P, s, s2, d, q, seg, nseg, hot, wrote_peer);
+        double acc;
+        if (FOLD && have_beta) {
+            acc = visc3d_apply_dot_fold_body<T, DIST>(P, s, s2, cur, r, (T)beta_d, nxt, q, seg, nseg, hot, wrote_peer);
+            T* t = cur; cur = nxt; nxt = t;
+        } else {
+            acc = visc3d_apply_dot_body<T, DIST, true>(P, s, s2, cur, q, seg, nseg, hot, wrote_peer);
+        }
         const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
         tick();
         if (DIST) ++seq0;
@@ -620,7 +708,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
         tick();
         // K2 phase: x += alpha d, r -= alpha q, r.r
         alpha_d = delta / dq;
-        acc = cg_update_xr_seg_body<T, 3, DIST>(NL, NL, seg, nseg, x, r, d, q, (T)alpha_d, hot);
+        acc = cg_update_xr_seg_body<T, 3, DIST>(NL, NL, seg, nseg, x, r, cur, q, (T)alpha_d, hot);
         tick();
         if (DIST) ++seq1;
         const double rr = grid_allreduce(acc, partials, gs, DIST ? peers : nullptr, 1, false, seq1);
@@ -631,12 +719,24 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
         if (rr < tol2) done = 1;
         else if (iter >= max_iter || !(rr == rr)) done = 2;      // NaN: the reference would spin to max_iter
         if (done) break;
-        // K3 phase: d = r + beta d
+        // K3 phase: d = r + beta d   (FOLD: deferred into the next K1 phase)
         beta_d = delta / delta_old;
-        cg_update_d_seg_body<T, 3>(NL, NL, seg, nseg, d, r, (T)beta_d);
-        tick();
-        gs.sync();
-        tick();
+        if (FOLD) {
+            have_beta = true;
+            tick();
+            tick();
+        } else {
+            cg_update_d_seg_body<T, 3>(NL, NL, seg, nseg, cur, r, (T)beta_d);
+            tick();
+            gs.sync();
+            tick();
+        }
+    }
+    if (FOLD) {
+        // leave the live search direction in the primary buffer: apply the pending update (iteration budget of this launch
+        // used up) or just move it (stopped: the reference breaks before updating d)
+        const bool pending = have_beta && !done;
+        if (pending || cur != d) visc3d_fold_finish_body<T>(NL, seg, nseg, d, cur, r, (T)beta_d, pending);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->delta = delta; st->delta_old = delta_old; st->dq = dq; st->alpha = alpha_d; st->beta = beta_d;
@@ -664,6 +764,7 @@ struct fs_visc3d {
     uint8_t* valid;  // [3][NL] extrapolation validity generations
     GridBar* bar;    // grid barrier of the persistent CG kernel
     ExtrapWork work; // extrapolation work lists
+    char* d2;        // [3][NL] second d buffer (folded persistent kernel); zero outside the active segments like r,d,q,b
     int cg_mode;     // FS_CG_AUTO / FS_CG_KERNELS / FS_CG_PERSISTENT
     bool sparse_clean;   // r,d,q,b are zero outside the segments of the current active list (sparse begin / clear may be used)
     uint8_t* act;    // [NL] computed-row bits
@@ -698,7 +799,7 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     return L;
 }
 
-struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, total; int grid_pts; unsigned int wcap; };
+struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, total; int grid_pts; unsigned int wcap; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -725,6 +826,9 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     o.wcap = (3 * L.NL < 0xffffffffLL) ? (unsigned int)(L.NL / 2 + 1024) : 0u;
     o.wlist = p; p = align_up(p + (size_t)2 * o.wcap * sizeof(unsigned int), 256);
     o.wcount = p; p = align_up(p + 4 * sizeof(unsigned int), 256);
+    // second search-direction buffer of the folded persistent kernel (ping-pong), with the same guard bands as `vecs`
+    p += guard;
+    o.d2 = p; p = align_up(p + 3 * L.NL * esz, 256) + guard;
     o.total = p;
     return o;
 }
@@ -845,7 +949,8 @@ int fs_visc3d_peer_error(fs_visc3d* h) {
 
 int fs_visc3d_set_cg_mode(fs_visc3d* h, int mode) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
-    if (mode != FS_CG_AUTO && mode != FS_CG_KERNELS && mode != FS_CG_PERSISTENT) return fail(FS_ERR_ARG, "fs_visc3d_set_cg_mode: bad mode");
+    if (mode != FS_CG_AUTO && mode != FS_CG_KERNELS && mode != FS_CG_PERSISTENT && mode != FS_CG_PERSISTENT_FOLD)
+        return fail(FS_ERR_ARG, "fs_visc3d_set_cg_mode: bad mode");
     h->cg_mode = mode;
     return FS_OK;
 }
@@ -919,6 +1024,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->mask = (uint8_t*)(h->ws + lay.mask); h->valid = (uint8_t*)(h->ws + lay.valid); h->act = (uint8_t*)(h->ws + lay.act);
     h->partials = (double*)(h->ws + lay.partials); h->st = (CgState*)(h->ws + lay.st);
     h->bar = (GridBar*)(h->ws + lay.bar);
+    h->d2 = h->ws + lay.d2;
     h->work.cap = lay.wcap;
     if (const char* e = getenv("FLUIDSOLVER_B200_EXTRAP_CAP")) {   // test hook: tiny lists force the overflow fall-back
         const long long c = atoll(e);
@@ -977,11 +1083,12 @@ int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double 
     if (h->sparse_clean) {
         if (h->seg.nseg > 0) {
             const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 8);
-            FS_DISPATCH(h, visc3d_clear_kernel<T><<<grid, kThreads, 0, s>>>(h->L.NL, reinterpret_cast<T*>(h->vecs), h->seg.list, h->seg.nseg_dev));
+            FS_DISPATCH(h, visc3d_clear_kernel<T><<<grid, kThreads, 0, s>>>(h->L.NL, reinterpret_cast<T*>(h->vecs), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev));
             FS_LAUNCH_CHECK();
         }
     } else {
         FS_CUDA(cudaMemsetAsync(h->vecs + (size_t)FS_VEC_R * 3 * h->L.NL * h->esz, 0, (size_t)12 * h->L.NL * h->esz, s));
+        FS_CUDA(cudaMemsetAsync(h->d2, 0, (size_t)3 * h->L.NL * h->esz, s));
         h->sparse_clean = true;
     }
     FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act,
@@ -1133,7 +1240,7 @@ static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
 static bool visc3d_use_persistent(const fs_visc3d* h) {
     if (h->comm && !h->peers) return false;
     if (h->cg_mode == FS_CG_KERNELS) return false;
-    if (h->cg_mode == FS_CG_PERSISTENT) return true;
+    if (h->cg_mode == FS_CG_PERSISTENT || h->cg_mode == FS_CG_PERSISTENT_FOLD) return true;
     static int mode = -2;
     if (mode == -2) {
         const char* e = getenv("FLUIDSOLVER_B200_PERSISTENT");
@@ -1148,6 +1255,13 @@ static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t 
     int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, kSMs);
     if (const char* e = getenv("FLUIDSOLVER_B200_PERSIST_GRID")) { const int g = atoi(e); if (g >= 1 && g <= kSMs) grid = g; }
     unsigned long long* prof = getenv("FLUIDSOLVER_B200_PROFILE") ? reinterpret_cast<unsigned long long*>(h->valid) : nullptr;   // scratch between solves
+    // K3 folded into K1 (two grid barriers per iteration instead of three): FS_CG_PERSISTENT_FOLD, or FLUIDSOLVER_B200_FOLD=1/0
+    bool fold = h->cg_mode == FS_CG_PERSISTENT_FOLD;
+    if (h->cg_mode != FS_CG_PERSISTENT_FOLD && h->cg_mode != FS_CG_PERSISTENT) {
+        static int fold_env = -2;
+        if (fold_env == -2) { const char* e = getenv("FLUIDSOLVER_B200_FOLD"); fold_env = !e ? -1 : (e[0] == '0' ? 0 : 1); }
+        fold = fold_env >= 0 ? fold_env == 1 : kFoldByDefault;
+    }
     while (n > 0) {
         int ni = (int)(n < (1 << 20) ? n : (1 << 20));
         cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);     // arrival counter / flag count from zero in every launch
@@ -1156,11 +1270,13 @@ static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t 
             Visc3Dev<T> P = dev_view<T>(h);
             T sv = (T)sm, s2v = (T)(2 * sm);
             T* x = vec_ptr<T>(h, FS_VEC_X); T* r = vec_ptr<T>(h, FS_VEC_R); T* d = vec_ptr<T>(h, FS_VEC_D); T* q = vec_ptr<T>(h, FS_VEC_Q);
+            T* d2 = reinterpret_cast<T*>(h->d2);
             const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
             CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
             PeerInfo* peers = h->peers; PeerHot hot = h->hot;
-            void* args[] = {&P, &sv, &s2v, &x, &r, &d, &q, &seg, &nsegp, &st, &partials, &bar, &ni, &peers, &hot, &prof};
-            const void* fn = h->peers ? (const void*)visc3d_cg_persistent_kernel<T, true> : (const void*)visc3d_cg_persistent_kernel<T, false>;
+            void* args[] = {&P, &sv, &s2v, &x, &r, &d, &q, &d2, &seg, &nsegp, &st, &partials, &bar, &ni, &peers, &hot, &prof};
+            const void* fn = fold ? (h->peers ? (const void*)visc3d_cg_persistent_kernel<T, true, true> : (const void*)visc3d_cg_persistent_kernel<T, false, true>)
+                                  : (h->peers ? (const void*)visc3d_cg_persistent_kernel<T, true, false> : (const void*)visc3d_cg_persistent_kernel<T, false, false>);
             e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args, 0, s);
         });
         if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));

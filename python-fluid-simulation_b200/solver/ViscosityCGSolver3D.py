@@ -103,9 +103,9 @@ class _Engine:
         N.check(self.lib.fs_visc3d_set_active_mode(self.h, code), "fs_visc3d_set_active_mode")
 
     def set_cg_mode(self, mode):
-        code = {"auto": N.CG_AUTO, "kernels": N.CG_KERNELS, "persistent": N.CG_PERSISTENT}.get(mode)
+        code = {"auto": N.CG_AUTO, "kernels": N.CG_KERNELS, "persistent": N.CG_PERSISTENT, "persistent_fold": N.CG_PERSISTENT_FOLD}.get(mode)
         if code is None:
-            raise ValueError("cg_mode must be 'auto', 'kernels' or 'persistent'")
+            raise ValueError("cg_mode must be 'auto', 'kernels', 'persistent' or 'persistent_fold'")
         N.check(self.lib.fs_visc3d_set_cg_mode(self.h, code), "fs_visc3d_set_cg_mode")
 
     def active_info(self):

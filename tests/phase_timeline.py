@@ -18,9 +18,10 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 if len(sys.argv) > 2:
     os.environ["FLUIDSOLVER_B200_PERSIST_GRID"] = sys.argv[2]
 aset = sys.argv[3] if len(sys.argv) > 3 else "nonzero"
+cgm = sys.argv[4] if len(sys.argv) > 4 else "persistent"
 lib = N.load()
 sc = scenes.buckling(n, device="cuda", mu=100.0)
-s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], cg_mode="persistent", active_set=aset)
+s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], cg_mode=cgm, active_set=aset)
 s.max_iter = 0
 v = [sc[k].clone() for k in ("vx", "vy", "vz")]
 try:
@@ -37,6 +38,6 @@ t = buf[: 7 * 64].astype(np.int64).reshape(64, 7)
 d = np.diff(t, axis=1)[8:]                   # skip the first iterations
 names = ["K1 body", "barrier1+dq", "K2 body", "barrier2+rr", "K3 body", "barrier3"]
 per_it = np.diff(t[:, 0])[8:]
-print(f"N={n} grid={os.environ.get('FLUIDSOLVER_B200_PERSIST_GRID', 'auto')} active={aset} segments={s.active_info()[0]}  iteration {per_it.mean()/1e3:.2f} us")
+print(f"mode={cgm} N={n} grid={os.environ.get('FLUIDSOLVER_B200_PERSIST_GRID', 'auto')} active={aset} segments={s.active_info()[0]}  iteration {per_it.mean()/1e3:.2f} us")
 for k, nm in enumerate(names):
     print(f"  {nm:14s} {d[:, k].mean()/1e3:7.2f} us  (min {d[:, k].min()/1e3:.2f}, max {d[:, k].max()/1e3:.2f})")

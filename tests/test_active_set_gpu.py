@@ -125,7 +125,7 @@ def test_persistent_kernel_matches_three_kernel_path(dtype):
     sc = scenes.buckling(48, device="cuda", mu=100.0)
     out = {}
     for aset in ("nonzero", "fluid"):
-        for mode in ("kernels", "persistent"):
+        for mode in ("kernels", "persistent", "persistent_fold"):
             s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], dtype=dtype, active_set=aset, cg_mode=mode)
             v = [sc[k].clone() for k in ("vx", "vy", "vz")]
             s.solve(sc["dt"], 100.0, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"])
@@ -143,13 +143,19 @@ def test_fixed_window_persistent_counts_iterations():
     import scenes
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
     sc = scenes.buckling(32, device="cuda", mu=100.0)
-    for mode in ("kernels", "persistent"):
+    d_after = {}
+    for mode in ("kernels", "persistent", "persistent_fold"):
         s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], cg_mode=mode)
         s.max_iter = 150
         v = [sc[k].clone() for k in ("vx", "vy", "vz")]
         with pytest.raises(ValueError, match="Failed to converge!"):
             s.solve(sc["dt"], 100.0, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"], tol=0.0)
         assert s.iterations == 150
+        d_after[mode] = [a.clone() for a in (s.d_x, s.d_y, s.d_z)]
+    # the live search direction ends up in the primary buffer whichever way the launches were cut (150 = 64 + 64 + 22)
+    for mode in ("persistent", "persistent_fold"):
+        for a, b in zip(d_after[mode], d_after["kernels"]):
+            assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 1e-3, mode
 
 
 @pytest.mark.parametrize("cap", ["0", "7", None])
