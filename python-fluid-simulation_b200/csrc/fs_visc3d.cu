@@ -94,69 +94,77 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
         const long long i = (long long)row * L.Zp + z;
         const long long f0 = frow + 2LL * z;         // fine node (2x,2y,2z)
         const bool iz = z < L.nz, inz = z <= L.nz;
-        // vol = lvol / vol_norm (:568); the division is skipped for the (very common) exact zeros, whose quotient is the same zero
-        auto vol = [&](long long off) { const double l = lvol[f0 + off]; return l == 0.0 ? (T)l : (T)(l / vol_norm); };
-        auto nz = [](T v) { return v != T(0); };     // NaN counts as non-zero: it must propagate like in the reference
-        const T vc = (ix && iy && iz) ? vol(fx + fy + fz) : T(0);   // cell centre (1,1,1)
-        const T exy = (iz) ? vol(fz) : T(0);                        // Exy: (0,0,1)
-        const T exz = (iy && inz) ? vol(fy) : T(0);                 // Exz: (0,1,0)
-        const T eyz = (ix && inz) ? vol(fx) : T(0);                 // Eyz: (1,0,0)
-        unsigned int abits = 0;
-        // faces: fine parities (0,1,1) (1,0,1) (1,1,0)
-        {
-            bool fluid = false;
-            T v = nan;
-            if (iy && iz) {
-                fluid = sphi[f0 + fy + fz] >= 0.0;
-                const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
-                if (fluid && yz && x >= 1 && x <= L.u_xhi) {
-                    v = vol(fy + fz);
-                    if (v == v) {
-                        bool on = true;
-                        if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(exz) || nz(vol(fy + fz - fx)) || nz(vol(fy + fz + fy)) || nz(vol(fy + fz + fz));
-                        if (on) abits |= 1u;
-                    }
-                }
-                if (fluid && halo_x && yz) abits |= 0x10u;
+        // All ten fine-grid values of this lattice point are requested first (one memory latency), then normalised.
+        // vol = lvol / vol_norm (:568): the fp64 division (~25 instructions) is skipped for the very common exact zeros, whose
+        // quotient is the same zero; the empty volatile asm keeps ptxas from if-converting the branch (it otherwise evaluates
+        // all 16 divisions of a lattice point unconditionally and selects: 45 % of the kernel's instructions).
+        auto norm = [&](double l) -> T {
+            if (l != 0.0) {
+                asm volatile("" : "+d"(l));
+                l = l / vol_norm;
             }
+            return (T)l;
+        };
+        auto vol = [&](long long off) -> T { return norm(lvol[f0 + off]); };
+        auto nz = [](T v) { return v != T(0); };     // NaN counts as non-zero: it must propagate like in the reference
+        const bool in_c = ix && iy && iz, in_u = iy && iz, in_v = ix && iz, in_w = ix && iy && inz;
+        const double l_vc = in_c ? lvol[f0 + fx + fy + fz] : 0.0;    // cell centre (1,1,1)
+        const double l_exy = iz ? lvol[f0 + fz] : 0.0;               // Exy: (0,0,1)
+        const double l_exz = (iy && inz) ? lvol[f0 + fy] : 0.0;      // Exz: (0,1,0)
+        const double l_eyz = (ix && inz) ? lvol[f0 + fx] : 0.0;      // Eyz: (1,0,0)
+        const double l_u = in_u ? lvol[f0 + fy + fz] : 0.0;          // faces: fine parities (0,1,1) (1,0,1) (1,1,0); they share
+        const double l_v = in_v ? lvol[f0 + fx + fz] : 0.0;          // their fine rows (and DRAM sectors) with Exz, Eyz, Vc
+        const double l_w = in_w ? lvol[f0 + fx + fy] : 0.0;
+        const double s_u = in_u ? sphi[f0 + fy + fz] : -1.0;
+        const double s_v = in_v ? sphi[f0 + fx + fz] : -1.0;
+        const double s_w = in_w ? sphi[f0 + fx + fy] : -1.0;
+        const T vc = norm(l_vc), exy = norm(l_exy), exz = norm(l_exz), eyz = norm(l_eyz);
+        unsigned int abits = 0;
+        {
+            const bool fluid = in_u && s_u >= 0.0;
+            T v = nan;
+            const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
+            if (fluid && yz && x >= 1 && x <= L.u_xhi) {
+                v = norm(l_u);
+                if (v == v) {
+                    bool on = true;
+                    if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(exz) || nz(vol(fy + fz - fx)) || nz(vol(fy + fz + fy)) || nz(vol(fy + fz + fz));
+                    if (on) abits |= 1u;
+                }
+            }
+            if (fluid && halo_x && yz) abits |= 0x10u;
             coef[0 * L.NL + i] = v;
             mask[0 * L.NL + i] = fluid;
         }
         {
-            bool fluid = false;
+            const bool fluid = in_v && s_v >= 0.0;
             T v = nan;
-            if (ix && iz) {
-                fluid = sphi[f0 + fx + fz] >= 0.0;
-                const bool yz = y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2;
-                if (fluid && yz && x >= 1 && x <= L.nx - 2) {
-                    v = vol(fx + fz);
-                    if (v == v) {
-                        bool on = true;
-                        if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(eyz) || nz(vol(fx + fz + fx)) || nz(vol(fx + fz - fy)) || nz(vol(fx + fz + fz));
-                        if (on) abits |= 2u;
-                    }
+            const bool yz = y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2;
+            if (fluid && yz && x >= 1 && x <= L.nx - 2) {
+                v = norm(l_v);
+                if (v == v) {
+                    bool on = true;
+                    if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(eyz) || nz(vol(fx + fz + fx)) || nz(vol(fx + fz - fy)) || nz(vol(fx + fz + fz));
+                    if (on) abits |= 2u;
                 }
-                if (fluid && halo_x && yz) abits |= 0x20u;
             }
+            if (fluid && halo_x && yz) abits |= 0x20u;
             coef[1 * L.NL + i] = v;
             mask[1 * L.NL + i] = fluid;
         }
         {
-            bool fluid = false;
+            const bool fluid = in_w && s_w >= 0.0;
             T v = nan;
-            if (ix && iy && inz) {
-                fluid = sphi[f0 + fx + fy] >= 0.0;
-                const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1;
-                if (fluid && yz && x >= 1 && x <= L.nx - 2) {
-                    v = vol(fx + fy);
-                    if (v == v) {
-                        bool on = true;
-                        if (nonzero_only) on = nz(v) || nz(vc) || nz(exz) || nz(eyz) || nz(vol(fx + fy + fx)) || nz(vol(fx + fy + fy)) || nz(vol(fx + fy - fz));
-                        if (on) abits |= 4u;
-                    }
+            const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1;
+            if (fluid && yz && x >= 1 && x <= L.nx - 2) {
+                v = norm(l_w);
+                if (v == v) {
+                    bool on = true;
+                    if (nonzero_only) on = nz(v) || nz(vc) || nz(exz) || nz(eyz) || nz(vol(fx + fy + fx)) || nz(vol(fx + fy + fy)) || nz(vol(fx + fy - fz));
+                    if (on) abits |= 4u;
                 }
-                if (fluid && halo_x && yz) abits |= 0x40u;
             }
+            if (fluid && halo_x && yz) abits |= 0x40u;
             coef[2 * L.NL + i] = v;
             mask[2 * L.NL + i] = fluid;
         }
