@@ -81,8 +81,10 @@ constexpr int kThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const double* __restrict__ sphi, const double* __restrict__ lvol,
                                                           double vol_norm, T* __restrict__ coef /*[7][NL]*/, uint8_t* __restrict__ mask /*[3][NL]*/,
-                                                          uint8_t* __restrict__ act /*[NL + 64]*/, int nonzero_only) {
+                                                          uint8_t* __restrict__ act /*[NL + 64]*/, uint8_t* __restrict__ rowflag /*[X*Y]*/,
+                                                          int nonzero_only) {
     const int row = blockIdx.x;                      // x*Y + y
+    int any_valid = 0;                               // does this lattice row hold any fluid face? (extrapolation sweep 1 skips far rows)
     const int x = row / L.Y, y = row - x * L.Y;
     const long long fz = 1, fy = 2LL * L.nz + 1, fx = fy * (2LL * L.ny + 1);
     const long long frow = 2LL * x * fx + 2LL * y * fy;
@@ -168,12 +170,15 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
             coef[2 * L.NL + i] = v;
             mask[2 * L.NL + i] = fluid;
         }
+        any_valid |= (in_u && s_u >= 0.0) || (in_v && s_v >= 0.0) || (in_w && s_w >= 0.0);
         coef[3 * L.NL + i] = vc;
         coef[4 * L.NL + i] = exy;
         coef[5 * L.NL + i] = exz;
         coef[6 * L.NL + i] = eyz;
         act[i] = (uint8_t)abits;
     }
+    any_valid = __syncthreads_or(any_valid);
+    if (threadIdx.x == 0) rowflag[row] = (uint8_t)(any_valid != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -278,12 +283,22 @@ __device__ __forceinline__ bool extrap_try_fill(const Lat3& L, T* v_all, uint8_t
 // fall-back of the list-driven sweeps (`only_if_overflow`).
 template <typename T>
 __global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, T* v_all, uint8_t* valid_all, int sweep /*1-based*/, ExtrapWork W,
-                                                                      int push_to /*list to record fills in, -1 = none*/, int only_if_overflow) {
+                                                                      int push_to /*list to record fills in, -1 = none*/, int only_if_overflow,
+                                                                      const uint8_t* __restrict__ rowflag /*sweep 1 only, or null*/) {
     if (only_if_overflow && (W.cap == 0u || W.count[2] == 0u)) return;
+    const int nrows = L.X * L.Y;
     const unsigned int sw = (unsigned int)sweep;
     const long long ngroups = L.NL / 4;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (long long)gridDim.x * blockDim.x) {
         const long long i4 = g * 4;
+        if (rowflag) {
+            // sweep 1 can only fill next to an originally valid face: a group whose lattice row and the four rows around it
+            // (y+-1, x+-1) hold no fluid face at all (deep inside the solid, outside the container) is skipped on five bytes
+            const int row = (int)(L.NL < 0x7fffffffLL ? (unsigned int)i4 / (unsigned int)L.Zp : i4 / L.Zp);
+            const int ra = row > 0 ? row - 1 : row, rb = row + 1 < nrows ? row + 1 : row;
+            const int rc = row >= L.Y ? row - L.Y : row, rd = row + L.Y < nrows ? row + L.Y : row;
+            if (!(__ldg(rowflag + row) | __ldg(rowflag + ra) | __ldg(rowflag + rb) | __ldg(rowflag + rc) | __ldg(rowflag + rd))) continue;
+        }
         uint32_t own[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) own[c] = *reinterpret_cast<const uint32_t*>(valid_all + c * L.NL + i4);
@@ -772,6 +787,7 @@ struct fs_visc3d {
     uint8_t* valid;  // [3][NL] extrapolation validity generations
     GridBar* bar;    // grid barrier of the persistent CG kernel
     ExtrapWork work; // extrapolation work lists
+    uint8_t* rowflag; // [X*Y] lattice row holds a fluid face (written by pack, read by extrapolation sweep 1)
     char* d2;        // [3][NL] second d buffer (folded persistent kernel); zero outside the active segments like r,d,q,b
     int cg_mode;     // FS_CG_AUTO / FS_CG_KERNELS / FS_CG_PERSISTENT
     bool sparse_clean;   // r,d,q,b are zero outside the segments of the current active list (sparse begin / clear may be used)
@@ -807,7 +823,7 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     return L;
 }
 
-struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, total; int grid_pts; unsigned int wcap; };
+struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -837,6 +853,7 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     // second search-direction buffer of the folded persistent kernel (ping-pong), with the same guard bands as `vecs`
     p += guard;
     o.d2 = p; p = align_up(p + 3 * L.NL * esz, 256) + guard;
+    o.rowflag = p; p = align_up(p + (size_t)L.X * L.Y, 256);
     o.total = p;
     return o;
 }
@@ -1033,6 +1050,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->partials = (double*)(h->ws + lay.partials); h->st = (CgState*)(h->ws + lay.st);
     h->bar = (GridBar*)(h->ws + lay.bar);
     h->d2 = h->ws + lay.d2;
+    h->rowflag = (uint8_t*)(h->ws + lay.rowflag);
     h->work.cap = lay.wcap;
     if (const char* e = getenv("FLUIDSOLVER_B200_EXTRAP_CAP")) {   // test hook: tiny lists force the overflow fall-back
         const long long c = atoll(e);
@@ -1099,7 +1117,7 @@ int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double 
         FS_CUDA(cudaMemsetAsync(h->d2, 0, (size_t)3 * h->L.NL * h->esz, s));
         h->sparse_clean = true;
     }
-    FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act,
+    FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act, h->rowflag,
                                                                                       h->active_mode == FS_ACTIVE_NONZERO ? 1 : 0));
     FS_LAUNCH_CHECK();
     FS_TRY(h->seg.enqueue(h->act, s));    // the list length (read back asynchronously) sizes the CG launches: see visc3d_list_ready
@@ -1156,14 +1174,15 @@ int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
     for (int k = 1; k <= sweeps; ++k) {
         const int push_to = (W.cap && k < sweeps) ? ((k - 1) & 1) : -1;
         if (k == 1 || !W.cap) {
-            FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<full_grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, push_to, 0));
+            FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<full_grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, push_to, 0,
+                                                                                       k == 1 ? h->rowflag : nullptr));
             FS_LAUNCH_CHECK();
         } else {
             const int from = (k - 2) & 1;
             if (push_to >= 0) FS_CUDA(cudaMemsetAsync(W.count + push_to, 0, sizeof(unsigned int), s));
             FS_DISPATCH(h, visc3d_extrapolate_list_kernel<T><<<kSMs * 4, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, from, push_to));
             FS_LAUNCH_CHECK();
-            FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<kSMs * 8, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, -1, 1));   // only if a list overflowed
+            FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<kSMs * 8, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, -1, 1, nullptr));   // only if a list overflowed
             FS_LAUNCH_CHECK();
         }
         if (h->comm) {   // the sweep is Jacobi over the GLOBAL grid: refresh the halo planes of the new values and generations
