@@ -101,24 +101,29 @@ __global__ void __launch_bounds__(kPT) press_apply_kernel(Grid<D> g, const doubl
         const double phi = __ldg(lphi + i);
         double res = 0.0;
         if (phi < 0) {
-            double val = 0.0, diag = 0.0;
+            double nphi[2 * D], w[2 * D], vn[2 * D];          // requested together, used in the reference's order (+a then -a)
             const double vc = __ldg(v + i);
 #pragma unroll
             for (int a = 0; a < D; ++a) {
 #pragma unroll
-                for (int sgn = 1; sgn >= -1; sgn -= 2) {          // +a then -a
-                    const long long j = i + sgn * g.cs[a];
-                    const double nphi = __ldg(lphi + j);
-                    const int foff = (sgn > 0 || (OP == OP_DENSITY && a == D - 1)) ? 1 : 0;
-                    const double w = __ldg(W.w[a] + face_idx<D>(g, a, c, foff));
-                    const double dw = (OP == OP_DENSITY) ? 1.0 : w;
-                    if (nphi < 0) {
-                        val = __dsub_rn(val, __dmul_rn(w, __ldg(v + j)));
-                        diag = __dadd_rn(diag, dw);
-                    } else {
-                        const double frac = fmin(1.0, fmax(0.01, phi / __dsub_rn(phi, nphi)));
-                        diag = __dadd_rn(diag, dw / frac);
-                    }
+                for (int t = 0; t < 2; ++t) {
+                    const long long j = i + (t == 0 ? g.cs[a] : -g.cs[a]);
+                    const int foff = (t == 0 || (OP == OP_DENSITY && a == D - 1)) ? 1 : 0;
+                    nphi[2 * a + t] = __ldg(lphi + j);
+                    w[2 * a + t] = __ldg(W.w[a] + face_idx<D>(g, a, c, foff));
+                    vn[2 * a + t] = __ldg(v + j);
+                }
+            }
+            double val = 0.0, diag = 0.0;
+#pragma unroll
+            for (int k = 0; k < 2 * D; ++k) {
+                const double dw = (OP == OP_DENSITY) ? 1.0 : w[k];
+                if (nphi[k] < 0) {
+                    val = __dsub_rn(val, __dmul_rn(w[k], vn[k]));
+                    diag = __dadd_rn(diag, dw);
+                } else {
+                    const double frac = fmin(1.0, fmax(0.01, phi / __dsub_rn(phi, nphi[k])));
+                    diag = __dadd_rn(diag, dw / frac);
                 }
             }
             res = __dadd_rn(val, __dmul_rn(diag, vc));
@@ -182,24 +187,31 @@ __device__ __forceinline__ double press_apply_seg_body(const Grid<D>& g, const d
         if (!interior<D>(g, c)) continue;
         const double phi = __ldg(lphi + i);
         if (!(phi < 0)) continue;                       // not computed: out holds 0 since the start of the solve
-        double val = 0.0, diag = 0.0;
+        // all 2D neighbour level-set values, face weights and vector entries are requested before the first use (one memory
+        // latency per segment instead of one per neighbour); the arithmetic below keeps the reference's order (+a then -a)
+        double nphi[2 * D], w[2 * D], vn[2 * D];
         const double vc = v[i];
 #pragma unroll
         for (int a = 0; a < D; ++a) {
 #pragma unroll
-            for (int sgn = 1; sgn >= -1; sgn -= 2) {          // +a then -a
-                const long long j = i + sgn * g.cs[a];
-                const double nphi = __ldg(lphi + j);
-                const int foff = (sgn > 0 || (OP == OP_DENSITY && a == D - 1)) ? 1 : 0;
-                const double w = __ldg(W.w[a] + face_idx<D>(g, a, c, foff));
-                const double dw = (OP == OP_DENSITY) ? 1.0 : w;
-                if (nphi < 0) {
-                    val = __dsub_rn(val, __dmul_rn(w, v[j]));
-                    diag = __dadd_rn(diag, dw);
-                } else {
-                    const double frac = fmin(1.0, fmax(0.01, phi / __dsub_rn(phi, nphi)));
-                    diag = __dadd_rn(diag, dw / frac);
-                }
+            for (int t = 0; t < 2; ++t) {                     // t = 0: +a, t = 1: -a
+                const long long j = i + (t == 0 ? g.cs[a] : -g.cs[a]);
+                const int foff = (t == 0 || (OP == OP_DENSITY && a == D - 1)) ? 1 : 0;
+                nphi[2 * a + t] = __ldg(lphi + j);
+                w[2 * a + t] = __ldg(W.w[a] + face_idx<D>(g, a, c, foff));
+                vn[2 * a + t] = v[j];
+            }
+        }
+        double val = 0.0, diag = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2 * D; ++k) {
+            const double dw = (OP == OP_DENSITY) ? 1.0 : w[k];
+            if (nphi[k] < 0) {
+                val = __dsub_rn(val, __dmul_rn(w[k], vn[k]));
+                diag = __dadd_rn(diag, dw);
+            } else {
+                const double frac = fmin(1.0, fmax(0.01, phi / __dsub_rn(phi, nphi[k])));
+                diag = __dadd_rn(diag, dw / frac);
             }
         }
         const double res = __dadd_rn(val, __dmul_rn(diag, vc));
