@@ -51,26 +51,62 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region: NVML in-process every ~2 ms when available (the timed
+    region of the default run is only tens of milliseconds), else `nvidia-smi` every 0.2 s."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    NVML_BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
         self.index = index
-        self.rows = []
+        self.rows = []          # [sm_mhz, sm_max_mhz, set(reasons)]
+        self.source = None
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES-free boxes: LOCAL_RANK indexes the physical devices the driver gave us
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        mx = float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM))
+        try:
+            bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        self.rows.append([sm, mx, {k for k, b in self.NVML_BITS.items() if bits & b}])
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            c = [v.strip() for v in out.split(",")]
+            self.rows.append([float(c[0]), float(c[1]), {n for n, v in zip(self.NAMES, c[2:6]) if v.lower().startswith("active")}])
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            self._stop.wait(0.2)
+                if self._nvml is not None:          # NVML hiccup: fall back to nvidia-smi for the rest of the run
+                    self._nvml = None
+                    self.source = "nvidia-smi"
+            self._stop.wait(0.002 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -82,12 +118,11 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows]
+        reasons = sorted(set().union(*[r[2] for r in self.rows])) if self.rows else []
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------------------
