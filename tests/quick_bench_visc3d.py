@@ -1,5 +1,5 @@
-import sys, time, ctypes
-sys.path.insert(0,'/root/repo/python-fluid-simulation_b200')
+import os, sys, time, ctypes
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'python-fluid-simulation_b200'))
 import torch, scenes
 from solver import _native as N
 from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
