@@ -327,6 +327,10 @@ def run_native(args):
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "share_of_step": dom_share,
+                "launch": ({"iterations_per_launch": 64, "algorithmic_bytes_per_launch": 64 * iter_bytes,
+                            "note": "achieved = algorithmic bytes / duration, both per launch of 64 iterations (= per iteration x 64); "
+                                    "traffic = dram bytes of one such launch (ncu)"} if persistent else
+                           {"iterations_per_launch": 1, "algorithmic_bytes_per_launch": kbytes[dom]}),
                 "cg_iteration_us": iter_ms * 1e3, "cg_iteration_bytes": iter_bytes, "setup_ms_per_step": ms / args.steps - iter_ms * args.iters,
                 "per_kernel_ms_standalone": kern, "per_kernel_GBps_standalone": {k: kbytes[k] / (kern[k] * 1e-3) / 1e9 for k in kern},
                 "bytes_per_launch": kbytes,

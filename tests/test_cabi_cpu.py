@@ -60,3 +60,49 @@ def test_product_has_no_cpu_fallback():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, fn)).read()
                 assert "numpy_oracle" not in src and "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/fluidsolver_b200.h must be consumable from C (no C++ types): compile a small C program against it with gcc,
+    link it to the shared library and run the calls that need no GPU."""
+    import shutil
+    import subprocess
+    from solver import _native as N
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    if not os.path.exists(N.LIB_PATH):
+        import build
+        build.build_library()
+    src = tmp_path / "abi_check.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "fluidsolver_b200.h"
+int main(void) {
+    fs_cg_stats st;                       /* plain C struct */
+    st.iterations = 0;
+    if (fs_abi_version() != FS_ABI_VERSION) return 2;
+    if (fs_visc3d_workspace_bytes(0, 4, 4, FS_F64) != 0) return 3;          /* bad grid -> 0, no CUDA call */
+    size_t v = fs_visc3d_workspace_bytes(32, 32, 32, FS_F64);
+    size_t p = fs_press_workspace_bytes(32, 32, 32);
+    size_t p2 = fs_press_workspace_bytes(32, 32, 0);
+    if (!v || !p || !p2) return 4;
+    /* every entry point a binding needs is a linkable C symbol */
+    void* fns[] = {(void*)fs_visc3d_solve, (void*)fs_visc3d_pack, (void*)fs_visc3d_set_active_mode, (void*)fs_visc3d_set_cg_mode,
+                   (void*)fs_visc2d_solve, (void*)fs_press_cg, (void*)fs_press_set_operator, (void*)fs_solidfrac3d, (void*)fs_solidfrac2d,
+                   (void*)fs_dens3d_scatter, (void*)fs_dens3d_gather, (void*)fs_comm_create, (void*)fs_visc3d_set_peers};
+    for (unsigned i = 0; i < sizeof(fns) / sizeof(fns[0]); ++i) if (!fns[i]) return 5;
+    printf("%zu %zu %zu %d\n", v, p, p2, (int)st.iterations);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(N.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-Wno-pedantic", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-lfluidsolver_b200", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    v, p, p2, _ = r.stdout.split()
+    assert int(v) == N.load().fs_visc3d_workspace_bytes(32, 32, 32, N.FS_F64)
