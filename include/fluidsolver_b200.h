@@ -58,7 +58,7 @@ extern "C" {
                                 (matvecmul / initialize_solver semantics, boundary layer untouched) */
 #define FS_STORE_FLUID 2     /* apply_viscosity semantics: indices 1..g-1 on all axes, fluid faces only */
 
-/* which rows the CG kernels visit (fs_visc3d_set_active_mode).  Both give bit-identical results:
+/* which rows the CG kernels visit (fs_visc3d_set_active_mode).  Both solve the same system (only exact zeros are dropped from the sums):
  *   FS_ACTIVE_FLUID    every row the reference's kernels compute (fluid face, interior; ViscosityCGSolver3D.py:251-258)
  *   FS_ACTIVE_NONZERO  (default) of those, only rows with at least one non-zero coefficient; an all-zero row is also an
  *                      all-zero column, its b, q, r, d stay exactly 0 and its x never changes (faces far from any liquid) */
