@@ -100,6 +100,104 @@ void port_visc3d_matvecmul(int nx, int ny, int nz, double scale, double mu,
     }
 }
 
+
+/* RHS row (ViscosityCGSolver3D.py:41-246): the off-diagonal terms of row_apply with the COMPLEMENTARY neighbour mask
+ * (sphi < 0: the neighbour face is solid and its extrapolated value moves to the right-hand side) and the opposite sign;
+ * the leading term is v_A[c]*vol[f]. */
+static inline double row_rhs(const geom_t* g, int A, const int* c, double s, const double* const* v,
+                             const double* sphi, const double* vol) {
+    ptrdiff_t f = 0;
+    for (int k = 0; k < 3; ++k) f += (2 * (ptrdiff_t)c[k] + (k == A ? 0 : 1)) * g->fs[k];
+    double hi[3], lo[3];
+    for (int ax = 0; ax < 3; ++ax) { hi[ax] = vol[f + g->fs[ax]]; lo[ax] = vol[f - g->fs[ax]]; }
+    const double* va = v[A];
+    const ptrdiff_t i = cidx(g, A, c);
+    double val = va[i] * vol[f];
+    for (int ax = 0; ax < 3; ++ax) {
+        const double cf = (ax == A) ? 2 * s : s;
+        if (sphi[f + 2 * g->fs[ax]] < 0) val += cf * hi[ax] * va[i + g->cs[A][ax]];
+        if (sphi[f - 2 * g->fs[ax]] < 0) val += cf * lo[ax] * va[i - g->cs[A][ax]];
+    }
+    for (int B = 0; B < 3; ++B) {
+        if (B == A) continue;
+        const double* vb = v[B];
+        const ptrdiff_t j = cidx(g, B, c);
+        const ptrdiff_t eb = g->cs[B][B], ea = g->cs[B][A];
+        if (sphi[f + g->fs[B] + g->fs[A]] < 0) val += s * hi[B] * vb[j + eb];
+        if (sphi[f + g->fs[B] - g->fs[A]] < 0) val -= s * hi[B] * vb[j + eb - ea];
+        if (sphi[f - g->fs[B] + g->fs[A]] < 0) val -= s * lo[B] * vb[j];
+        if (sphi[f - g->fs[B] - g->fs[A]] < 0) val += s * lo[B] * vb[j - ea];
+    }
+    return val;
+}
+
+/* initialize_solver (:504-513): b on interior rows, 0 on solid rows, boundary layer untouched */
+void port_visc3d_rhs(int nx, int ny, int nz, double scale, double mu,
+                     const double* vx, const double* vy, const double* vz,
+                     double* bx, double* by, double* bz, const double* sphi, const double* vol) {
+    geom_t g;
+    make_geom(&g, nx, ny, nz);
+    const double s = scale * mu;
+    const double* v[3] = {vx, vy, vz};
+    double* o[3] = {bx, by, bz};
+    for (int A = 0; A < 3; ++A) {
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int x = 1; x <= g.sh[A][0] - 2; ++x)
+            for (int y = 1; y <= g.sh[A][1] - 2; ++y)
+                for (int z = 1; z <= g.sh[A][2] - 2; ++z) {
+                    const int c[3] = {x, y, z};
+                    ptrdiff_t f = 0;
+                    for (int k = 0; k < 3; ++k) f += (2 * (ptrdiff_t)c[k] + (k == A ? 0 : 1)) * g.fs[k];
+                    o[A][cidx(&g, A, c)] = (sphi[f] < 0) ? 0.0 : row_rhs(&g, A, c, s, v, sphi, vol);
+                }
+    }
+}
+
+/* extrapolate (:472-502, kernel :8-39): num_iter Jacobi sweeps per component; validity = sphi >= 0 at the face's fine node.
+ * tmp_v / tmp_m: caller scratch of the largest component's size (doubles / bytes x 2). */
+void port_visc3d_extrapolate(int nx, int ny, int nz, int num_iter, double* vx, double* vy, double* vz, const double* sphi,
+                             double* tmp_v, unsigned char* tmp_m) {
+    geom_t g;
+    make_geom(&g, nx, ny, nz);
+    double* v[3] = {vx, vy, vz};
+    for (int A = 0; A < 3; ++A) {
+        const ptrdiff_t n = (ptrdiff_t)g.sh[A][0] * g.sh[A][1] * g.sh[A][2];
+        unsigned char* valid = tmp_m;
+        unsigned char* nvalid = tmp_m + n;
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int x = 0; x < g.sh[A][0]; ++x)
+            for (int y = 0; y < g.sh[A][1]; ++y)
+                for (int z = 0; z < g.sh[A][2]; ++z) {
+                    const int c[3] = {x, y, z};
+                    ptrdiff_t f = 0;
+                    for (int k = 0; k < 3; ++k) f += (2 * (ptrdiff_t)c[k] + (k == A ? 0 : 1)) * g.fs[k];
+                    valid[cidx(&g, A, c)] = sphi[f] >= 0;
+                }
+        for (int it = 0; it < num_iter; ++it) {
+#pragma omp parallel for schedule(static)
+            for (ptrdiff_t i = 0; i < n; ++i) { tmp_v[i] = v[A][i]; nvalid[i] = valid[i]; }
+#pragma omp parallel for collapse(2) schedule(static)
+            for (int x = 1; x <= g.sh[A][0] - 2; ++x)
+                for (int y = 1; y <= g.sh[A][1] - 2; ++y)
+                    for (int z = 1; z <= g.sh[A][2] - 2; ++z) {
+                        const int c[3] = {x, y, z};
+                        const ptrdiff_t i = cidx(&g, A, c);
+                        if (valid[i]) continue;
+                        double val = 0.0;
+                        int cnt = 0;
+                        for (int ax = 0; ax < 3; ++ax) {          /* +x,-x,+y,-y,+z,-z (:19-36) */
+                            const ptrdiff_t e = g.cs[A][ax];
+                            if (valid[i + e]) { val += v[A][i + e]; ++cnt; }
+                            if (valid[i - e]) { val += v[A][i - e]; ++cnt; }
+                        }
+                        if (cnt > 0) { tmp_v[i] = val / cnt; nvalid[i] = 1; }
+                    }
+#pragma omp parallel for schedule(static)
+            for (ptrdiff_t i = 0; i < n; ++i) { v[A][i] = tmp_v[i]; valid[i] = nvalid[i]; }
+        }
+    }
+}
+
 static double dot3(const geom_t* g, double* const* a, double* const* b) {
     double tot = 0.0;
     for (int A = 0; A < 3; ++A) {
@@ -151,6 +249,12 @@ int64_t port_visc3d_cg(int nx, int ny, int nz, double scale, double mu,
     }
     *delta_io = delta;
     return it;
+}
+
+void port_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
 }
 
 int port_num_threads(void) {

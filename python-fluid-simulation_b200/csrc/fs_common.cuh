@@ -65,6 +65,9 @@ struct CgState {
     int dist;          // 1: multi-GPU — reducing kernels leave their LOCAL sum in `red`; cg_finish_kernel applies it after the allreduce
     double red;
     unsigned int counter[4];  // last-block tickets (one per reducing kernel type)
+    // single-reduction (Chronopoulos-Gear) CG: `first` = no search direction yet (beta = 0, alpha = gamma/(w.r))
+    int sr_first;
+    int pad_;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -153,6 +156,52 @@ __device__ __forceinline__ double peer_allreduce_warp(double local, PeerInfo* P,
     return sum;
 }
 
+// Two scalars in ONE mailbox round (single-reduction CG): kind 0 carries `a`, kind 1 carries `b`; both sequence numbers
+// advance together.  All 32 lanes of one warp call this; results replace a and b (same bits on every rank).
+__device__ __forceinline__ void peer_allreduce2_warp(double& a, double& b, PeerInfo* P) {
+    const int lane = threadIdx.x & 31;
+    unsigned int seq0 = 0, seq1 = 0;
+    if (lane == 0) { seq0 = P->seq[0] + 1; P->seq[0] = seq0; seq1 = P->seq[1] + 1; P->seq[1] = seq1; }
+    seq0 = __shfl_sync(0xffffffffu, seq0, 0);
+    seq1 = __shfl_sync(0xffffffffu, seq1, 0);
+    const int n = P->nranks;
+    const int kind = lane >> 4, rk = lane & 15;              // lanes 0..15: kind 0, lanes 16..31: kind 1
+    const unsigned int seq = kind ? seq1 : seq0;
+    const int slot = ((kind * 2 + (int)(seq & 1u)) * kMaxRanks);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(kind ? b : a);
+    const unsigned long long w0 = ((unsigned long long)seq << 32) | (bits & 0xffffffffull);
+    const unsigned long long w1 = ((unsigned long long)seq << 32) | (bits >> 32);
+    __threadfence_system();
+    if (rk < n) {
+        unsigned long long* dst = P->mbox[rk] + (slot + P->rank) * 2;
+        st_sys_u64(dst, w0);
+        st_sys_u64(dst + 1, w1);
+    }
+    double v = 0.0;
+    bool ok = true;
+    if (rk < n) {
+        const unsigned long long* src = P->mbox[P->rank] + (slot + rk) * 2;
+        unsigned long long x, y;
+        const long long t0 = clock64();
+        for (;;) {
+            x = ld_sys_u64(src);
+            y = ld_sys_u64(src + 1);
+            if ((unsigned int)(x >> 32) == seq && (unsigned int)(y >> 32) == seq) break;
+            if (clock64() - t0 > 20000000000LL) { ok = false; break; }
+        }
+        v = __longlong_as_double((long long)(((y & 0xffffffffull) << 32) | (x & 0xffffffffull)));
+    }
+    if (!__all_sync(0xffffffffu, ok)) {
+        if (lane == 0) P->error = 1;
+        a = b = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    double sa = 0.0, sb = 0.0;
+    for (int r = 0; r < n; ++r) { sa += __shfl_sync(0xffffffffu, v, r); sb += __shfl_sync(0xffffffffu, v, 16 + r); }   // fixed rank order
+    __threadfence_system();
+    a = sa; b = sb;
+}
+
 // ---------------------------------------------------------------------------------------------
 // reductions: warp shuffle -> shared -> one partial per block -> last block sums the partials
 // in a fixed order (deterministic run to run; no floating-point atomics).
@@ -207,6 +256,42 @@ __device__ __forceinline__ void grid_sum_finish(double v, double* partials, unsi
         if (threadIdx.x == 0) {
             *counter = 0;
             fin(s);
+        }
+    }
+}
+
+// Two sums in one pass (single-reduction CG: r.r and w.r travel together).  partials: 2 * nblocks doubles.
+template <class Fin>
+__device__ __forceinline__ void grid_sum2_finish(double v1, double v2, double* partials, unsigned int* counter, Fin fin,
+                                                 PeerInfo* peers = nullptr, bool wrote_peer = false) {
+    __shared__ double sm[32];
+    __shared__ bool is_last;
+    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    v1 = block_sum(v1, sm);
+    v2 = block_sum(v2, sm);
+    if (threadIdx.x == 0) {
+        partials[bid] = v1;
+        partials[nblocks + bid] = v2;
+        if (wrote_peer) __threadfence_system(); else __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == nblocks - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s1 = 0.0, s2 = 0.0;
+        for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) { s1 += __ldcg(partials + i); s2 += __ldcg(partials + nblocks + i); }
+        s1 = block_sum(s1, sm);
+        s2 = block_sum(s2, sm);
+        if (peers && threadIdx.x < 32) {          // both scalars cross NVLink in the same mailbox round (kinds 0 and 1)
+            s1 = __shfl_sync(0xffffffffu, s1, 0);
+            s2 = __shfl_sync(0xffffffffu, s2, 0);
+            peer_allreduce2_warp(s1, s2, peers);
+        }
+        if (threadIdx.x == 0) {
+            *counter = 0;
+            fin(s1, s2);
         }
     }
 }
@@ -534,6 +619,82 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_d_seg_kernel(long long 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Single-reduction CG (Chronopoulos & Gear 1989): the same Krylov iterates as the reference's loop
+// (ViscosityCGSolver3D.py:588-610) with BOTH dot products of an iteration taken at one point, so an
+// iteration needs one grid-wide (and, multi-GPU, one cross-GPU) reduction instead of two:
+//     w = A r ;  gamma = r.r ;  dl = w.r                      (K1s: operator apply fused with both dots)
+//     stop if gamma < tol^2      (the reference's test "after each r update", evaluated on the same r)
+//     beta = gamma/gamma_old (0 first) ;  alpha = gamma / (dl - beta*gamma/alpha_old)
+//     p = r + beta p ;  s = w + beta s  (= A p) ;  x += alpha p ;  r -= alpha s      (K2s: one fused pass)
+// p lives in the D vector, s in Q (it IS the reference's q = A d), w in the second direction buffer.
+// Words per point and iteration are unchanged (13 + 27 instead of 13 + 18 + 9).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cg_sr_scalars(double gamma, double dl, double gamma_old, double alpha_old, bool first,
+                                              double& alpha, double& beta) {
+    beta = first ? 0.0 : gamma / gamma_old;
+    alpha = first ? gamma / dl : gamma / (dl - beta * gamma / alpha_old);
+}
+
+// bookkeeping after the (r.r, w.r) reduction of K1s (thread 0 of the finishing block)
+__device__ __forceinline__ void cg_sr_after_dots(CgState* st, double gamma, double dl) {
+    st->delta = gamma;
+    if (gamma < st->tol2) { st->done = 1; return; }
+    if (st->iter >= st->max_iter || !(gamma == gamma)) { st->done = 2; return; }   // NaN: the reference would spin to max_iter
+    double alpha, beta;
+    cg_sr_scalars(gamma, dl, st->delta_old, st->alpha, st->sr_first != 0, alpha, beta);
+    st->alpha = alpha; st->beta = beta; st->dq = dl; st->delta_old = gamma; st->sr_first = 0;
+}
+
+template <typename T, int NCOMP>
+__device__ __forceinline__ void cg_update_sr_seg_body(long long comp_stride, long long npts, const int* __restrict__ seg, int nseg,
+                                                      T* x, T* r, T* p, T* sv, const T* w, T alpha, T beta) {
+    using V = typename Vec2<T>::type;
+    const int hl = threadIdx.x & 15;
+    const long long hw0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const long long nhw = ((long long)gridDim.x * blockDim.x) >> 4;
+    long long j = hw0;
+    int sg = j < nseg ? __ldg(seg + j) : 0;
+    while (j < nseg) {
+        const long long pt = (long long)sg * kSegPts + 2 * hl;
+        j += nhw;
+        sg = j < nseg ? __ldg(seg + j) : 0;
+        if (pt >= npts) continue;
+        V xv[NCOMP], rv[NCOMP], pv[NCOMP], qv[NCOMP], wv[NCOMP];
+#pragma unroll
+        for (int c = 0; c < NCOMP; ++c) {
+            const long long e = (long long)c * comp_stride + pt;
+            xv[c] = *reinterpret_cast<const V*>(x + e);
+            rv[c] = *reinterpret_cast<const V*>(r + e);
+            pv[c] = *reinterpret_cast<const V*>(p + e);
+            qv[c] = *reinterpret_cast<const V*>(sv + e);
+            wv[c] = *reinterpret_cast<const V*>(w + e);
+        }
+#pragma unroll
+        for (int c = 0; c < NCOMP; ++c) {
+            const long long e = (long long)c * comp_stride + pt;
+            pv[c].x = rv[c].x + beta * pv[c].x; pv[c].y = rv[c].y + beta * pv[c].y;
+            qv[c].x = wv[c].x + beta * qv[c].x; qv[c].y = wv[c].y + beta * qv[c].y;
+            xv[c].x = xv[c].x + alpha * pv[c].x; xv[c].y = xv[c].y + alpha * pv[c].y;
+            rv[c].x = rv[c].x - alpha * qv[c].x; rv[c].y = rv[c].y - alpha * qv[c].y;
+            *reinterpret_cast<V*>(p + e) = pv[c];
+            *reinterpret_cast<V*>(sv + e) = qv[c];
+            *reinterpret_cast<V*>(x + e) = xv[c];
+            *reinterpret_cast<V*>(r + e) = rv[c];
+        }
+    }
+}
+
+template <typename T, int NCOMP>
+__global__ void __launch_bounds__(kVecThreads) cg_update_sr_seg_kernel(long long comp_stride, long long npts,
+                                                                       const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                       T* x, T* r, T* p, T* sv, const T* w, CgState* st, int freeze) {
+    if (*(volatile int*)&st->done) return;
+    const double alpha_d = st->alpha, beta_d = st->beta;
+    cg_update_sr_seg_body<T, NCOMP>(comp_stride, npts, seg, *nseg_p, x, r, p, sv, w, (T)alpha_d, (T)beta_d);
+    if (!freeze && blockIdx.x == 0 && threadIdx.x == 0) st->iter += 1;     // read by the next K1s (stream order)
+}
+
+// ---------------------------------------------------------------------------------------------
 // Grid-wide synchronisation for the persistent whole-iteration kernels (cooperative launch: every
 // CTA is resident).  One monotonically increasing arrival counter (reset by the host before each
 // launch): barrier k is passed when the counter reaches k*gridDim.x, so the last arriver's atomic
@@ -706,6 +867,101 @@ __device__ __forceinline__ double grid_allreduce(double v, double* partials /*2*
     s = block_sum_all(s, sm);
     if (peers) s = peer_allreduce_block(s, peers, kind, seq, &s_glob, gs.bar->result_ll);
     return s;
+}
+
+// Two-scalar variant of peer_allreduce_block / grid_allreduce (single-reduction CG): both values cross NVLink in one
+// mailbox round (kind 0 and kind 1 slots, sequence numbers seq0 / seq1) and come back through the two local LL word pairs.
+__device__ __forceinline__ void peer_allreduce2_block(double& a, double& b, PeerInfo* P, unsigned int seq0, unsigned int seq1,
+                                                      double* sm_bcast /*[2]*/, unsigned long long* result_ll) {
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        const int kind = lane >> 4, rk = lane & 15;
+        const unsigned int seq = kind ? seq1 : seq0;
+        unsigned long long* res = result_ll + (kind * 2 + (int)(seq & 1u)) * 2;
+        double sum = 0.0;
+        if (blockIdx.x == 0) {
+            const int n = P->nranks, me = P->rank;
+            const int slot = ((kind * 2 + (int)(seq & 1u)) * kMaxRanks);
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(kind ? b : a);
+            const unsigned long long w0 = ((unsigned long long)seq << 32) | (bits & 0xffffffffull);
+            const unsigned long long w1 = ((unsigned long long)seq << 32) | (bits >> 32);
+            fence_acq_rel_sys();
+            if (rk < n) {
+                unsigned long long* dst = P->mbox[rk] + (slot + me) * 2;
+                st_relaxed_sys_u64(dst, w0);
+                st_relaxed_sys_u64(dst + 1, w1);
+            }
+            double v = 0.0;
+            bool ok = true;
+            if (rk < n) {
+                const unsigned long long* src = P->mbox[me] + (slot + rk) * 2;
+                unsigned long long x, y;
+                const long long t0 = clock64();
+                for (;;) {
+                    x = ld_relaxed_sys_u64(src);
+                    y = ld_relaxed_sys_u64(src + 1);
+                    if ((unsigned int)(x >> 32) == seq && (unsigned int)(y >> 32) == seq) break;
+                    if (clock64() - t0 > 20000000000LL) { ok = false; break; }
+                }
+                v = __longlong_as_double((long long)(((y & 0xffffffffull) << 32) | (x & 0xffffffffull)));
+            }
+            fence_acq_rel_sys();
+            const bool all_ok = __all_sync(0xffffffffu, ok);
+            double sa = 0.0, sb = 0.0;
+            for (int r = 0; r < n; ++r) { sa += __shfl_sync(0xffffffffu, v, r); sb += __shfl_sync(0xffffffffu, v, 16 + r); }
+            if (!all_ok) {
+                if (lane == 0) P->error = 1;
+                sa = sb = __longlong_as_double(0x7ff8000000000000LL);
+            }
+            sum = kind ? sb : sa;
+            if (rk == 0) {
+                const unsigned long long sbits = (unsigned long long)__double_as_longlong(sum);
+                st_relaxed_gpu_u64(res, ((unsigned long long)seq << 32) | (sbits & 0xffffffffull));
+                st_relaxed_gpu_u64(res + 1, ((unsigned long long)seq << 32) | (sbits >> 32));
+            }
+        } else if (rk == 0) {
+            unsigned long long x, y;
+            const long long t0 = clock64();
+            for (;;) {
+                x = ld_relaxed_gpu_u64(res);
+                y = ld_relaxed_gpu_u64(res + 1);
+                if ((unsigned int)(x >> 32) == seq && (unsigned int)(y >> 32) == seq) break;
+                if (clock64() - t0 > 40000000000LL) { x = 0; y = 0x7ff80000ull; break; }
+            }
+            fence_acq_rel_gpu();
+            sum = __longlong_as_double((long long)(((y & 0xffffffffull) << 32) | (x & 0xffffffffull)));
+        }
+        if (rk == 0) sm_bcast[kind] = sum;
+    }
+    __syncthreads();
+    a = sm_bcast[0];
+    b = sm_bcast[1];
+    __syncthreads();
+}
+
+// partials: 4 * gridDim.x doubles (two values, double-buffered by barrier parity)
+__device__ __forceinline__ void grid_allreduce2(double& v1, double& v2, double* partials, GridSync& gs,
+                                                PeerInfo* peers = nullptr, bool wrote_peer = false, unsigned int seq0 = 0, unsigned int seq1 = 0) {
+    __shared__ double sm[32];
+    __shared__ double s_glob[2];
+    const unsigned int nblocks = gridDim.x;
+    double* slot = partials + (size_t)(gs.passed & 1u) * 2 * nblocks;
+    v1 = block_sum(v1, sm);
+    v2 = block_sum(v2, sm);
+    if (threadIdx.x == 0) {
+        slot[blockIdx.x] = v1;
+        slot[nblocks + blockIdx.x] = v2;
+        gs.arrive_and_wait(wrote_peer);
+    } else {
+        ++gs.passed;
+    }
+    __syncthreads();
+    double s1 = 0.0, s2 = 0.0;
+    for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) { s1 += __ldcg(slot + i); s2 += __ldcg(slot + nblocks + i); }
+    s1 = block_sum_all(s1, sm);
+    s2 = block_sum_all(s2, sm);
+    if (peers) peer_allreduce2_block(s1, s2, peers, seq0, seq1, s_glob, gs.bar->result_ll);
+    v1 = s1; v2 = s2;
 }
 
 constexpr int kPersistThreads = 512;      // one CTA per SM (128 registers per thread for the operator body)

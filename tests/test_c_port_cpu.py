@@ -17,6 +17,48 @@ def test_c_port_apply_bit_exact_vs_reference():
         assert np.array_equal(a[~np.isnan(ref)], ref[~np.isnan(ref)])
 
 
+def test_c_port_rhs_and_extrapolate_bit_exact_vs_reference():
+    """the C restatements of initialize_solver (:504-513) and extrapolate (:472-502) against the reference's own outputs"""
+    f = load_golden("visc3d_kernels_6x7x8")
+    b = [np.full(f[k].shape, np.nan) for k in ("vx", "vy", "vz")]
+    c_port.initialize_solver(f["gres"], float(f["scale"]), float(f["mu"]), f["vx"], f["vy"], f["vz"], f["sphi"], None, f["vol"], *b)
+    for a, n in zip(b, "xyz"):
+        ref = f["b" + n]
+        assert np.array_equal(np.isnan(a), np.isnan(ref))
+        assert np.array_equal(a[~np.isnan(ref)], ref[~np.isnan(ref)])
+    v = [f[k].copy() for k in ("vx", "vy", "vz")]
+    c_port.extrapolate(f["gres"], 3, *v, f["sphi"])
+    for a, n in zip(v, "xyz"):
+        assert np.array_equal(a, f["e" + n])
+
+
+def test_c_port_setup_vs_numpy_oracle_scene():
+    """same two functions on the benchmark scene (non-trivial solid geometry), bit for bit against the NumPy oracle"""
+    import scenes
+    sc = scenes.buckling(20, mu=10.0)
+    g = sc["gres"]
+    sphi = sc["sphi"].numpy()
+    vol = np.ascontiguousarray(sc["lvol"].numpy() / 3.0e-7)
+    va = [sc[k].numpy().astype(np.float64) for k in ("vx", "vy", "vz")]
+    vb = [a.copy() for a in va]
+    O.visc3d_extrapolate(g, 3, *va, sphi)
+    c_port.extrapolate(g, 3, *vb, sphi)
+    for a, b in zip(va, vb):
+        assert np.array_equal(a, b)
+    ba = [np.zeros_like(a) for a in va]
+    bb = [np.zeros_like(a) for a in va]
+    O.visc3d_initialize_solver(g, 1.7, 10.0, *va, sphi, None, vol, *ba)
+    c_port.initialize_solver(g, 1.7, 10.0, *vb, sphi, None, vol, *bb)
+    for a, b in zip(ba, bb):
+        assert np.array_equal(a, b)
+    assert any(np.any(a != 0) for a in ba)
+
+
+def test_c_port_thread_control():
+    n = c_port.use_all_cores()
+    assert n >= 1 and n == c_port.num_threads()
+
+
 def test_c_port_solve_vs_reference():
     for tag in ("visc3d_solve_8x10x8", "visc3d_solve_stiff_6x8x6"):
         f = load_golden(tag)
