@@ -130,16 +130,25 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 
 def run_reference(args):
+    """CPU arm: the fp64 C/OpenMP restatement of the reference's solve() on this box's host cores (the reference itself
+    has no CPU implementation).  One solve is prepared exactly like the GPU step (extrapolation, RHS, first apply: timed
+    once); every timed step then runs a bounded sample of `--ref-iters` CG iterations of the same 200-iteration window, and
+    the set-up time is charged pro rata, so the figure is iterations/s of the WHOLE step like the GPU arm's.  With
+    `--ref-full-step` (default at N=1) one complete 200-iteration step is also timed end to end, once."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import numpy as np
     import scenes
     from oracle import c_port
+    cores = c_port.use_all_cores()          # torchrun exports OMP_NUM_THREADS=1: size the team to the host cores explicitly
     n = args.size
     sc = scenes.buckling(n, device="cpu", mu=args.mu)
     s = c_port.ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
-    st = s.prepare(sc["dt"], args.mu, sc["rho"], sc["vx"].numpy(), sc["vy"].numpy(), sc["vz"].numpy(), sc["sphi"].numpy(), sc["lvol"].numpy())
+    arrs = [sc[k].numpy() for k in ("vx", "vy", "vz", "sphi", "lvol")]
+    t0 = time.perf_counter()
+    st = s.prepare(sc["dt"], args.mu, sc["rho"], *arrs)
+    t_prep = time.perf_counter() - t0
     sample = args.ref_iters
     delta = st["delta"]
 
@@ -153,18 +162,29 @@ def run_reference(args):
     for _ in range(args.steps):
         delta = step(delta)
     dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
-    cores = c_port.num_threads()
+    per_iter = dt / (sample * args.steps)
+    step_s = t_prep + args.iters * per_iter                 # one whole step: set-up + the fixed iteration window
+    value = args.iters / step_s
+    full = None
+    if args.ref_full_step:
+        t0 = time.perf_counter()
+        st2 = s.prepare(sc["dt"], args.mu, sc["rho"], *arrs)
+        c_port.cg(sc["gres"], st2["scale"], args.mu, st2["x"], st2["r"], st2["d"], st2["q"], st2["sphi"], st2["vol"], 0.0, args.iters, st2["delta"])
+        tf = time.perf_counter() - t0
+        full = {"seconds": tf, "value": args.iters / tf, "what": f"one complete step (extrapolation + RHS + first apply + {args.iters} CG iterations), timed once"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n, "cpu"),
+        "config": workload_config(args, n, "gpu"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} CG iterations per step of the same {n}^3 buckling scene (fp64 C/OpenMP restatement, oracle/c_port)"},
+                         "sample": f"set-up of one solve timed once ({t_prep:.2f} s) + {sample} CG iterations per timed step of the same {n}^3 "
+                                   f"buckling scene ({1e3 * per_iter:.1f} ms per iteration); value = {args.iters} / (set-up + {args.iters} x per-iteration time); "
+                                   "fp64 C/OpenMP restatement (oracle/c_port)",
+                         "setup_s": t_prep, "ms_per_iteration": 1e3 * per_iter, "full_step": full},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference has no CPU implementation (Numba-CUDA only); this arm times a line-by-line C/OpenMP port of its CG loop",
+        "note": "the reference has no CPU implementation (Numba-CUDA only); this arm times a line-by-line C/OpenMP port of its solve()",
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -176,7 +196,7 @@ def workload_config(args, n, where):
                 "iters_per_step": args.iters, "l2": "working set >> L2"}
     return {"workload": f"buckling-{n}^3 high-viscosity (mu={args.mu:g}), ViscosityCGSolver3D fixed {args.iters}-iteration CG window per step"
                         if where != "cpu" else f"buckling-{n}^3 high-viscosity (mu={args.mu:g}), ViscosityCGSolver3D CG iterations",
-            "grid": [n, n, n], "mu": args.mu, "dt": 1.0 / 300, "rho": 1000.0, "iters_per_step": args.iters if where != "cpu" else args.ref_iters,
+            "grid": [n, n, n], "mu": args.mu, "dt": 1.0 / 300, "rho": 1000.0, "iters_per_step": args.iters,
             "partition": f"x-slabs over {args.gpus} GPU(s)" if args.gpus > 1 else "single GPU",
             "active_set": getattr(args, "active_set", "nonzero") + " (the CG kernels visit only rows with a non-zero operator row; same iterates, "
                           "iteration counts and velocities as the dense loop: tests/test_active_set_gpu.py)"
@@ -227,33 +247,40 @@ def run_native(args):
     sc = scenes.buckling(n, device="cuda", mu=args.mu) if args.scene == "buckling" else scenes.viscous_column((n, n, n), device="cuda", mu=args.mu)
     solver = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], dtype=tdtype, active_set=args.active_set, cg_mode=args.cg_mode)
     solver.max_iter = args.iters
-    dev_in = [sc[k] for k in ("vx", "vy", "vz")]
-
-    def step_device():
-        try:
-            solver.solve(sc["dt"], args.mu, sc["rho"], *dev_in, sc["sphi"], None, None, sc["lvol"], tol=0.0)
-        except ValueError:
-            pass                                  # "Failed to converge!" after exactly max_iter iterations (reference :611-612)
-        assert solver.iterations == args.iters
-
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    torch.cuda.synchronize()
-    l0 = N.launch_count()
-    with ClockSampler(local) as clocks:
+
+    def window(scene, steps, warm):
+        """`steps` fixed-window solves with device-resident inputs: (ms per step, launches per step)"""
+        dev_in = [scene[k] for k in ("vx", "vy", "vz")]
+
+        def step():
+            try:
+                solver.solve(scene["dt"], args.mu, scene["rho"], *dev_in, scene["sphi"], None, None, scene["lvol"], tol=0.0)
+            except ValueError:
+                pass                              # "Failed to converge!" after exactly max_iter iterations (reference :611-612)
+            assert solver.iterations == args.iters, solver.iterations
+
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        l0 = N.launch_count()
         ev0.record()
-        for _ in range(args.steps):
-            step_device()
+        for _ in range(steps):
+            step()
         ev1.record()
         torch.cuda.synchronize()
-    launches = N.launch_count() - l0
-    ms = ev0.elapsed_time(ev1)
-    value = args.iters * args.steps / (ms * 1e-3)
+        return ev0.elapsed_time(ev1) / steps, (N.launch_count() - l0) / steps
+
+    with ClockSampler(local) as clocks:
+        ms_step, launches_step = window(sc, args.steps, max(args.warmup, 3))
+    ms = ms_step * args.steps
+    launches = int(round(launches_step * args.steps))
+    value = args.iters / (ms_step * 1e-3)
 
     # ---- e2e: the same call with host (pinned) buffers -------------------------------------------------------
     host = {k: sc[k].cpu().pin_memory() for k in ("vx", "vy", "vz", "sphi", "lvol")}
-    out_host = [torch.empty(tuple(a.shape), dtype=tdtype).pin_memory() for a in (solver.x_x, solver.x_y, solver.x_z)]
+    # the step's result in the caller's own precision: the API writes fp32 vx, vy, vz (reference :613), so that is what comes back
+    out_host = [torch.empty(tuple(a.shape), dtype=host["vx"].dtype).pin_memory() for a in (solver.x_x, solver.x_y, solver.x_z)]
     h2d = sum(host[k].numel() * host[k].element_size() for k in host)
     d2h = sum(a.numel() * a.element_size() for a in out_host)
 
@@ -269,31 +296,137 @@ def run_native(args):
     e2e_steps = max(2, min(args.steps, 5))
     step_e2e()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    ev0.record()
-    for _ in range(e2e_steps):
-        step_e2e()
-    ev1.record()
-    torch.cuda.synchronize()
+    with ClockSampler(local) as clocks_e2e:
+        ev0.record()
+        for _ in range(e2e_steps):
+            step_e2e()
+        ev1.record()
+        torch.cuda.synchronize()
     e2e_ms = ev0.elapsed_time(ev1)
     e2e_value = args.iters * e2e_steps / (e2e_ms * 1e-3)
     del host
 
-    # ---- roofline: the CG window alone, and each kernel of the iteration alone --------------------------------
+    # ---- roofline of the default leg: the CG window alone, and each kernel of the iteration alone ------------------
     scale = sc["dt"] / solver.cell_vol / sc["rho"]
+    kinfo = kernel_study(solver, lib, N, torch, scale, args, esz)
+    persistent = kinfo["persistent"]
+    iter_ms, kern, kbytes, iter_bytes = kinfo["iter_ms"], kinfo["kernel_ms"], kinfo["kernel_bytes"], kinfo["iter_bytes"]
+    l2_resident = kinfo["working_set"] < 100e6
+    if persistent:
+        # the iteration runs as ONE persistent kernel (its phases are the kernels above): that kernel is the dominant one of the step
+        dom = kinfo["persistent_name"]
+        achieved = iter_bytes / (iter_ms * 1e-3) / 1e9
+        dom_share = iter_ms * args.iters / ms_step
+        per_launch = {"iterations_per_launch": 64, "algorithmic_bytes_per_launch": 64 * iter_bytes,
+                      "note": "achieved = active-set bytes / duration, both per launch of 64 iterations; traffic = dram bytes of one such launch (ncu)"}
+    else:
+        dom = max(kern, key=kern.get)
+        achieved = kbytes[dom] / (kern[dom] * 1e-3) / 1e9
+        dom_share = kern[dom] * args.iters / ms_step
+        per_launch = {"iterations_per_launch": 1, "algorithmic_bytes_per_launch": kbytes[dom]}
+    traffic, traffic_src = None, None
+    try:                                              # dram bytes per launch from the committed ncu --set full capture of this command
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        key = args.scene + ":" + args.active_set + ":" + ("persistent_sr" if persistent and kinfo["sr"] else "persistent" if persistent else dom.split()[0])
+        traffic = tj.get(key)
+        traffic_src = tj.get("_source", {}).get(key) if isinstance(tj.get("_source"), dict) else None
+    except Exception:
+        pass
+    iter_gbs = words_iter * esz * value / 1e9
+    if l2_resident:
+        # The active set of this scene (0.45 % of the face rows) is an L2-resident problem: the kernel is bound by grid-barrier
+        # and L2 latency, not by HBM.  `achieved` is the rate at which it walks its (L2-resident) working set and is NOT
+        # compared with the HBM peak; the DRAM-side figure is traffic / duration.  The HBM-bound regimes of the SAME kernels
+        # are measured below (hbm_leg), against the HBM roofline.
+        dram_gbs = (traffic / (64 * iter_ms * 1e-3) / 1e9) if (traffic and persistent) else None
+        roofline = {"bound": "l2-latency", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": None,
+                    "achieved_is": "active-set bytes per second served from L2 (not DRAM); no HBM fraction is claimed for this leg",
+                    "dram_GBps": dram_gbs, "dram_frac_of_peak": (dram_gbs / peak) if dram_gbs else None}
+    else:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}
+    roofline.update({
+        "traffic": traffic, "traffic_source": traffic_src or "profiles/ncu_traffic.json (ncu --set full capture, per launch)",
+        "peak_source": peak_src, "share_of_step": dom_share, "launch": per_launch,
+        "cg_iteration_us": iter_ms * 1e3, "cg_iteration_bytes": iter_bytes, "setup_ms_per_step": ms_step - iter_ms * args.iters,
+        "per_kernel_ms_standalone": kern, "per_kernel_GBps_standalone": {k: kbytes[k] / (kern[k] * 1e-3) / 1e9 for k in kern},
+        "bytes_per_launch": kbytes, "cg_mode": kinfo["mode"],
+        "active_set": dict(kinfo["active"], faces=F, row_fraction=kinfo["active"]["computed_rows"] / F, l2_resident=l2_resident),
+        "dense_equivalent": {"algorithmic_GB_per_iter": words_iter * esz / 1e9, "equivalent_GBps": iter_gbs,
+                             "note": "what a kernel streaming every face row (11F+V7 words, SURVEY 8d) would need to move to match this "
+                                     "iteration rate; the active-set kernels do not move these bytes, so this is a speed-up figure, not a bandwidth"}})
+
+    # ---- CPU baseline (bounded sample) on this box's host cores ----------------------------------------------
+    cpu = cpu_baseline(args, sc, solver, lib, scale)
+
+    # ---- HBM-bound regimes of the same kernels, in the same run ----------------------------------------------------
+    hbm_variant = None
+    if args.hbm_leg and args.scene == "buckling":
+        # (1) the same scene with every fluid row visited (what the reference's kernels compute): 627 MB CG working set
+        solver._e.set_active_mode("fluid")
+        with ClockSampler(local) as cl:
+            ms_f, _ = window(sc, max(2, min(args.steps, 5)), 2)
+        k2 = kernel_study(solver, lib, N, torch, scale, args, esz)
+        hbm_variant = {"what": "same scene and window, active_set='fluid' (every row the reference's kernels compute)", "value": args.iters / (ms_f * 1e-3),
+                       "unit": UNIT, "ms_per_step": ms_f, "cg_iteration_us": k2["iter_ms"] * 1e3, "cg_mode": k2["mode"], "active_set": k2["active"],
+                       "per_kernel_ms": k2["kernel_ms"], "per_kernel_frac_of_hbm_peak": {k: k2["kernel_bytes"][k] / (k2["kernel_ms"][k] * 1e-3) / 1e9 / peak for k in k2["kernel_ms"]},
+                       "iteration_frac_of_hbm_peak_active_bytes": k2["iter_bytes"] / (k2["iter_ms"] * 1e-3) / 1e9 / peak, "clocks": cl.summary()}
+        solver._e.set_active_mode(args.active_set)
+        # (2) dense liquid (viscous column, 93 % of the rows are fluid): the regime SURVEY 8d's 11F+V7 accounting describes
+        del sc
+        torch.cuda.empty_cache()
+        col = scenes.viscous_column((n, n, n), device="cuda", mu=args.mu)
+        solver._e.set_active_mode("fluid")
+        with ClockSampler(local) as cl:
+            ms_c, _ = window(col, 2, 1)
+            k3 = kernel_study(solver, lib, N, torch, col["dt"] / solver.cell_vol / col["rho"], args, esz, win=30)
+        kb = {"K1": (2 * F + V7) * esz, "K2": 9 * F * esz} if k3["sr"] else {"K1": (2 * F + V7) * esz, "K2": 6 * F * esz, "K3": 3 * F * esz}
+        per_k = {}
+        for name, t in k3["kernel_ms"].items():
+            per_k[name] = {"ms": t, "algorithmic_bytes": kb[name.split()[0][:2]], "GBps": kb[name.split()[0][:2]] / (t * 1e-3) / 1e9,
+                           "frac": kb[name.split()[0][:2]] / (t * 1e-3) / 1e9 / peak}
+        it_gbs = words_iter * esz / (k3["iter_ms"] * 1e-3) / 1e9
+        roofline["hbm_leg"] = {"what": f"viscous-column-{n}^3 (dense liquid), active_set='fluid': the HBM-bound regime of the same kernels, 30-iteration window",
+                               "bound": "hbm", "achieved": it_gbs, "peak": peak, "unit": "GB/s", "frac": it_gbs / peak,
+                               "accounting": "(11F+V7) words per iteration, SURVEY 8d: K1 2F+V7, update kernels 9F", "bytes_per_iteration": words_iter * esz,
+                               "cg_iteration_ms": k3["iter_ms"], "iters_per_s": 1e3 / k3["iter_ms"], "cg_mode": k3["mode"], "per_kernel": per_k,
+                               "active_set": k3["active"], "step_ms": ms_c, "clocks": cl.summary()}
+        del col
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, n, "gpu"),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": e2e_ms / e2e_steps, "clocks": clocks_e2e.summary()},
+        "gpu_launches": launches, "roofline": roofline, "hbm_variant": hbm_variant, "cpu_baseline": cpu, "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), file=args._json_out, flush=True)
+    return 0
+
+
+def kernel_study(solver, lib, N, torch, scale, args, esz, win=None):
+    """CUDA-event timings on the solver's CURRENT operator / active set: the CG window alone (per-iteration time) and each
+    kernel of the iteration alone.  Bytes: the kernels walk the ACTIVE 32-point lattice segments only, so the
+    unit is the lattice point of an active segment.  Two-reduction CG: K1 13 words + 1 activity byte, K2 18, K3 9;
+    single-reduction CG: K1s 13 words + 1 byte (reads r, 7 coefficients; writes w), K2s 27 (reads r, w, p, s, x; writes p, s, x, r)."""
     stream = torch.cuda.current_stream().cuda_stream
-    # bytes: the kernels walk the ACTIVE 32-point lattice segments only, so the unit is the lattice point of an
-    # active segment: K1 reads d (3) + coefficients (7) and writes q (3) = 13 words + 1 activity byte; K2 reads x,d,r,q and
-    # writes x,r = 18 words; K3 reads r,d and writes d = 9 words (3 components per point)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     segs, segs_total, rows = solver.active_info()
     pts = segs * 32
-    kbytes = {"K1 visc3d_apply_dot": pts * (13 * esz + 1), "K2 cg_update_xr": pts * 18 * esz, "K3 cg_update_d": pts * 9 * esz}
-    iter_bytes = sum(kbytes.values())
-    working_set = pts * (22 * esz + 1)
-    persistent = N.check(lib.fs_visc3d_cg_mode_in_use(solver._e.h), "mode") == N.CG_PERSISTENT
+    mode = N.check(lib.fs_visc3d_cg_mode_in_use(solver._e.h), "mode")
+    persistent = mode in (N.CG_PERSISTENT, N.CG_PERSISTENT_SR)
+    sr = mode in (N.CG_KERNELS_SR, N.CG_PERSISTENT_SR)
+    if sr:
+        names = ((1, "K1s visc3d_apply_dot2"), (2, "K2s cg_update_sr"))
+        kbytes = {names[0][1]: pts * (13 * esz + 1), names[1][1]: pts * 27 * esz}
+    else:
+        names = ((1, "K1 visc3d_apply_dot"), (2, "K2 cg_update_xr"), (3, "K3 cg_update_d"))
+        kbytes = {names[0][1]: pts * (13 * esz + 1), names[1][1]: pts * 18 * esz, names[2][1]: pts * 9 * esz}
     N.check(lib.fs_visc3d_cg_enqueue(solver._e.h, scale, args.mu, 64, stream), "warm")
     torch.cuda.synchronize()
-    win = 512 if persistent else 192
+    if win is None:
+        win = 512 if persistent else 192
     ev0.record()
     N.check(lib.fs_visc3d_cg_enqueue(solver._e.h, scale, args.mu, win, stream), "window")
     ev1.record()
@@ -301,7 +434,7 @@ def run_native(args):
     iter_ms = ev0.elapsed_time(ev1) / win
     kern = {}
     reps = 30
-    for which, name in ((1, "K1 visc3d_apply_dot"), (2, "K2 cg_update_xr"), (3, "K3 cg_update_d")):
+    for which, name in names:
         N.check(lib.fs_visc3d_kernel_enqueue(solver._e.h, which, scale, args.mu, 3, stream), "warm")
         torch.cuda.synchronize()
         ev0.record()
@@ -309,54 +442,13 @@ def run_native(args):
         ev1.record()
         torch.cuda.synchronize()
         kern[name] = ev0.elapsed_time(ev1) / reps
-    if persistent:
-        # the iteration runs as ONE persistent kernel (K1, K2, K3 are its phases): that kernel is the dominant one of the step
-        dom = "visc3d_cg_persistent_kernel (K1+K2+K3 phases of one cooperative launch per 64 iterations)"
-        achieved = iter_bytes / (iter_ms * 1e-3) / 1e9
-        dom_share = iter_ms * args.iters / (ms / args.steps)
-    else:
-        dom = max(kern, key=kern.get)
-        achieved = kbytes[dom] / (kern[dom] * 1e-3) / 1e9
-        dom_share = kern[dom] * args.iters / (ms / args.steps)
-    iter_gbs = words_iter * esz * value / 1e9
-    traffic = None
-    try:                                              # dram bytes per launch from the committed ncu --set full capture, if any
-        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(args.scene + ":" + args.active_set + ":" + ("persistent" if persistent else dom.split()[0]))
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "share_of_step": dom_share,
-                "launch": ({"iterations_per_launch": 64, "algorithmic_bytes_per_launch": 64 * iter_bytes,
-                            "note": "achieved = algorithmic bytes / duration, both per launch of 64 iterations (= per iteration x 64); "
-                                    "traffic = dram bytes of one such launch (ncu)"} if persistent else
-                           {"iterations_per_launch": 1, "algorithmic_bytes_per_launch": kbytes[dom]}),
-                "cg_iteration_us": iter_ms * 1e3, "cg_iteration_bytes": iter_bytes, "setup_ms_per_step": ms / args.steps - iter_ms * args.iters,
-                "per_kernel_ms_standalone": kern, "per_kernel_GBps_standalone": {k: kbytes[k] / (kern[k] * 1e-3) / 1e9 for k in kern},
-                "bytes_per_launch": kbytes,
-                "cg_mode": "persistent" if persistent else "kernels",
-                "active_set": {"mode": args.active_set, "segments": segs, "segments_total": segs_total, "computed_rows": rows,
-                               "faces": F, "row_fraction": rows / F, "cg_working_set_MB": working_set / 1e6,
-                               "l2_resident": working_set < 100e6},
-                "note": "bytes = lattice points of ACTIVE segments x words per point (13+18+9 words per iteration); when the CG working set "
-                        "is L2-resident the achieved figure is L2, not HBM, traffic (see --scene column / --active-set fluid for the "
-                        "HBM-bound regimes)",
-                "dense_equivalent": {"algorithmic_GB_per_iter": words_iter * esz / 1e9, "achieved_GBps": iter_gbs, "frac": iter_gbs / peak,
-                                     "formula": "(11F+V7) words/iter if every face row were streamed, SURVEY §8d"}}
-
-    # ---- CPU baseline (bounded sample) on this box's host cores ----------------------------------------------
-    cpu = cpu_baseline(args, sc, solver, lib, scale)
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, n, "gpu"),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "ms_per_step": e2e_ms / e2e_steps},
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
-    }
-    print(json.dumps(line), file=args._json_out, flush=True)
-    return 0
+    modes = {N.CG_KERNELS: "kernels", N.CG_PERSISTENT: "persistent", N.CG_KERNELS_SR: "kernels_sr", N.CG_PERSISTENT_SR: "persistent_sr"}
+    return {"iter_ms": iter_ms, "kernel_ms": kern, "kernel_bytes": kbytes, "iter_bytes": sum(kbytes.values()), "working_set": pts * (22 * esz + 1),
+            "persistent": persistent, "sr": sr, "mode": modes[mode],
+            "persistent_name": ("visc3d_cg_sr_persistent_kernel (phases A: apply + both dots, B: fused update; one cooperative launch per 64 iterations)" if sr else
+                                "visc3d_cg_persistent_kernel (K1+K2+K3 phases of one cooperative launch per 64 iterations)"),
+            "active": {"mode": "fluid" if solver._e.active_mode_name == "fluid" else "nonzero", "segments": segs, "segments_total": segs_total,
+                       "computed_rows": rows, "cg_working_set_MB": pts * (22 * esz + 1) / 1e6}}
 
 
 def cpu_baseline(args, sc, solver, lib, scale):
@@ -366,6 +458,7 @@ def cpu_baseline(args, sc, solver, lib, scale):
     from oracle import c_port
     from solver import _native as N
     try:
+        c_port.use_all_cores()                   # (torchrun exports OMP_NUM_THREADS=1)
         solver.max_iter = 0
         try:
             solver.solve(sc["dt"], args.mu, sc["rho"], sc["vx"], sc["vy"], sc["vz"], sc["sphi"], None, None, sc["lvol"], tol=0.0)
@@ -399,15 +492,19 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--iters", type=int, default=200, help="CG iterations per step (fixed window)")
     ap.add_argument("--ref-iters", type=int, default=4, help="CG iterations per step of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--ref-full-step", type=int, default=None, help="CPU arm: also time one complete 200-iteration step (default: on at N=1)")
+    ap.add_argument("--hbm-leg", type=int, default=1, help="also measure the HBM-bound regimes of the same kernels (roofline.hbm_leg, hbm_variant)")
     ap.add_argument("--mu", type=float, default=100.0)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="solver storage/arithmetic type (reference: f64)")
     ap.add_argument("--active-set", default="nonzero", choices=["nonzero", "fluid"],
                     help="rows the CG kernels visit: nonzero (default) = rows with a non-zero coefficient; fluid = every row the reference computes")
-    ap.add_argument("--cg-mode", default="auto", choices=["auto", "kernels", "persistent", "persistent_fold"],
+    ap.add_argument("--cg-mode", default="auto", choices=["auto", "kernels", "persistent", "kernels_sr", "persistent_sr"],
                     help="three kernels per iteration from a CUDA graph, one persistent cooperative kernel, or auto by working-set size")
     ap.add_argument("--scene", default="buckling", choices=["buckling", "column"],
                     help="buckling = BASELINE config 4 (default); column = dense-fluid viscous column (config 5 geometry) for kernel studies")
     args = ap.parse_args()
+    if args.ref_full_step is None:
+        args.ref_full_step = 1 if args.gpus == 1 else 0
     if args.impl == "reference":
         return run_reference(args)
     return run_native(args)

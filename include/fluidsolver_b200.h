@@ -66,13 +66,19 @@ extern "C" {
 #define FS_ACTIVE_NONZERO 1
 
 /* how the CG iterations are executed (fs_visc3d_set_cg_mode); identical arithmetic:
- *   FS_CG_KERNELS     three kernels per iteration (K1 apply+d.q, K2 x/r update + r.r, K3 d update), replayed from a CUDA graph
- *   FS_CG_PERSISTENT  one cooperative launch runs whole iterations: the three kernels become phases separated by grid barriers
- *   FS_CG_AUTO        (default) persistent while the CG working set is small (launch-latency bound), kernels otherwise */
+ *   FS_CG_KERNELS     the reference's recurrence (two reductions per iteration): three kernels per iteration (K1 apply+d.q,
+ *                     K2 x/r update + r.r, K3 d update), replayed from a CUDA graph
+ *   FS_CG_PERSISTENT  the same recurrence in one cooperative launch: the three kernels become phases separated by grid barriers
+ *   FS_CG_KERNELS_SR / FS_CG_PERSISTENT_SR   single-reduction (Chronopoulos-Gear) form of the same iteration: w = A r fused
+ *                     with both dot products (r.r, w.r), then one fused update of p, s, x, r — two kernels / two grid
+ *                     barriers and ONE reduction per iteration; same iterates up to rounding, same stopping test
+ *   FS_CG_AUTO        (default) single-reduction; persistent while the CG working set is small (launch-latency bound),
+ *                     stand-alone kernels otherwise; the NCCL transport always uses FS_CG_KERNELS */
 #define FS_CG_AUTO 0
 #define FS_CG_KERNELS 1
 #define FS_CG_PERSISTENT 2
-#define FS_CG_PERSISTENT_FOLD 3 /* persistent, with the d update folded into the next apply phase (two grid barriers per iteration) */
+#define FS_CG_KERNELS_SR 3
+#define FS_CG_PERSISTENT_SR 4
 
 /* result of a CG run */
 typedef struct fs_cg_stats {
@@ -111,7 +117,7 @@ void* fs_visc3d_vector_ptr(const fs_visc3d* h, int vec, int comp);
 int fs_visc3d_debug_read(fs_visc3d* h, int what, void* out_host, size_t bytes);
 /* Select how iterations are launched (FS_CG_*). */
 int fs_visc3d_set_cg_mode(fs_visc3d* h, int mode);
-/* After fs_visc3d_pack: the mode FS_CG_AUTO resolves to for the current active set (FS_CG_KERNELS or FS_CG_PERSISTENT). */
+/* After fs_visc3d_pack: the mode in use for the current active set (FS_CG_KERNELS, FS_CG_PERSISTENT, FS_CG_KERNELS_SR or FS_CG_PERSISTENT_SR). */
 int fs_visc3d_cg_mode_in_use(fs_visc3d* h);
 /* Select the active-row set (FS_ACTIVE_*); takes effect at the next fs_visc3d_pack. */
 int fs_visc3d_set_active_mode(fs_visc3d* h, int mode);

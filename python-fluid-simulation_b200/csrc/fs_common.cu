@@ -8,6 +8,14 @@ namespace fs {
 thread_local char g_err[512] = "";
 long long g_launches = 0;
 
+int coop_max_blocks(const void* fn, int threads, size_t dyn_smem) {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, dyn_smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return sms * per_sm;
+}
+
 __global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_iter, int dist) {
     st->delta = 0.0;
     st->delta_old = 0.0;

@@ -48,6 +48,11 @@ constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Largest grid a cooperative launch of `fn` with `threads` threads per block can have on the CURRENT context: the SM count
+// the context exposes (smaller than kSMs under MPS active-thread percentages, green contexts, other sm_100 SKUs) times
+// the resident blocks per SM.  0 on error.
+int coop_max_blocks(const void* fn, int threads, size_t dyn_smem = 0);
+
 // ---------------------------------------------------------------------------------------------
 // device-resident CG control block: alpha/beta/convergence live on the GPU so the iteration
 // needs no host round trip (the reference does two blocking .item() reads per iteration).
@@ -102,6 +107,8 @@ struct PeerHot {
     int has_lo, has_hi;
     char* q_lo[3];
     char* q_hi[3];
+    char* w_lo[3];     // the same planes of the neighbours' w = A r buffer (single-reduction CG)
+    char* w_hi[3];
     long long comp_len, halo_lo_end, halo_hi_begin, halo_hi_end;
     long long hb[6], he[6];   // the same halo rows as [begin,end) intervals of the flat 3-component index (empty if unused)
 };

@@ -481,7 +481,11 @@ static int press_prepare_list(fs_press* h, const double* x, const double* d, con
 
 static int press_persistent(fs_press* h, double* x, double* d, double* r, double* q, const double* wx, const double* wy, const double* wz,
                             const double* lphi, long long n, cudaStream_t s) {
-    const int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, kSMs);
+    const void* fn3 = h->op == OP_DENSITY ? (const void*)press_cg_persistent_kernel<3, OP_DENSITY> : (const void*)press_cg_persistent_kernel<3, OP_PRESSURE>;
+    const void* fn = h->nz > 0 ? fn3 : (const void*)press_cg_persistent_kernel<2, OP_PRESSURE>;
+    const int cap = coop_max_blocks(fn, kPersistThreads);      // SMs of this context x resident CTAs per SM
+    if (cap < 1) { h->use_list = false; return 1; }
+    const int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, cap < kSMs ? cap : kSMs);
     while (n > 0) {
         int ni = (int)(n < (1 << 20) ? n : (1 << 20));
         cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);
@@ -492,13 +496,17 @@ static int press_persistent(fs_press* h, double* x, double* d, double* r, double
             Grid<3> g = make_grid<3>(h->nx, h->ny, h->nz);
             PressW<3> W = mkW<3>(wx, wy, wz);
             void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni};
-            const void* fn = h->op == OP_DENSITY ? (const void*)press_cg_persistent_kernel<3, OP_DENSITY> : (const void*)press_cg_persistent_kernel<3, OP_PRESSURE>;
             e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args, 0, s);
         } else {
             Grid<2> g = make_grid<2>(h->nx, h->ny, 0);
             PressW<2> W = mkW<2>(wx, wy, nullptr);
             void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni};
-            e = cudaLaunchCooperativeKernel((const void*)press_cg_persistent_kernel<2, OP_PRESSURE>, dim3(grid), dim3(kPersistThreads), args, 0, s);
+            e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args, 0, s);
+        }
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported) {
+            cudaGetLastError();                      // this context cannot hold the cooperative grid: dense three-kernel path
+            h->use_list = false;
+            return 1;
         }
         if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
         FS_LAUNCH_CHECK();
@@ -509,7 +517,10 @@ static int press_persistent(fs_press* h, double* x, double* d, double* r, double
 
 static int press_iterations(fs_press* h, double* x, double* d, double* r, double* q, const double* wx, const double* wy, const double* wz,
                             const double* lphi, long long n, cudaStream_t s) {
-    if (h->use_list) return press_persistent(h, x, d, r, q, wx, wy, wz, lphi, n, s);
+    if (h->use_list) {
+        const int st = press_persistent(h, x, d, r, q, wx, wy, wz, lphi, n, s);
+        if (st != 1) return st;                      // 1 = cooperative launch impossible here, nothing was enqueued
+    }
     const void* ptrs[9] = {x, d, r, q, wx, wy, wz, lphi, nullptr};
     if (!press_same_ptrs(h, ptrs)) {                      // the graph bakes the array pointers in
         h->graph.valid = false;

@@ -33,11 +33,16 @@ struct Lat3 {
     long long sx, sy, NL;
     int u_xhi;   // last computed x-plane of u rows: nx-1, or nx-2 when a higher slab owns plane nx-1 (multi-GPU)
     int has_lo, has_hi;   // multi-GPU: plane 0 / plane nx-1 mirrors rows owned by the lower / higher slab
+    // x-window of the once-per-solve passes (pack, load, extrapolation): the caller's arrays hold the cells [wlo, wcells) of
+    // the grid only — lattice planes wlo..whi are (re)built from them.  Whole grid: wlo = 0, whi = nx, wcells = nx.
+    // (gathered multi-GPU solve: every rank packs its own window of the GLOBAL lattice; chunked host uploads)
+    int wlo, whi, wcells;
 };
 
 template <typename T> struct Visc3Dev {
     Lat3 L;
     const T* coef[7];
+    const T* cs[7];          // pre-scaled coefficients of the CG-loop apply (visc3d_scale_kernel): diag_u, diag_v, diag_w, 2s*Vc, s*Exy, s*Exz, s*Eyz
     const uint8_t* mask[3];
     const uint8_t* act;      // per lattice point: bit c set <=> row c is computed (same information as the NaN tags, 1 byte)
 };
@@ -83,12 +88,16 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
                                                           double vol_norm, T* __restrict__ coef /*[7][NL]*/, uint8_t* __restrict__ mask /*[3][NL]*/,
                                                           uint8_t* __restrict__ act /*[NL + 64]*/, uint8_t* __restrict__ rowflag /*[X*Y]*/,
                                                           int nonzero_only) {
-    const int row = blockIdx.x;                      // x*Y + y
+    const int row = blockIdx.x + L.wlo * L.Y;        // x*Y + y
     int any_valid = 0;                               // does this lattice row hold any fluid face? (extrapolation sweep 1 skips far rows)
     const int x = row / L.Y, y = row - x * L.Y;
     const long long fz = 1, fy = 2LL * L.nz + 1, fx = fy * (2LL * L.ny + 1);
-    const long long frow = 2LL * x * fx + 2LL * y * fy;
-    const bool ix = x < L.nx, iy = y < L.ny;
+    const long long frow = 2LL * (x - L.wlo) * fx + 2LL * y * fy;     // the fine grids start at fine plane 2*wlo
+    const bool ix = x < L.wcells, iy = y < L.ny;
+    // windowed pack: the activity test of a row reads fine planes 2x-1 .. 2x+2; on the first plane of a window that does not
+    // start at the grid boundary, and on the closing plane of one that does not end there, they are not all present — those
+    // planes get no activity bits from this rank (their owner supplies them)
+    const bool act_ok = !((L.wlo > 0 && x == L.wlo) || (L.wcells < L.nx && x >= L.wcells));
     const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
     // rows of these planes are computed by a neighbour slab and mirrored here (K2/K3 keep r and d current on them)
     const bool halo_x = (L.has_lo && x == 0) || (L.has_hi && x == L.nx - 1);
@@ -126,13 +135,11 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
             const bool fluid = in_u && s_u >= 0.0;
             T v = nan;
             const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
-            if (fluid && yz && x >= 1 && x <= L.u_xhi) {
+            if (fluid && yz && x >= 1 && x <= L.u_xhi && act_ok) {    // (act_ok: fine plane 2x-1 is present)
                 v = norm(l_u);
-                if (v == v) {
-                    bool on = true;
-                    if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(exz) || nz(vol(fy + fz - fx)) || nz(vol(fy + fz + fy)) || nz(vol(fy + fz + fz));
-                    if (on) abits |= 1u;
-                }
+                bool on = true;
+                if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(exz) || nz(vol(fy + fz - fx)) || nz(vol(fy + fz + fy)) || nz(vol(fy + fz + fz));
+                if (on) abits |= 1u;
             }
             if (fluid && halo_x && yz) abits |= 0x10u;
             coef[0 * L.NL + i] = v;
@@ -144,11 +151,9 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
             const bool yz = y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2;
             if (fluid && yz && x >= 1 && x <= L.nx - 2) {
                 v = norm(l_v);
-                if (v == v) {
-                    bool on = true;
-                    if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(eyz) || nz(vol(fx + fz + fx)) || nz(vol(fx + fz - fy)) || nz(vol(fx + fz + fz));
-                    if (on) abits |= 2u;
-                }
+                bool on = true;
+                if (nonzero_only) on = nz(v) || nz(vc) || nz(exy) || nz(eyz) || nz(vol(fx + fz + fx)) || nz(vol(fx + fz - fy)) || nz(vol(fx + fz + fz));
+                if (on) abits |= 2u;
             }
             if (fluid && halo_x && yz) abits |= 0x20u;
             coef[1 * L.NL + i] = v;
@@ -160,11 +165,9 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
             const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1;
             if (fluid && yz && x >= 1 && x <= L.nx - 2) {
                 v = norm(l_w);
-                if (v == v) {
-                    bool on = true;
-                    if (nonzero_only) on = nz(v) || nz(vc) || nz(exz) || nz(eyz) || nz(vol(fx + fy + fx)) || nz(vol(fx + fy + fy)) || nz(vol(fx + fy - fz));
-                    if (on) abits |= 4u;
-                }
+                bool on = true;
+                if (nonzero_only) on = nz(v) || nz(vc) || nz(exz) || nz(eyz) || nz(vol(fx + fy + fx)) || nz(vol(fx + fy + fy)) || nz(vol(fx + fy - fz));
+                if (on) abits |= 4u;
             }
             if (fluid && halo_x && yz) abits |= 0x40u;
             coef[2 * L.NL + i] = v;
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
         coef[4 * L.NL + i] = exy;
         coef[5 * L.NL + i] = exz;
         coef[6 * L.NL + i] = eyz;
-        act[i] = (uint8_t)abits;
+        act[i] = (uint8_t)(act_ok ? abits : 0u);
     }
     any_valid = __syncthreads_or(any_valid);
     if (threadIdx.x == 0) rowflag[row] = (uint8_t)(any_valid != 0);
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
 template <typename T, typename S>
 __global__ void __launch_bounds__(512) visc3d_load_kernel(Lat3 L, const S* __restrict__ a0, const S* __restrict__ a1, const S* __restrict__ a2,
                                                           T* __restrict__ vec /*[3][NL]*/) {
-    const int row = blockIdx.x;                      // x*Y + y, one block per lattice row
+    const int row = blockIdx.x + L.wlo * L.Y;        // x*Y + y, one block per lattice row of the window
     const int x = row / L.Y, y = row - x * L.Y;
     const S* src[3] = {a0, a1, a2};
     for (int z = threadIdx.x; z < L.Zp; z += blockDim.x) {
@@ -196,8 +199,9 @@ __global__ void __launch_bounds__(512) visc3d_load_kernel(Lat3 L, const S* __res
         for (int c = 0; c < 3; ++c) {
             int s0, s1, s2;
             comp_shape(L, c, s0, s1, s2);
+            const int xs = c == 0 ? L.whi + 1 : L.wcells;          // planes present in the caller's (windowed) array: [wlo, xs)
             T v = T(0);
-            if (x < s0 && y < s1 && z < s2) v = (T)src[c][((long long)x * s1 + y) * s2 + z];
+            if (x < xs && y < s1 && z < s2) v = (T)src[c][((long long)(x - L.wlo) * s1 + y) * s2 + z];
             vec[c * L.NL + i] = v;
         }
     }
@@ -284,12 +288,12 @@ __device__ __forceinline__ bool extrap_try_fill(const Lat3& L, T* v_all, uint8_t
 template <typename T>
 __global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, T* v_all, uint8_t* valid_all, int sweep /*1-based*/, ExtrapWork W,
                                                                       int push_to /*list to record fills in, -1 = none*/, int only_if_overflow,
-                                                                      const uint8_t* __restrict__ rowflag /*sweep 1 only, or null*/) {
+                                                                      const uint8_t* __restrict__ rowflag /*sweep 1 only, or null*/,
+                                                                      long long g_begin, long long g_end /*4-point groups of the swept x-planes*/) {
     if (only_if_overflow && (W.cap == 0u || W.count[2] == 0u)) return;
     const int nrows = L.X * L.Y;
     const unsigned int sw = (unsigned int)sweep;
-    const long long ngroups = L.NL / 4;
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (long long)gridDim.x * blockDim.x) {
+    for (long long g = g_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < g_end; g += (long long)gridDim.x * blockDim.x) {
         const long long i4 = g * 4;
         if (rowflag) {
             // sweep 1 can only fill next to an originally valid face: a group whose lattice row and the four rows around it
@@ -508,6 +512,55 @@ __global__ void __launch_bounds__(kThreads) visc3d_store_active_kernel(Lat3 L, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pre-scaled coefficients for the CG-loop apply, once per solve, on the active segments: the row diagonals (reference
+// association: diag = vol + scale*mu*(2*hi_x + 2*lo_x + hi_y + ...), :268) and the products 2*scale*mu*Vc, scale*mu*E the
+// reference forms first in every off-diagonal term.  An active row also reads volumes that sit at neighbour points
+// (i-e_A for Vc, i+e_ax for the edges), possibly in segments that are not active themselves, so each lane writes the scaled
+// values of its own point AND of the nine neighbour slots its rows read; duplicates store identical values.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) visc3d_scale_kernel(Visc3Dev<T> P, T s, T s2, T* __restrict__ cs /*[7][NL]*/,
+                                                                const int* __restrict__ seg, const int* __restrict__ nseg_p) {
+    const Lat3& L = P.L;
+    const long long NL = L.NL;
+    const long long st[3] = {L.sx, L.sy, 1};
+    const int nseg = *nseg_p;
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long k = w0; k < nseg; k += nw) {
+        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+        if (i >= NL) continue;
+        auto put = [&](int plane, long long j, T c) {
+            if (j >= 0 && j < NL) cs[plane * NL + j] = c * __ldg(P.coef[plane] + j);
+        };
+        put(3, i, s2); put(3, i - st[0], s2); put(3, i - st[1], s2); put(3, i - st[2], s2);      // 2s*Vc at i, i-e_x, i-e_y, i-e_z
+        put(4, i, s); put(4, i + st[1], s); put(4, i + st[0], s);                                 // s*Exy at i, i+e_y, i+e_x
+        put(5, i, s); put(5, i + st[2], s); put(5, i + st[0], s);                                 // s*Exz at i, i+e_z, i+e_x
+        put(6, i, s); put(6, i + st[2], s); put(6, i + st[1], s);                                 // s*Eyz at i, i+e_z, i+e_y
+        const unsigned int a = (unsigned int)P.act[i] & kActCompute;
+        auto diag = [&](auto Atag) {
+            constexpr int A = decltype(Atag)::value;
+            if (!(a & (1u << A))) return;
+            T sum = T(0);
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                T hi, lo;
+                if (ax == A) { hi = __ldg(P.coef[3] + i); lo = __ldg(P.coef[3] + i - st[A]); }
+                else { const T* E = P.coef[3 + A + ax]; hi = __ldg(E + i + st[ax]); lo = __ldg(E + i); }
+                const T h = (ax == A) ? Ar<true>::mul(T(2), hi) : hi;
+                const T l = (ax == A) ? Ar<true>::mul(T(2), lo) : lo;
+                sum = (ax == 0) ? Ar<true>::add(h, l) : Ar<true>::add(Ar<true>::add(sum, h), l);
+            }
+            cs[A * NL + i] = Ar<true>::add(__ldg(P.coef[A] + i), Ar<true>::mul(s, sum));
+        };
+        diag(std::integral_constant<int, 0>{});
+        diag(std::integral_constant<int, 1>{});
+        diag(std::integral_constant<int, 2>{});
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1: CG-loop apply fused with d.q.  Inside the loop d is exactly zero on every row that is not
 // computed (solid / boundary / padding / other slab / all-zero row), so neighbour masks are not
 // needed (SURVEY A-1).
@@ -523,7 +576,6 @@ __global__ void __launch_bounds__(kThreads) visc3d_store_active_kernel(Lat3 L, c
 // around the coefficient and vector regions for exactly that.  One block reduction at the very end
 // (fixed order, deterministic).
 // ---------------------------------------------------------------------------------------------
-constexpr bool kFoldByDefault = false;   // FS_CG_AUTO: fold K3 into K1 inside the persistent kernel
 constexpr int kK1Threads = 256;
 constexpr int kK1SegsPerBlock = kK1Threads / 32;
 // CTAs per SM: the fp64 body keeps 43 loaded values (86 registers) in flight, so it gets 128 registers per thread
@@ -535,16 +587,18 @@ template <> struct K1Occ<float> { static constexpr int value = 3; };
 // One pass over the active segments: q = A d on computed rows, returns this thread's share of d.q.
 // COHERENT = false: d is read through the read-only path (stand-alone K1: nothing writes d during the launch);
 // COHERENT = true : plain loads (persistent kernel: other CTAs rewrote d before the last grid barrier).
-template <typename T, bool DIST, bool COHERENT>
+// SR (single-reduction CG): d is the residual r, q the buffer w = A r; acc2 additionally collects r.r over the computed
+// rows, and the boundary rows go to the neighbours' w planes instead of their q planes.
+template <typename T, bool DIST, bool COHERENT, bool SR = false>
 __device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T s, T s2, const T* d, T* q, const int* __restrict__ seg, int nseg,
-                                                        const PeerHot& hot, bool& wrote_peer) {
+                                                        const PeerHot& hot, bool& wrote_peer, double* acc2_out = nullptr) {
     const Lat3& L = P.L;
     const long long NL = L.NL;
     const long long st[3] = {L.sx, L.sy, 1};
     const int lane = threadIdx.x & 31;
     const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    double acc = 0.0;
+    double acc = 0.0, acc2 = 0.0;
     auto nb = [&](int comp, long long j) -> T { return COHERENT ? d[comp * NL + j] : __ldg(d + comp * NL + j); };
     int sg_n = w0 < nseg ? __ldg(seg + w0) : 0;
     for (long long k = w0; k < nseg; k += nw) {
@@ -557,112 +611,39 @@ __device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T 
         const long long j = in ? i : (NL - 1);
         const unsigned int a = in ? ((unsigned int)__ldg(P.act + i) & kActCompute) : 0u;
         const bool au = a & 1u, av = a & 2u, aw = a & 4u;
-        const T cu = __ldg(P.coef[0] + j), cv = __ldg(P.coef[1] + j), cw = __ldg(P.coef[2] + j);
+        const T cu = __ldg(P.cs[0] + j), cv = __ldg(P.cs[1] + j), cw = __ldg(P.cs[2] + j);      // row diagonals
         const T du = nb(0, j), dv = nb(1, j), dw = nb(2, j);
-        const T ru = visc_row<T, 3, 0, false, ROW_APPLY>(P.coef, j, st, cu, du, s, s2, nb);
-        const T rv = visc_row<T, 3, 1, false, ROW_APPLY>(P.coef, j, st, cv, dv, s, s2, nb);
-        const T rw = visc_row<T, 3, 2, false, ROW_APPLY>(P.coef, j, st, cw, dw, s, s2, nb);
-        if (au) { q[i] = ru; acc += (double)du * (double)ru; }
-        if (av) { q[NL + i] = rv; acc += (double)dv * (double)rv; }
-        if (aw) { q[2 * NL + i] = rw; acc += (double)dw * (double)rw; }
+        const T ru = visc_row_scaled<T, 3, 0>(P.cs, j, st, cu, du, nb);
+        const T rv = visc_row_scaled<T, 3, 1>(P.cs, j, st, cv, dv, nb);
+        const T rw = visc_row_scaled<T, 3, 2>(P.cs, j, st, cw, dw, nb);
+        if (au) { q[i] = ru; acc += (double)du * (double)ru; if (SR) acc2 += (double)du * (double)du; }
+        if (av) { q[NL + i] = rv; acc += (double)dv * (double)rv; if (SR) acc2 += (double)dv * (double)dv; }
+        if (aw) { q[2 * NL + i] = rw; acc += (double)dw * (double)rw; if (SR) acc2 += (double)dw * (double)dw; }
         if (DIST && a != 0u) {
             // multi-GPU: my first / last owned planes are the neighbours' halo planes of q — store them straight
             // into the peers' memory over NVLink; the all-reduce that follows publishes them.  (The local halo
             // planes 0 and X-2 carry no computed row: their q is written by the NEIGHBOURS, never by this rank.)
             const long long lo0 = L.sx, hi0 = (long long)(L.X - 3) * L.sx;
+            char* const* plo = SR ? hot.w_lo : hot.q_lo;
+            char* const* phi = SR ? hot.w_hi : hot.q_hi;
             if (hot.has_lo && i >= lo0 && i < lo0 + L.sx) {
                 const long long o = i - lo0;
-                if (au) reinterpret_cast<T*>(hot.q_lo[0])[o] = ru;
-                if (av) reinterpret_cast<T*>(hot.q_lo[1])[o] = rv;
-                if (aw) reinterpret_cast<T*>(hot.q_lo[2])[o] = rw;
+                if (au) reinterpret_cast<T*>(plo[0])[o] = ru;
+                if (av) reinterpret_cast<T*>(plo[1])[o] = rv;
+                if (aw) reinterpret_cast<T*>(plo[2])[o] = rw;
                 wrote_peer = true;
             }
             if (hot.has_hi && i >= hi0 && i < hi0 + L.sx) {
                 const long long o = i - hi0;
-                if (au) reinterpret_cast<T*>(hot.q_hi[0])[o] = ru;
-                if (av) reinterpret_cast<T*>(hot.q_hi[1])[o] = rv;
-                if (aw) reinterpret_cast<T*>(hot.q_hi[2])[o] = rw;
+                if (au) reinterpret_cast<T*>(phi[0])[o] = ru;
+                if (av) reinterpret_cast<T*>(phi[1])[o] = rv;
+                if (aw) reinterpret_cast<T*>(phi[2])[o] = rw;
                 wrote_peer = true;
             }
         }
     }
+    if (SR) *acc2_out = acc2;
     return acc;
-}
-
-// K3 folded into K1 (persistent kernel only): the search direction of this iteration, d_new = r + beta d_old, is formed
-// on the fly for the point itself AND for its 26 stencil neighbours from r and d_old, stored for the point (all three
-// components of every point of the segment, computed row or not — mirrored halo rows included), and q = A d_new follows
-// as usual.  d_old must stay intact while other CTAs read it, so d ping-pongs between two buffers.  This removes the
-// separate d-update phase and its grid barrier from every iteration.
-template <typename T, bool DIST>
-__device__ __forceinline__ double visc3d_apply_dot_fold_body(const Visc3Dev<T>& P, T s, T s2, const T* dold, const T* r, T beta, T* dnew, T* q,
-                                                             const int* __restrict__ seg, int nseg, const PeerHot& hot, bool& wrote_peer) {
-    const Lat3& L = P.L;
-    const long long NL = L.NL;
-    const long long st[3] = {L.sx, L.sy, 1};
-    const int lane = threadIdx.x & 31;
-    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    double acc = 0.0;
-    auto nb = [&](int comp, long long j) -> T { return r[comp * NL + j] + beta * dold[comp * NL + j]; };
-    int sg_n = w0 < nseg ? __ldg(seg + w0) : 0;
-    for (long long k = w0; k < nseg; k += nw) {
-        const long long i = (long long)sg_n * kSegPts + lane;
-        {
-            const long long k2 = k + nw;
-            sg_n = k2 < nseg ? __ldg(seg + k2) : 0;
-        }
-        const bool in = i < NL;
-        const long long j = in ? i : (NL - 1);
-        const unsigned int a = in ? ((unsigned int)__ldg(P.act + i) & kActCompute) : 0u;
-        const bool au = a & 1u, av = a & 2u, aw = a & 4u;
-        const T cu = __ldg(P.coef[0] + j), cv = __ldg(P.coef[1] + j), cw = __ldg(P.coef[2] + j);
-        const T du = nb(0, j), dv = nb(1, j), dw = nb(2, j);
-        if (in) { dnew[i] = du; dnew[NL + i] = dv; dnew[2 * NL + i] = dw; }
-        const T ru = visc_row<T, 3, 0, false, ROW_APPLY>(P.coef, j, st, cu, du, s, s2, nb);
-        const T rv = visc_row<T, 3, 1, false, ROW_APPLY>(P.coef, j, st, cv, dv, s, s2, nb);
-        const T rw = visc_row<T, 3, 2, false, ROW_APPLY>(P.coef, j, st, cw, dw, s, s2, nb);
-        if (au) { q[i] = ru; acc += (double)du * (double)ru; }
-        if (av) { q[NL + i] = rv; acc += (double)dv * (double)rv; }
-        if (aw) { q[2 * NL + i] = rw; acc += (double)dw * (double)rw; }
-        if (DIST && a != 0u) {
-            const long long lo0 = L.sx, hi0 = (long long)(L.X - 3) * L.sx;
-            if (hot.has_lo && i >= lo0 && i < lo0 + L.sx) {
-                const long long o = i - lo0;
-                if (au) reinterpret_cast<T*>(hot.q_lo[0])[o] = ru;
-                if (av) reinterpret_cast<T*>(hot.q_lo[1])[o] = rv;
-                if (aw) reinterpret_cast<T*>(hot.q_lo[2])[o] = rw;
-                wrote_peer = true;
-            }
-            if (hot.has_hi && i >= hi0 && i < hi0 + L.sx) {
-                const long long o = i - hi0;
-                if (au) reinterpret_cast<T*>(hot.q_hi[0])[o] = ru;
-                if (av) reinterpret_cast<T*>(hot.q_hi[1])[o] = rv;
-                if (aw) reinterpret_cast<T*>(hot.q_hi[2])[o] = rw;
-                wrote_peer = true;
-            }
-        }
-    }
-    return acc;
-}
-
-// end of a folded launch: dst = r + beta * src (pending d update) or dst = src (beta_valid == false), own segments
-template <typename T>
-__device__ __forceinline__ void visc3d_fold_finish_body(long long NL, const int* __restrict__ seg, int nseg, T* dst, const T* src, const T* r,
-                                                        T beta, bool apply_beta) {
-    const int lane = threadIdx.x & 31;
-    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long k = w0; k < nseg; k += nw) {
-        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
-        if (i >= NL) continue;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const long long e = c * NL + i;
-            const T v = src[e];
-            dst[e] = apply_beta ? (r[e] + beta * v) : v;
-        }
-    }
 }
 
 template <typename T, bool DIST>
@@ -685,8 +666,8 @@ __global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot_
 // convergence logic as the three-kernel path; runs up to n_iters iterations and stops early when
 // the state says done.
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool DIST, bool FOLD>
-__global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kernel(Visc3Dev<T> P, T s, T s2, T* x, T* r, T* d, T* q, T* d2,
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kernel(Visc3Dev<T> P, T s, T s2, T* x, T* r, T* d, T* q,
                                                                                   const int* __restrict__ seg, const int* __restrict__ nseg_p,
                                                                                   CgState* st, double* partials, GridBar* bar, int n_iters,
                                                                                   PeerInfo* peers, PeerHot hot, unsigned long long* prof) {
@@ -710,20 +691,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
     auto tick = [&]() {
         if (stamp && np < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); prof[np++] = t; }
     };
-    T* cur = d;                 // buffer holding the search direction of the current iteration
-    T* nxt = d2;                // FOLD: the other buffer of the ping-pong
-    bool have_beta = false;     // FOLD: a d update (beta_d) is pending
     for (int it = 0; it < n_iters && !done; ++it) {
         tick();
-        // K1 phase: q = A d, d.q   (FOLD, from the second iteration of a launch on: d = r + beta d_old formed on the fly)
+        // K1 phase: q = A d, d.q
         bool wrote_peer = false;
-        double acc;
-        if (FOLD && have_beta) {
-            acc = visc3d_apply_dot_fold_body<T, DIST>(P, s, s2, cur, r, (T)beta_d, nxt, q, seg, nseg, hot, wrote_peer);
-            T* t = cur; cur = nxt; nxt = t;
-        } else {
-            acc = visc3d_apply_dot_body<T, DIST, true>(P, s, s2, cur, q, seg, nseg, hot, wrote_peer);
-        }
+        double acc = visc3d_apply_dot_body<T, DIST, true>(P, s, s2, d, q, seg, nseg, hot, wrote_peer);
         const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
         tick();
         if (DIST) ++seq0;
@@ -731,7 +703,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
         tick();
         // K2 phase: x += alpha d, r -= alpha q, r.r
         alpha_d = delta / dq;
-        acc = cg_update_xr_seg_body<T, 3, DIST>(NL, NL, seg, nseg, x, r, cur, q, (T)alpha_d, hot);
+        acc = cg_update_xr_seg_body<T, 3, DIST>(NL, NL, seg, nseg, x, r, d, q, (T)alpha_d, hot);
         tick();
         if (DIST) ++seq1;
         const double rr = grid_allreduce(acc, partials, gs, DIST ? peers : nullptr, 1, false, seq1);
@@ -742,28 +714,95 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
         if (rr < tol2) done = 1;
         else if (iter >= max_iter || !(rr == rr)) done = 2;      // NaN: the reference would spin to max_iter
         if (done) break;
-        // K3 phase: d = r + beta d   (FOLD: deferred into the next K1 phase)
+        // K3 phase: d = r + beta d
         beta_d = delta / delta_old;
-        if (FOLD) {
-            have_beta = true;
-            tick();
-            tick();
-        } else {
-            cg_update_d_seg_body<T, 3>(NL, NL, seg, nseg, cur, r, (T)beta_d);
-            tick();
-            gs.sync();
-            tick();
-        }
-    }
-    if (FOLD) {
-        // leave the live search direction in the primary buffer: apply the pending update (iteration budget of this launch
-        // used up) or just move it (stopped: the reference breaks before updating d)
-        const bool pending = have_beta && !done;
-        if (pending || cur != d) visc3d_fold_finish_body<T>(NL, seg, nseg, d, cur, r, (T)beta_d, pending);
+        cg_update_d_seg_body<T, 3>(NL, NL, seg, nseg, d, r, (T)beta_d);
+        tick();
+        gs.sync();
+        tick();
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->delta = delta; st->delta_old = delta_old; st->dq = dq; st->alpha = alpha_d; st->beta = beta_d;
         st->iter = iter; st->done = done;
+        if (DIST) { peers->seq[0] = seq0; peers->seq[1] = seq1; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-reduction CG (see cg_sr_scalars in fs_common.cuh).  K1s: w = A r fused with BOTH dot products (r.r, w.r);
+// its tail computes alpha and beta on the device.  The update p, s, x, r follows in one fused pass (K2s,
+// cg_update_sr_seg_kernel).  Two kernels and ONE reduction per iteration instead of three and two; the persistent
+// form below has two grid barriers per iteration (one carrying the reduction) instead of three (two carrying one).
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot2_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ r, T* __restrict__ w,
+                                                                                        const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                                        CgState* st_, double* partials, PeerInfo* peers, PeerHot hot, int freeze) {
+    if (*(volatile int*)&st_->done) return;
+    bool wrote_peer = false;
+    double rr = 0.0;
+    const double wr = visc3d_apply_dot_body<T, DIST, false, true>(P, s, s2, r, w, seg, *nseg_p, hot, wrote_peer, &rr);
+    const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
+    grid_sum2_finish(rr, wr, partials, &st_->counter[0], [=](double gamma, double dl) {
+        if (freeze) return;                      // profiling hook: repeated launches leave the CG state alone
+        cg_sr_after_dots(st_, gamma, dl);
+    }, (DIST && !freeze) ? peers : nullptr, block_wrote_peer);
+}
+
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_sr_persistent_kernel(Visc3Dev<T> P, T s, T s2, T* x, T* r, T* p, T* sv, T* w,
+                                                                                     const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                                     CgState* st, double* partials, GridBar* bar, int n_slots,
+                                                                                     PeerInfo* peers, PeerHot hot, unsigned long long* prof) {
+    const int nseg = *nseg_p;
+    const long long NL = P.L.NL;
+    double delta = st->delta, gamma_old = st->delta_old, dl = st->dq, alpha_d = st->alpha, beta_d = st->beta;
+    bool first = st->sr_first != 0;
+    const double tol2 = st->tol2;
+    long long iter = st->iter;
+    const long long max_iter = st->max_iter;
+    int done = st->done;
+    GridSync gs{bar, 0u};
+    unsigned int seq0 = 0, seq1 = 0;
+    if (DIST) { seq0 = peers->seq[0]; seq1 = peers->seq[1]; }
+    const bool stamp = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    int np = 0;
+    auto tick = [&]() {
+        if (stamp && np < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); prof[np++] = t; }
+    };
+    for (int it = 0; it < n_slots && !done; ++it) {
+        tick();
+        // phase A: w = A r, (r.r, w.r)
+        bool wrote_peer = false;
+        double rr = 0.0;
+        double wr = visc3d_apply_dot_body<T, DIST, true, true>(P, s, s2, r, w, seg, nseg, hot, wrote_peer, &rr);
+        const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
+        tick();
+        if (DIST) { ++seq0; ++seq1; }
+        grid_allreduce2(rr, wr, partials, gs, DIST ? peers : nullptr, block_wrote_peer, seq0, seq1);
+        tick();
+        delta = rr;                               // r.r of the residual after `iter` updates
+        if (rr < tol2) done = 1;
+        else if (iter >= max_iter || !(rr == rr)) done = 2;
+        if (done) break;
+        dl = wr;
+        {
+            double a, b;
+            cg_sr_scalars(rr, wr, gamma_old, alpha_d, first, a, b);
+            alpha_d = a; beta_d = b;
+        }
+        gamma_old = rr;
+        first = false;
+        // phase B: p = r + beta p, s = w + beta s, x += alpha p, r -= alpha s   (halo rows included: they mirror the owner's)
+        cg_update_sr_seg_body<T, 3>(NL, NL, seg, nseg, x, r, p, sv, w, (T)alpha_d, (T)beta_d);
+        iter += 1;
+        tick();
+        gs.sync();
+        tick();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->delta = delta; st->delta_old = gamma_old; st->dq = dl; st->alpha = alpha_d; st->beta = beta_d;
+        st->iter = iter; st->done = done; st->sr_first = first ? 1 : 0;
         if (DIST) { peers->seq[0] = seq0; peers->seq[1] = seq1; }
     }
 }
@@ -782,14 +821,16 @@ struct fs_visc3d {
     char* ws;
     size_t ws_bytes;
     char* coef;      // [7][NL] T
+    char* coefs;     // [7][NL] T pre-scaled coefficients of the CG-loop apply (valid on the active segments and the slots their rows read)
     char* vecs;      // [5][3][NL] T
     uint8_t* mask;   // [3][NL]
     uint8_t* valid;  // [3][NL] extrapolation validity generations
     GridBar* bar;    // grid barrier of the persistent CG kernel
     ExtrapWork work; // extrapolation work lists
     uint8_t* rowflag; // [X*Y] lattice row holds a fluid face (written by pack, read by extrapolation sweep 1)
-    char* d2;        // [3][NL] second d buffer (folded persistent kernel); zero outside the active segments like r,d,q,b
-    int cg_mode;     // FS_CG_AUTO / FS_CG_KERNELS / FS_CG_PERSISTENT
+    char* d2;        // [3][NL] w = A r of the single-reduction CG; zero outside the active segments like r,d,q,b
+    int cg_mode;     // FS_CG_*
+    bool coop_failed; // a cooperative launch was refused on this context: use the stand-alone kernels from now on
     bool sparse_clean;   // r,d,q,b are zero outside the segments of the current active list (sparse begin / clear may be used)
     uint8_t* act;    // [NL] computed-row bits
     double* partials;
@@ -820,10 +861,11 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     L.sy = L.Zp; L.sx = (long long)L.Y * L.Zp; L.NL = L.sx * L.X;
     L.u_xhi = nx - 1;
     L.has_lo = 0; L.has_hi = 0;
+    L.wlo = 0; L.whi = nx; L.wcells = nx;
     return L;
 }
 
-struct Visc3Layout { size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
+struct Visc3Layout { size_t coefs; size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -850,10 +892,13 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     o.wcap = (3 * L.NL < 0xffffffffLL) ? (unsigned int)(L.NL / 2 + 1024) : 0u;
     o.wlist = p; p = align_up(p + (size_t)2 * o.wcap * sizeof(unsigned int), 256);
     o.wcount = p; p = align_up(p + 4 * sizeof(unsigned int), 256);
-    // second search-direction buffer of the folded persistent kernel (ping-pong), with the same guard bands as `vecs`
+    // w = A r buffer of the single-reduction CG, with the same guard bands as `vecs`
     p += guard;
     o.d2 = p; p = align_up(p + 3 * L.NL * esz, 256) + guard;
     o.rowflag = p; p = align_up(p + (size_t)L.X * L.Y, 256);
+    // pre-scaled coefficient planes of the CG-loop apply (same guard bands as `coef`: the branch-free K1 reads neighbours of discarded lanes)
+    p += guard;
+    o.coefs = p; p = align_up(p + 7 * L.NL * esz, 256) + guard;
     o.total = p;
     return o;
 }
@@ -862,6 +907,7 @@ template <typename T> static Visc3Dev<T> dev_view(const fs_visc3d* h) {
     Visc3Dev<T> P;
     P.L = h->L;
     for (int k = 0; k < 7; ++k) P.coef[k] = reinterpret_cast<const T*>(h->coef) + k * h->L.NL;
+    for (int k = 0; k < 7; ++k) P.cs[k] = reinterpret_cast<const T*>(h->coefs) + k * h->L.NL;
     for (int k = 0; k < 3; ++k) P.mask[k] = h->mask + k * h->L.NL;
     P.act = h->act;
     return P;
@@ -899,6 +945,7 @@ static int visc3d_halo_vec(fs_visc3d* h, int vec, cudaStream_t s) {
 extern "C" {
 
 static bool visc3d_use_persistent(const fs_visc3d* h);
+static bool visc3d_use_sr(const fs_visc3d* h);
 
 int fs_visc3d_set_slab(fs_visc3d* h, fs_comm* comm, int has_lo, int has_hi) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
@@ -931,14 +978,18 @@ int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int h
     if (h->has_lo) {
         Lat3 Ln = make_lat3(lo_nx, h->L.ny, h->L.nz);
         Visc3Layout ln = visc3_layout(Ln, esz);
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 3; ++c) {
             pi.q_lo[c] = (char*)lo_ws + ln.vecs + (((size_t)FS_VEC_Q * 3 + c) * Ln.NL + (size_t)(Ln.X - 2) * Ln.sx) * esz;
+            h->hot.w_lo[c] = (char*)lo_ws + ln.d2 + ((size_t)c * Ln.NL + (size_t)(Ln.X - 2) * Ln.sx) * esz;
+        }
     }
     if (h->has_hi) {
         Lat3 Ln = make_lat3(hi_nx, h->L.ny, h->L.nz);
         Visc3Layout ln = visc3_layout(Ln, esz);
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 3; ++c) {
             pi.q_hi[c] = (char*)hi_ws + ln.vecs + (((size_t)FS_VEC_Q * 3 + c) * Ln.NL) * esz;
+            h->hot.w_hi[c] = (char*)hi_ws + ln.d2 + ((size_t)c * Ln.NL) * esz;
+        }
     }
     pi.comp_len = h->L.NL;
     pi.halo_lo_end = h->has_lo ? h->L.sx : 0;
@@ -974,9 +1025,10 @@ int fs_visc3d_peer_error(fs_visc3d* h) {
 
 int fs_visc3d_set_cg_mode(fs_visc3d* h, int mode) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
-    if (mode != FS_CG_AUTO && mode != FS_CG_KERNELS && mode != FS_CG_PERSISTENT && mode != FS_CG_PERSISTENT_FOLD)
+    if (mode != FS_CG_AUTO && mode != FS_CG_KERNELS && mode != FS_CG_PERSISTENT && mode != FS_CG_KERNELS_SR && mode != FS_CG_PERSISTENT_SR)
         return fail(FS_ERR_ARG, "fs_visc3d_set_cg_mode: bad mode");
     h->cg_mode = mode;
+    h->graph.valid = false;
     return FS_OK;
 }
 
@@ -984,6 +1036,7 @@ int fs_visc3d_cg_mode_in_use(fs_visc3d* h) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_cg_mode_in_use before fs_visc3d_pack");
     FS_TRY(h->seg.finish());
+    if (visc3d_use_sr(h)) return visc3d_use_persistent(h) ? FS_CG_PERSISTENT_SR : FS_CG_KERNELS_SR;
     return visc3d_use_persistent(h) ? FS_CG_PERSISTENT : FS_CG_KERNELS;
 }
 
@@ -1045,7 +1098,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     Visc3Layout lay = visc3_layout(h->L, h->esz);
     if (ws_bytes < lay.total) { delete h; return fail(FS_ERR_ARG, "fs_visc3d_create: workspace too small"); }
     h->ws = (char*)ws; h->ws_bytes = ws_bytes;
-    h->coef = h->ws + lay.coef; h->vecs = h->ws + lay.vecs;
+    h->coef = h->ws + lay.coef; h->vecs = h->ws + lay.vecs; h->coefs = h->ws + lay.coefs;
     h->mask = (uint8_t*)(h->ws + lay.mask); h->valid = (uint8_t*)(h->ws + lay.valid); h->act = (uint8_t*)(h->ws + lay.act);
     h->partials = (double*)(h->ws + lay.partials); h->st = (CgState*)(h->ws + lay.st);
     h->bar = (GridBar*)(h->ws + lay.bar);
@@ -1060,6 +1113,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->work.list[1] = h->work.list[0] + lay.wcap;
     h->work.count = (unsigned int*)(h->ws + lay.wcount);
     h->cg_mode = FS_CG_AUTO;
+    h->coop_failed = false;
     h->sparse_clean = true;          // the workspace is zeroed below and the list is empty
     h->grid_pts = lay.grid_pts;
     h->packed = false;
@@ -1117,7 +1171,7 @@ int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double 
         FS_CUDA(cudaMemsetAsync(h->d2, 0, (size_t)3 * h->L.NL * h->esz, s));
         h->sparse_clean = true;
     }
-    FS_DISPATCH(h, visc3d_pack_kernel<T><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act, h->rowflag,
+    FS_DISPATCH(h, visc3d_pack_kernel<T><<<(h->L.whi - h->L.wlo + 1) * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act, h->rowflag,
                                                                                       h->active_mode == FS_ACTIVE_NONZERO ? 1 : 0));
     FS_LAUNCH_CHECK();
     FS_TRY(h->seg.enqueue(h->act, s));    // the list length (read back asynchronously) sizes the CG launches: see visc3d_list_ready
@@ -1132,9 +1186,9 @@ int fs_visc3d_load(fs_visc3d* h, int vec, const void* vx, const void* vy, const 
     if (vec != FS_VEC_X) h->sparse_clean = false;
     cudaStream_t s = (cudaStream_t)stream;
     if (src_dtype == FS_F32) {
-        FS_DISPATCH(h, visc3d_load_kernel<T, float><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, (const float*)vx, (const float*)vy, (const float*)vz, vec_ptr<T>(h, vec)));
+        FS_DISPATCH(h, visc3d_load_kernel<T, float><<<(h->L.whi - h->L.wlo + 1) * h->L.Y, row_block(h->L), 0, s>>>(h->L, (const float*)vx, (const float*)vy, (const float*)vz, vec_ptr<T>(h, vec)));
     } else if (src_dtype == FS_F64) {
-        FS_DISPATCH(h, visc3d_load_kernel<T, double><<<h->L.X * h->L.Y, row_block(h->L), 0, s>>>(h->L, (const double*)vx, (const double*)vy, (const double*)vz, vec_ptr<T>(h, vec)));
+        FS_DISPATCH(h, visc3d_load_kernel<T, double><<<(h->L.whi - h->L.wlo + 1) * h->L.Y, row_block(h->L), 0, s>>>(h->L, (const double*)vx, (const double*)vy, (const double*)vz, vec_ptr<T>(h, vec)));
     } else return fail(FS_ERR_ARG, "fs_visc3d_load: bad dtype");
     FS_LAUNCH_CHECK();
     return FS_OK;
@@ -1164,25 +1218,33 @@ int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
     if (vec != FS_VEC_X) h->sparse_clean = false;
     cudaStream_t s = (cudaStream_t)stream;
     const long long NL3 = 3 * h->L.NL;
-    FS_CUDA(cudaMemcpyAsync(h->valid, h->mask, NL3, cudaMemcpyDeviceToDevice, s));   // generation 1 = (sphi >= 0)  (:479-481)
+    // x-planes swept: the whole lattice, or — windowed inputs — the window minus its edge planes (a sweep reads x+-1)
+    const Lat3& L = h->L;
+    const int p_lo = L.wlo > 0 ? L.wlo + 1 : 0, p_hi = L.whi < L.nx ? L.whi - 1 : L.nx;
+    if (p_hi < p_lo) return FS_OK;
+    for (int c = 0; c < 3; ++c)                                                           // generation 1 = (sphi >= 0)  (:479-481)
+        FS_CUDA(cudaMemcpyAsync(h->valid + c * L.NL + (size_t)L.wlo * L.sx, h->mask + c * L.NL + (size_t)L.wlo * L.sx,
+                                (size_t)(L.whi - L.wlo + 1) * L.sx, cudaMemcpyDeviceToDevice, s));
+    (void)NL3;
     // single GPU: sweep 1 is a full pass that records what it filled, later sweeps only look around those faces.
     // Multi-GPU slabs always run full passes (the neighbours' fills arrive through the halo exchange, not the list).
     ExtrapWork W = h->work;
     if (h->comm) W.cap = 0u;
     if (W.cap) FS_CUDA(cudaMemsetAsync(W.count, 0, 4 * sizeof(unsigned int), s));
-    const int full_grid = (int)((h->L.NL / 4 + kThreads - 1) / kThreads);
+    const long long g_begin = (long long)p_lo * L.sx / 4, g_end = (long long)(p_hi + 1) * L.sx / 4;
+    const int full_grid = (int)((g_end - g_begin + kThreads - 1) / kThreads);
     for (int k = 1; k <= sweeps; ++k) {
         const int push_to = (W.cap && k < sweeps) ? ((k - 1) & 1) : -1;
         if (k == 1 || !W.cap) {
             FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<full_grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, push_to, 0,
-                                                                                       k == 1 ? h->rowflag : nullptr));
+                                                                                       k == 1 ? h->rowflag : nullptr, g_begin, g_end));
             FS_LAUNCH_CHECK();
         } else {
             const int from = (k - 2) & 1;
             if (push_to >= 0) FS_CUDA(cudaMemsetAsync(W.count + push_to, 0, sizeof(unsigned int), s));
             FS_DISPATCH(h, visc3d_extrapolate_list_kernel<T><<<kSMs * 4, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, from, push_to));
             FS_LAUNCH_CHECK();
-            FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<kSMs * 8, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, -1, 1, nullptr));   // only if a list overflowed
+            FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<kSMs * 8, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, -1, 1, nullptr, g_begin, g_end));   // only if a list overflowed
             FS_LAUNCH_CHECK();
         }
         if (h->comm) {   // the sweep is Jacobi over the GLOBAL grid: refresh the halo planes of the new values and generations
@@ -1237,8 +1299,48 @@ static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
     FS_DISPATCH(h, FS_TRY((cg_launch_update_d_seg<T, 3>(h->L.NL, h->L.NL, h->seg, vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, s))));
     return FS_OK;
 }
+// single-reduction CG: K1s (w = A r, r.r, w.r, alpha/beta on the device) and K2s (p, s, x, r in one pass)
+static int visc3d_k1s(fs_visc3d* h, double sm, cudaStream_t s, int freeze = 0) {
+    const int cap = kSMs * (h->dtype == FS_F32 ? K1Occ<float>::value : K1Occ<double>::value);
+    const int grid = seg_grid(h->seg.nseg, kK1SegsPerBlock, cap);
+    if (h->peers) {
+        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, h->peers, h->hot, freeze));
+    } else {
+        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot, freeze));
+    }
+    FS_LAUNCH_CHECK();
+    return FS_OK;
+}
+static int visc3d_k2s(fs_visc3d* h, cudaStream_t s, int freeze = 0) {
+    const int grid = seg_grid(h->seg.nseg, kSegsPerVecBlock, kVecGrid);
+    FS_DISPATCH(h, cg_update_sr_seg_kernel<T, 3><<<grid, kVecThreads, 0, s>>>(h->L.NL, h->L.NL, h->seg.list, h->seg.nseg_dev, vec_ptr<T>(h, FS_VEC_X), vec_ptr<T>(h, FS_VEC_R),
+                                                                              vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_Q), reinterpret_cast<const T*>(h->d2), h->st, freeze));
+    FS_LAUNCH_CHECK();
+    return FS_OK;
+}
+
+// Which CG recurrence runs: the single-reduction form (default) or the reference's two-reduction loop
+// (FS_CG_KERNELS / FS_CG_PERSISTENT, and always with the NCCL transport, whose collectives are host-launched).
+static bool visc3d_use_sr(const fs_visc3d* h) {
+    if (h->comm && !h->peers) return false;
+    if (h->cg_mode == FS_CG_KERNELS || h->cg_mode == FS_CG_PERSISTENT) return false;
+    if (h->cg_mode == FS_CG_KERNELS_SR || h->cg_mode == FS_CG_PERSISTENT_SR) return true;
+    static int mode = -2;
+    if (mode == -2) {
+        const char* e = getenv("FLUIDSOLVER_B200_SR");
+        mode = !e ? -1 : (e[0] == '0' ? 0 : 1);
+    }
+    return mode != 0;
+}
 
 static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
+    if (visc3d_use_sr(h)) {
+        // one reduction per iteration; multi-GPU (fused transport): K1s pushes its boundary w rows into the neighbours and
+        // all-reduces both scalars in its tail, K2s keeps the mirrored halo rows of p, s, x, r current.  No other traffic.
+        FS_TRY(visc3d_k1s(h, sm, s));
+        FS_TRY(visc3d_k2s(h, s));
+        return FS_OK;
+    }
     if (h->peers) {
         // fused path: K1 pushes its boundary q planes into the neighbours and all-reduces d.q in its tail; K2 updates the
         // halo rows of r with them and all-reduces r.r in its tail; K3 keeps the halo rows of d current.  No other traffic.
@@ -1263,11 +1365,13 @@ static int visc3d_iteration(fs_visc3d* h, double sm, cudaStream_t s) {
 // NCCL calls are not captured: graphs are used on a single GPU and with the fused peer-memory transport only
 // Persistent whole-iteration kernel: used when the per-iteration work is small enough that launch gaps and kernel
 // ramp-up/tails matter (FLUIDSOLVER_B200_PERSISTENT=0/1 forces it off/on; default: CG working set <= 256 MB).
-// Not with the NCCL transport (host-launched collectives between the phases).
+// Not with the NCCL transport (host-launched collectives between the phases), and not on a context that cannot hold
+// the cooperative grid (MPS / green contexts: the launch failed once -> the stand-alone kernels take over).
 static bool visc3d_use_persistent(const fs_visc3d* h) {
     if (h->comm && !h->peers) return false;
-    if (h->cg_mode == FS_CG_KERNELS) return false;
-    if (h->cg_mode == FS_CG_PERSISTENT || h->cg_mode == FS_CG_PERSISTENT_FOLD) return true;
+    if (h->coop_failed) return false;
+    if (h->cg_mode == FS_CG_KERNELS || h->cg_mode == FS_CG_KERNELS_SR) return false;
+    if (h->cg_mode == FS_CG_PERSISTENT || h->cg_mode == FS_CG_PERSISTENT_SR) return true;
     static int mode = -2;
     if (mode == -2) {
         const char* e = getenv("FLUIDSOLVER_B200_PERSISTENT");
@@ -1278,17 +1382,17 @@ static bool visc3d_use_persistent(const fs_visc3d* h) {
     return ws <= 256e6;
 }
 
+// `n` = iteration slots (classic: iterations; single-reduction: an extra closing slot evaluates r.r of the last iterate)
 static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
-    int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, kSMs);
-    if (const char* e = getenv("FLUIDSOLVER_B200_PERSIST_GRID")) { const int g = atoi(e); if (g >= 1 && g <= kSMs) grid = g; }
+    const bool sr = visc3d_use_sr(h);
+    const void* fn = nullptr;
+    FS_DISPATCH(h, fn = sr ? (h->peers ? (const void*)visc3d_cg_sr_persistent_kernel<T, true> : (const void*)visc3d_cg_sr_persistent_kernel<T, false>)
+                           : (h->peers ? (const void*)visc3d_cg_persistent_kernel<T, true> : (const void*)visc3d_cg_persistent_kernel<T, false>));
+    const int cap = coop_max_blocks(fn, kPersistThreads);        // SMs of this context x resident CTAs per SM
+    if (cap < 1) { h->coop_failed = true; return 1; }
+    int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, cap < kSMs ? cap : kSMs);
+    if (const char* e = getenv("FLUIDSOLVER_B200_PERSIST_GRID")) { const int g = atoi(e); if (g >= 1 && g <= cap) grid = g; }
     unsigned long long* prof = getenv("FLUIDSOLVER_B200_PROFILE") ? reinterpret_cast<unsigned long long*>(h->valid) : nullptr;   // scratch between solves
-    // K3 folded into K1 (two grid barriers per iteration instead of three): FS_CG_PERSISTENT_FOLD, or FLUIDSOLVER_B200_FOLD=1/0
-    bool fold = h->cg_mode == FS_CG_PERSISTENT_FOLD;
-    if (h->cg_mode != FS_CG_PERSISTENT_FOLD && h->cg_mode != FS_CG_PERSISTENT) {
-        static int fold_env = -2;
-        if (fold_env == -2) { const char* e = getenv("FLUIDSOLVER_B200_FOLD"); fold_env = !e ? -1 : (e[0] == '0' ? 0 : 1); }
-        fold = fold_env >= 0 ? fold_env == 1 : kFoldByDefault;
-    }
     while (n > 0) {
         int ni = (int)(n < (1 << 20) ? n : (1 << 20));
         cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);     // arrival counter / flag count from zero in every launch
@@ -1297,15 +1401,19 @@ static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t 
             Visc3Dev<T> P = dev_view<T>(h);
             T sv = (T)sm, s2v = (T)(2 * sm);
             T* x = vec_ptr<T>(h, FS_VEC_X); T* r = vec_ptr<T>(h, FS_VEC_R); T* d = vec_ptr<T>(h, FS_VEC_D); T* q = vec_ptr<T>(h, FS_VEC_Q);
-            T* d2 = reinterpret_cast<T*>(h->d2);
+            T* w = reinterpret_cast<T*>(h->d2);
             const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
             CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
             PeerInfo* peers = h->peers; PeerHot hot = h->hot;
-            void* args[] = {&P, &sv, &s2v, &x, &r, &d, &q, &d2, &seg, &nsegp, &st, &partials, &bar, &ni, &peers, &hot, &prof};
-            const void* fn = fold ? (h->peers ? (const void*)visc3d_cg_persistent_kernel<T, true, true> : (const void*)visc3d_cg_persistent_kernel<T, false, true>)
-                                  : (h->peers ? (const void*)visc3d_cg_persistent_kernel<T, true, false> : (const void*)visc3d_cg_persistent_kernel<T, false, false>);
-            e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args, 0, s);
+            void* args_sr[] = {&P, &sv, &s2v, &x, &r, &d, &q, &w, &seg, &nsegp, &st, &partials, &bar, &ni, &peers, &hot, &prof};
+            void* args_cl[] = {&P, &sv, &s2v, &x, &r, &d, &q, &seg, &nsegp, &st, &partials, &bar, &ni, &peers, &hot, &prof};
+            e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), sr ? args_sr : args_cl, 0, s);
         });
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported) {
+            cudaGetLastError();                      // this context cannot run the cooperative grid: use the stand-alone kernels
+            h->coop_failed = true;
+            return 1;
+        }
         if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
         FS_LAUNCH_CHECK();
         n -= ni;
@@ -1314,23 +1422,37 @@ static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t 
 }
 
 static int visc3d_iterations(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
-    if (visc3d_use_persistent(h)) return visc3d_persistent(h, sm, n, s);
+    if (visc3d_use_persistent(h)) {
+        const int st = visc3d_persistent(h, sm, n, s);
+        if (st != 1) return st;                      // 1 = cooperative launch impossible here, nothing was enqueued
+    }
     const bool graph_ok = !(h->comm && !h->peers);
     return cg_enqueue_iterations(h->graph, graph_ok, sm, n, [&](cudaStream_t ss) { return visc3d_iteration(h, sm, ss); }, s, seg_level(h->seg.nseg));
+}
+
+// pre-scaled coefficients of the CG-loop apply for this solve's operator (scale*mu) on the current active list
+static int visc3d_scale(fs_visc3d* h, double sm, cudaStream_t s) {
+    const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 4);
+    FS_DISPATCH(h, visc3d_scale_kernel<T><<<grid, kThreads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), reinterpret_cast<T*>(h->coefs), h->seg.list, h->seg.nseg_dev));
+    FS_LAUNCH_CHECK();
+    return FS_OK;
 }
 
 // Start of a solve on the active set (fs_visc3d_solve): one kernel builds b, q = A x, d = r = b - q and delta0.
 static int visc3d_cg_begin_sparse(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, cudaStream_t s) {
     FS_TRY(h->seg.finish());                      // list length: enqueued by pack, needed from here on for the launch sizes
     const double sm = scale * mu;
+    FS_TRY(visc3d_scale(h, sm, s));
     cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, (h->comm && !h->peers) ? 1 : 0);
     FS_LAUNCH_CHECK();
     FS_CUDA(cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s));
-    if (h->peers) {   // belt and braces: the halo planes of q must read as zero until the neighbours store into them
+    if (h->peers) {   // belt and braces: the halo planes of q (and w) must read as zero until the neighbours store into them
         for (int c = 0; c < 3; ++c) {
-            char* comp = h->vecs + ((size_t)FS_VEC_Q * 3 + c) * h->L.NL * h->esz;
-            if (h->has_lo) FS_CUDA(cudaMemsetAsync(comp, 0, (size_t)h->L.sx * h->esz, s));
-            if (h->has_hi) FS_CUDA(cudaMemsetAsync(comp + (size_t)(h->L.X - 2) * h->L.sx * h->esz, 0, (size_t)h->L.sx * h->esz, s));
+            char* comps[2] = {h->vecs + ((size_t)FS_VEC_Q * 3 + c) * h->L.NL * h->esz, h->d2 + (size_t)c * h->L.NL * h->esz};
+            for (char* comp : comps) {
+                if (h->has_lo) FS_CUDA(cudaMemsetAsync(comp, 0, (size_t)h->L.sx * h->esz, s));
+                if (h->has_hi) FS_CUDA(cudaMemsetAsync(comp + (size_t)(h->L.X - 2) * h->L.sx * h->esz, 0, (size_t)h->L.sx * h->esz, s));
+            }
         }
     }
     const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 4);
@@ -1353,6 +1475,7 @@ static int visc3d_cg_begin_sparse(fs_visc3d* h, double scale, double mu, double 
 static int visc3d_cg_begin(fs_visc3d* h, double scale, double mu, double tol, int64_t max_iter, cudaStream_t s) {
     FS_TRY(h->seg.finish());
     const long long n = 3 * h->L.NL;
+    FS_TRY(visc3d_scale(h, scale * mu, s));
     cg_state_init_kernel<<<1, 1, 0, s>>>(h->st, tol * tol, (long long)max_iter, (h->comm && !h->peers) ? 1 : 0);
     FS_LAUNCH_CHECK();
     FS_TRY(visc3d_general(h, scale, mu, FS_VEC_X, FS_VEC_Q, ROW_APPLY, s));   // q = A x   (:575)
@@ -1386,7 +1509,8 @@ int fs_visc3d_cg(fs_visc3d* h, double scale, double mu, double tol, int64_t max_
     FS_CUDA(cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s));
     FS_TRY(visc3d_cg_begin(h, scale, mu, tol, max_iter, s));
     const double sm = scale * mu;
-    return cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter, stats, s,
+    // single-reduction CG: one extra slot whose apply evaluates r.r of the last iterate (and sets the final status)
+    return cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter + (visc3d_use_sr(h) ? 1 : 0), stats, s,
                     visc3d_use_persistent(h) ? kCgBatchPersistent : kCgBatch);
 }
 
@@ -1409,9 +1533,11 @@ int fs_visc3d_kernel_enqueue(fs_visc3d* h, int which, double scale, double mu, i
     const double sm = scale * mu;
     cg_state_unlimit_kernel<<<1, 1, 0, s>>>(h->st);
     FS_LAUNCH_CHECK();
+    const bool sr = visc3d_use_sr(h);
+    if (sr && which == 3) return fail(FS_ERR_ARG, "fs_visc3d_kernel_enqueue: the single-reduction CG has two kernels (1, 2)");
     for (int64_t k = 0; k < n; ++k) {
-        if (which == 1) FS_TRY(visc3d_k1(h, sm, s));
-        else if (which == 2) FS_TRY(visc3d_k2(h, s, 1));
+        if (which == 1) FS_TRY(sr ? visc3d_k1s(h, sm, s, 1) : visc3d_k1(h, sm, s));
+        else if (which == 2) FS_TRY(sr ? visc3d_k2s(h, s, 1) : visc3d_k2(h, s, 1));
         else FS_TRY(visc3d_k3(h, s));
     }
     return FS_OK;
@@ -1441,11 +1567,13 @@ int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_
     FS_TRY(fs_visc3d_load(h, FS_VEC_X, vx, vy, vz, vel_dtype, stream));         // :569-571
     FS_TRY(fs_visc3d_extrapolate(h, FS_VEC_X, 3, stream));                      // :573
     FS_TRY(visc3d_cg_begin_sparse(h, scale, mu, tol, max_iter, s));             // :574-587 on the active set
-    int status = cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter, stats, s,
-                          visc3d_use_persistent(h) ? kCgBatchPersistent : kCgBatch);   // :588-612
+    // :588-612 (single-reduction CG: one extra slot whose apply evaluates r.r of the last iterate and sets the final status)
+    int status = cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter + (visc3d_use_sr(h) ? 1 : 0), stats, s,
+                          visc3d_use_persistent(h) ? kCgBatchPersistent : kCgBatch);
     if (status != FS_OK) return status;                                         // the reference raises before write-back
-    if (h->dtype == FS_F64 || vel_dtype == FS_F32) {
-        // :613 — only rows of the active set can differ from what was loaded from these very arrays
+    {
+        // :613 — only rows of the active set can differ from what was loaded from these very arrays; every other fluid face
+        // keeps the caller's value untouched (also when the solver stores fp32 and the caller fp64)
         const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 4);
         if (vel_dtype == FS_F32) {
             FS_DISPATCH(h, visc3d_store_active_kernel<T, float><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (float*)vx, (float*)vy, (float*)vz));
@@ -1453,8 +1581,6 @@ int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_
             FS_DISPATCH(h, visc3d_store_active_kernel<T, double><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (double*)vx, (double*)vy, (double*)vz));
         }
         FS_LAUNCH_CHECK();
-    } else {   // fp32 solver storage with fp64 caller arrays: every fluid face is rounded through fp32, as before
-        FS_TRY(fs_visc3d_store(h, FS_VEC_X, vx, vy, vz, vel_dtype, FS_STORE_FLUID, stream));
     }
     FS_CUDA(cudaStreamSynchronize(s));
     return FS_OK;

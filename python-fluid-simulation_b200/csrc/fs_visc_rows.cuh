@@ -96,4 +96,36 @@ __device__ __forceinline__ T visc_row(const T* const* __restrict__ coef, long lo
     return val;
 }
 
+// CG-loop row on PRE-SCALED coefficients (visc3d_scale_kernel, once per solve): plane A (A < D) holds the row's diagonal
+// diag_A = V_A + scale*mu*(2 hi_A + 2 lo_A + sum of the other axes' hi + lo), plane D holds 2*scale*mu*Vc and planes
+// D+a+b hold scale*mu*E_ab, i.e. exactly the products (c*vol) the reference forms first in every term (`2*scale*mu*vol*v`),
+// so a row is one multiply and 14 fused multiply-adds instead of ~30 fp64 operations — what takes the operator apply off
+// the fp64 pipe (64 lanes per clock per SM on B200) and back onto the memory system.  Inside the loop d is zero on every
+// row that is not computed, so no neighbour masks (SURVEY A-1).
+template <typename T, int D, int A, class NB>
+__device__ __forceinline__ T visc_row_scaled(const T* const* __restrict__ cs, long long i, const long long* st, T diag, T own, NB nb) {
+    T val = diag * own;
+#pragma unroll
+    for (int ax = 0; ax < D; ++ax) {
+        T hi, lo;
+        if (ax == A) {
+            hi = __ldg(cs[D] + i);
+            lo = __ldg(cs[D] + i - st[A]);
+        } else {
+            const T* E = cs[D + A + ax];
+            hi = __ldg(E + i + st[ax]);
+            lo = __ldg(E + i);
+        }
+        val -= hi * nb(A, i + st[ax]);
+        val -= lo * nb(A, i - st[ax]);
+        if (ax != A) {                       // cross-component terms of component B = ax
+            val -= hi * nb(ax, i + st[ax]);
+            val += hi * nb(ax, i + st[ax] - st[A]);
+            val += lo * nb(ax, i);
+            val -= lo * nb(ax, i - st[A]);
+        }
+    }
+    return val;
+}
+
 }  // namespace fs

@@ -101,11 +101,13 @@ class _Engine:
         if code is None:
             raise ValueError("active_set must be 'nonzero' or 'fluid'")
         N.check(self.lib.fs_visc3d_set_active_mode(self.h, code), "fs_visc3d_set_active_mode")
+        self.active_mode_name = mode
 
     def set_cg_mode(self, mode):
-        code = {"auto": N.CG_AUTO, "kernels": N.CG_KERNELS, "persistent": N.CG_PERSISTENT, "persistent_fold": N.CG_PERSISTENT_FOLD}.get(mode)
+        code = {"auto": N.CG_AUTO, "kernels": N.CG_KERNELS, "persistent": N.CG_PERSISTENT, "kernels_sr": N.CG_KERNELS_SR,
+                "persistent_sr": N.CG_PERSISTENT_SR}.get(mode)
         if code is None:
-            raise ValueError("cg_mode must be 'auto', 'kernels', 'persistent' or 'persistent_fold'")
+            raise ValueError("cg_mode must be 'auto', 'kernels', 'persistent', 'kernels_sr' or 'persistent_sr'")
         N.check(self.lib.fs_visc3d_set_cg_mode(self.h, code), "fs_visc3d_set_cg_mode")
 
     def active_info(self):
@@ -217,9 +219,11 @@ class ViscosityCGSolver3D:
 
     def __init__(self, gres, bound_size, dtype=torch.float64, active_set="nonzero", cg_mode="auto"):
         """``active_set`` (extra, not in the reference): which rows the CG kernels visit — "nonzero" (default; rows
-        with at least one non-zero coefficient) or "fluid" (every row the reference computes).  ``cg_mode``: "auto",
-        "kernels" (three kernels per iteration from a CUDA graph) or "persistent" (one cooperative launch runs whole
-        iterations).  Results are identical up to reduction-order rounding."""
+        with at least one non-zero coefficient) or "fluid" (every row the reference computes).  ``cg_mode``: "auto"
+        (single-reduction CG; persistent kernel for small working sets, stand-alone kernels otherwise), "kernels" /
+        "persistent" (the reference's two-reduction recurrence as three kernels per iteration from a CUDA graph / as one
+        cooperative launch) or "kernels_sr" / "persistent_sr" (the single-reduction form, explicitly).  Results are
+        identical up to rounding."""
         self.gres = gres
         self._g = A.to_host_ints(gres)
         if len(self._g) != 3:

@@ -16,7 +16,7 @@ FS_F64 = 1
 VEC_X, VEC_R, VEC_D, VEC_Q, VEC_B = range(5)
 STORE_ALL, STORE_INTERIOR, STORE_FLUID = range(3)
 ACTIVE_FLUID, ACTIVE_NONZERO = range(2)
-CG_AUTO, CG_KERNELS, CG_PERSISTENT, CG_PERSISTENT_FOLD = range(4)
+CG_AUTO, CG_KERNELS, CG_PERSISTENT, CG_KERNELS_SR, CG_PERSISTENT_SR = range(5)
 OP_PRESSURE, OP_DENSITY = range(2)
 
 

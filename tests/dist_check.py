@@ -27,7 +27,8 @@ def main():
     cases = [(24, 10.0, torch.float64, None, "nccl", "auto", "nonzero"), (24, 10.0, torch.float64, None, "p2p", "persistent", "nonzero"),
              (24, 10.0, torch.float64, None, "p2p", "kernels", "fluid"),
              (32, 100.0, torch.float64, (37, 24, 28), "p2p", "persistent", "fluid"), (32, 100.0, torch.float64, (37, 24, 28), "p2p", "kernels", "nonzero"),
-             (32, 100.0, torch.float32, None, "p2p", "auto", "nonzero"), (32, 100.0, torch.float64, (37, 24, 28), "p2p", "persistent_fold", "nonzero"),
+             (32, 100.0, torch.float32, None, "p2p", "auto", "nonzero"), (32, 100.0, torch.float64, (37, 24, 28), "p2p", "persistent_sr", "nonzero"),
+             (32, 100.0, torch.float64, (37, 24, 28), "p2p", "kernels_sr", "fluid"),
              (32, 100.0, torch.float64, (37, 24, 28), "nccl", "auto", "fluid")]
     for N, mu, dtype, g, transport, cg_mode, aset in cases:
         full = scenes.buckling(N, device="cuda", mu=mu, gres=g)

@@ -117,15 +117,15 @@ def test_active_set_changes_between_solves():
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_persistent_kernel_matches_three_kernel_path(dtype):
-    """cg_mode="persistent" (one cooperative launch, grid barriers) and cg_mode="kernels" (K1/K2/K3 from a CUDA graph)
-    run the same arithmetic: same iteration count up to reduction-order rounding, same velocities, on both active-set
+    """cg_mode="persistent" (one cooperative launch, grid barriers), cg_mode="kernels" (K1/K2/K3 from a CUDA graph) and the
+    single-reduction forms ("kernels_sr", "persistent_sr"; "auto" resolves to one of them) run the same iteration: same iteration count up to reduction-order rounding, same velocities, on both active-set
     modes, and on a grid large enough for several segments per warp."""
     import scenes
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
     sc = scenes.buckling(48, device="cuda", mu=100.0)
     out = {}
     for aset in ("nonzero", "fluid"):
-        for mode in ("kernels", "persistent", "persistent_fold"):
+        for mode in ("kernels", "persistent", "kernels_sr", "persistent_sr", "auto"):
             s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], dtype=dtype, active_set=aset, cg_mode=mode)
             v = [sc[k].clone() for k in ("vx", "vy", "vz")]
             s.solve(sc["dt"], 100.0, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"])
@@ -143,8 +143,8 @@ def test_fixed_window_persistent_counts_iterations():
     import scenes
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
     sc = scenes.buckling(32, device="cuda", mu=100.0)
-    d_after = {}
-    for mode in ("kernels", "persistent", "persistent_fold"):
+    d_after, x_after, deltas = {}, {}, {}
+    for mode in ("kernels", "persistent", "kernels_sr", "persistent_sr", "auto"):
         s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], cg_mode=mode)
         s.max_iter = 150
         v = [sc[k].clone() for k in ("vx", "vy", "vz")]
@@ -152,10 +152,18 @@ def test_fixed_window_persistent_counts_iterations():
             s.solve(sc["dt"], 100.0, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"], tol=0.0)
         assert s.iterations == 150
         d_after[mode] = [a.clone() for a in (s.d_x, s.d_y, s.d_z)]
-    # the live search direction ends up in the primary buffer whichever way the launches were cut (150 = 64 + 64 + 22)
-    for mode in ("persistent", "persistent_fold"):
+        x_after[mode] = [a.clone() for a in (s.x_x, s.x_y, s.x_z)]
+        deltas[mode] = s.delta
+    # the live search direction ends up in the primary buffer whichever way the launches were cut (150 = 64 + 64 + 22);
+    # in the single-reduction forms d holds p_k, the direction the last update used, while the reference's loop has already
+    # formed d_{k+1} = r + beta d_k — compare those through x instead
+    for mode in ("persistent",):
         for a, b in zip(d_after[mode], d_after["kernels"]):
             assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 1e-3, mode
+    for mode in x_after:
+        assert abs(deltas[mode] - deltas["kernels"]) <= 1e-3 * deltas["kernels"], (mode, deltas)
+        for a, b in zip(x_after[mode], x_after["kernels"]):
+            assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 1e-6, mode
 
 
 @pytest.mark.parametrize("cap", ["0", "7", None])

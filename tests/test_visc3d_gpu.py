@@ -76,11 +76,12 @@ def test_extrapolate_and_writeback_vs_reference(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cg_mode", ["auto", "kernels"])
 @pytest.mark.parametrize("tag", ["visc3d_solve_8x10x8", "visc3d_solve_stiff_6x8x6"])
-def test_solve_vs_reference(tag, dtype):
+def test_solve_vs_reference(tag, cg_mode, dtype):
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
     f = load_golden(tag)
-    s = ViscosityCGSolver3D(f["gres"], f["bound_size"], dtype=dtype)
+    s = ViscosityCGSolver3D(f["gres"], f["bound_size"], dtype=dtype, cg_mode=cg_mode)
     assert s.cell_vol == float(f["cell_vol"])
     v = [_dev(f[k]) for k in ("vx", "vy", "vz")]          # fp32, as the notebook passes them
     sv = torch.zeros(tuple(f["sphi"].shape) + (3,), dtype=torch.float64, device="cuda")
@@ -104,7 +105,10 @@ def test_solve_vs_reference(tag, dtype):
     # NOTE: a 1e-15 relative perturbation of a single dot product moves the converged solution of this system by
     # ~2e-6 relative (measured with the oracle), so 1e-4 is the meaningful bar even for the fp64 path; the CG
     # trajectory is only reproducible to reduction-order rounding (SURVEY §8c "Third-party arithmetic").
-    if dtype == torch.float64:
+    # The reference's own two-reduction recurrence ("kernels") lands within ONE iteration of the reference on these tiny,
+    # ill-conditioned systems (95 iterations for ~700 unknowns); the default single-reduction form ("auto") computes alpha
+    # from (r.r, w.r) instead of d.q and lands within the +-2 % bar (97 vs 95 on the stiff fixture, measured on B200).
+    if dtype == torch.float64 and cg_mode == "kernels":
         assert abs(s.iterations - it_ref) <= 1
 
 
@@ -127,6 +131,22 @@ def test_solve_vs_oracle_buckling(N, mu, dtype):
     assert abs(s.iterations - it_ref) <= max(1, round(0.02 * it_ref)), (s.iterations, it_ref)
     for a, b in zip(v, rv):
         assert rel_l2(a.cpu().numpy(), b) < 1e-4
+
+
+def test_nan_volume_fails_to_converge_like_reference():
+    """A NaN face volume on a computed row propagates (the reference's residual goes NaN and the loop never converges);
+    here the solve reports it at once with the same ValueError instead of silently dropping the row."""
+    import scenes
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    sc = scenes.buckling(16, device="cuda", mu=1.0)
+    lvol = sc["lvol"].clone()
+    nz = torch.nonzero(lvol[2:-2:2, 3:-3:2, 3:-3:2])          # a u-face node (even, odd, odd) with liquid
+    i, j, k = (int(v) for v in nz[len(nz) // 2])
+    lvol[2 + 2 * i, 3 + 2 * j, 3 + 2 * k] = float("nan")
+    s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
+    v = [sc[n].clone() for n in ("vx", "vy", "vz")]
+    with pytest.raises(ValueError, match="Failed to converge!"):
+        s.solve(sc["dt"], 1.0, sc["rho"], *v, sc["sphi"], None, None, lvol)
 
 
 def test_fixed_iterations_raise_like_reference():
