@@ -190,6 +190,37 @@ int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int h
 int fs_visc3d_peer_error(fs_visc3d* h);
 
 /* ------------------------------------------------------------------------------------------
+ * Gathered multi-GPU solve — for active sets small enough to live in one GPU's L2 (the benchmark scene: 0.45 % of the
+ * rows).  Splitting such a CG across GPUs only adds NVLink latency to every iteration, so here the once-per-solve passes
+ * are sharded instead: every rank builds a handle for the GLOBAL grid, declares the x-window of cells its input arrays
+ * cover (fs_visc3d_set_window: owned cells extended by 4 = sweeps + 1 towards each neighbour), packs / loads /
+ * extrapolates only that window, and publishes one record per lattice segment the CG will touch on the planes it owns
+ * (fs_visc3d_gather_export).  The host program all-gathers the records (torch.distributed / NCCL), every rank scatters
+ * its peers' records into its lattice (fs_visc3d_gather_import) and runs the whole CG locally — no traffic between the
+ * GPUs inside the iteration — then writes the rows of its own planes back (fs_visc3d_solve_packed).  Also usable on one
+ * GPU to pack a host upload chunk by chunk.
+ * ---------------------------------------------------------------------------------------- */
+/* The caller's arrays hold the cells [cell_lo, cell_hi) only: vx has cell_hi-cell_lo+1 x-planes, vy/vz cell_hi-cell_lo,
+ * sphi/lvol the fine planes 2*cell_lo .. 2*cell_hi.  (0, nx) restores whole-grid inputs. */
+int fs_visc3d_set_window(fs_visc3d* h, int cell_lo, int cell_hi);
+size_t fs_visc3d_gather_record_bytes(const fs_visc3d* h);
+/* pack + load + 3-sweep extrapolation of the window, then one record per segment that holds a computed row of the
+ * lattice planes [own_lo, own_hi) or is read by such a row's stencil.  *count = records written (<= cap).  Blocks. */
+int fs_visc3d_gather_export(fs_visc3d* h, const void* vx_dev, const void* vy_dev, const void* vz_dev, int vel_dtype,
+                            const double* sphi_dev, const double* lvol_dev, double vol_norm, int own_lo, int own_hi,
+                            void* records_dev, int64_t cap, int64_t* count, void* stream);
+/* *count > cap: nothing was written; grow the buffer and write the same records with this call */
+int fs_visc3d_gather_reexport(fs_visc3d* h, void* records_dev, int64_t cap, void* stream);
+/* records of rank r at records_dev + r*stride*record_bytes, counts_dev[r] of them (device array of nranks int64);
+ * block `skip_rank` (the local one) is not re-read.  Rebuilds the active list over the whole lattice. */
+int fs_visc3d_gather_import(fs_visc3d* h, const void* records_dev, const int64_t* counts_dev, int nranks, int64_t stride,
+                            int skip_rank, void* stream);
+/* RHS + CG on the packed lattice, write-back of the computed rows on planes [own_lo, own_hi) into the windowed arrays */
+int fs_visc3d_solve_packed(fs_visc3d* h, double dt, double mu, double rho, double cell_vol,
+                           void* vx_dev, void* vy_dev, void* vz_dev, int vel_dtype, int own_lo, int own_hi,
+                           double tol, int64_t max_iter, fs_cg_stats* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Viscosity, 2-D  (ViscosityCGSolver2D) — fluid test is sphi > 0, no extrapolation, tol 1e-4
  * lattice X=W+1, Y'=roundup(H+1,4); MAC faces u (W+1,H), v (W,H+1); fine grid (2W+1,2H+1)
  * ---------------------------------------------------------------------------------------- */

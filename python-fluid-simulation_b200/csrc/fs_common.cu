@@ -59,9 +59,14 @@ __global__ void cg_state_unlimit_kernel(CgState* st) {
 }
 
 // ---- active-segment list -------------------------------------------------------------------------------------
-__global__ void seg_count_kernel(const uint8_t* act, long long nseg_total, int* block_count) {
+__device__ __forceinline__ bool seg_listed(const uint8_t* __restrict__ act, long long s, long long nseg_total, int per_seg_flags) {
+    if (per_seg_flags) return s < nseg_total && act[s] != 0;
+    return seg_flag(act, s, nseg_total);
+}
+
+__global__ void seg_count_kernel(const uint8_t* act, long long nseg_total, int* block_count, int per_seg_flags) {
     const long long s = (long long)blockIdx.x * kSegBlock + threadIdx.x;
-    const int n = __syncthreads_count(seg_flag(act, s, nseg_total) ? 1 : 0);
+    const int n = __syncthreads_count(seg_listed(act, s, nseg_total, per_seg_flags) ? 1 : 0);
     if (threadIdx.x == 0) block_count[blockIdx.x] = n;
 }
 
@@ -102,10 +107,10 @@ __global__ void seg_scan_kernel(int* block_count, int nblocks, int* nseg_out) {
     if (threadIdx.x == 0) *nseg_out = carry;
 }
 
-__global__ void seg_write_kernel(const uint8_t* act, long long nseg_total, const int* block_off, int* list) {
+__global__ void seg_write_kernel(const uint8_t* act, long long nseg_total, const int* block_off, int* list, int per_seg_flags) {
     __shared__ int wsum[kSegBlock / 32];
     const long long s = (long long)blockIdx.x * kSegBlock + threadIdx.x;
-    const bool f = seg_flag(act, s, nseg_total);
+    const bool f = seg_listed(act, s, nseg_total, per_seg_flags);
     const unsigned int m = __ballot_sync(0xffffffffu, f);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) wsum[w] = __popc(m);
@@ -134,13 +139,13 @@ void SegList::destroy() {
     pending = false;
 }
 
-int SegList::enqueue(const uint8_t* act, cudaStream_t s) {
+int SegList::enqueue(const uint8_t* act, cudaStream_t s, int per_seg_flags) {
     if (!ready) FS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    seg_count_kernel<<<nblocks, kSegBlock, 0, s>>>(act, nseg_total, block_off);
+    seg_count_kernel<<<nblocks, kSegBlock, 0, s>>>(act, nseg_total, block_off, per_seg_flags);
     FS_LAUNCH_CHECK();
     seg_scan_kernel<<<1, 1024, 0, s>>>(block_off, nblocks, nseg_dev);
     FS_LAUNCH_CHECK();
-    seg_write_kernel<<<nblocks, kSegBlock, 0, s>>>(act, nseg_total, block_off, list);
+    seg_write_kernel<<<nblocks, kSegBlock, 0, s>>>(act, nseg_total, block_off, list, per_seg_flags);
     FS_LAUNCH_CHECK();
     FS_CUDA(cudaMemcpyAsync(nseg_pinned, nseg_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
     FS_CUDA(cudaEventRecord(ready, s));

@@ -462,10 +462,12 @@ __device__ __forceinline__ bool seg_flag(const uint8_t* __restrict__ act, long l
     return ((a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) & 0x77777777u) != 0u;
 }
 
-__global__ void seg_count_kernel(const uint8_t* act, long long nseg_total, int* block_count);
+// per_seg_flags = 0: `act` holds one activity byte per POINT (a segment is listed if any of its 32 bytes has a row bit);
+//               = 1: `act` holds one flag byte per SEGMENT (listed if non-zero)
+__global__ void seg_count_kernel(const uint8_t* act, long long nseg_total, int* block_count, int per_seg_flags);
 // exclusive scan of block_count[0..nblocks) in place; total -> *nseg_out
 __global__ void seg_scan_kernel(int* block_count, int nblocks, int* nseg_out);
-__global__ void seg_write_kernel(const uint8_t* act, long long nseg_total, const int* block_off, int* list);
+__global__ void seg_write_kernel(const uint8_t* act, long long nseg_total, const int* block_off, int* list, int per_seg_flags);
 
 struct SegList {
     int* list = nullptr;        // device: active segment ids, ascending
@@ -485,7 +487,7 @@ struct SegList {
     // act: one byte per point, readable up to 32*nseg_total bytes.  build() = enqueue() + finish().
     // enqueue() launches the three list kernels and the async read-back of the count; finish() blocks until the count
     // is on the host.  Independent work enqueued in between hides the host round trip.
-    int enqueue(const uint8_t* act, cudaStream_t s);
+    int enqueue(const uint8_t* act, cudaStream_t s, int per_seg_flags = 0);
     int finish();
     int build(const uint8_t* act, cudaStream_t s);
     cudaEvent_t ready = nullptr;

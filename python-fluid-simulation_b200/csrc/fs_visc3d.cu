@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(kThreads) visc3d_begin_kernel(Visc3Dev<T> P, T
 // zero r, d, q, b on the segments of the (previous) active list
 template <typename T>
 __global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T* __restrict__ vecs /*[5][3][NL]*/, T* __restrict__ d2 /*[3][NL]*/,
-                                                                const int* __restrict__ seg, const int* __restrict__ nseg_p) {
+                                                                const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                uint8_t* __restrict__ act_clear /*gathered mode: also forget the activity bits, else null*/) {
     const int nseg = *nseg_p;
     const int lane = threadIdx.x & 31;
     const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -480,6 +481,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T*
             for (int c = 0; c < 3; ++c) vecs[((long long)v * 3 + c) * NL + i] = T(0);
 #pragma unroll
         for (int c = 0; c < 3; ++c) d2[(long long)c * NL + i] = T(0);
+        if (act_clear) act_clear[i] = 0;
     }
 }
 
@@ -488,7 +490,8 @@ __global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T*
 template <typename T, typename S>
 __global__ void __launch_bounds__(kThreads) visc3d_store_active_kernel(Lat3 L, const T* __restrict__ vec, const uint8_t* __restrict__ act,
                                                                        const int* __restrict__ seg, const int* __restrict__ nseg_p,
-                                                                       S* __restrict__ a0, S* __restrict__ a1, S* __restrict__ a2) {
+                                                                       S* __restrict__ a0, S* __restrict__ a1, S* __restrict__ a2,
+                                                                       int own_lo, int own_hi /*x-planes [own_lo, own_hi) are written; the arrays start at plane L.wlo*/) {
     const int nseg = *nseg_p;
     const int lane = threadIdx.x & 31;
     const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -501,12 +504,13 @@ __global__ void __launch_bounds__(kThreads) visc3d_store_active_kernel(Lat3 L, c
         if (a == 0u) continue;
         int x, y, z;
         lat_decode(L, i, x, y, z);
+        if (x < own_lo || x >= own_hi) continue;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             if (!(a & (1u << c))) continue;
             int s0, s1, s2;
             comp_shape(L, c, s0, s1, s2);
-            dst[c][((long long)x * s1 + y) * s2 + z] = (S)vec[c * L.NL + i];
+            dst[c][((long long)(x - L.wlo) * s1 + y) * s2 + z] = (S)vec[c * L.NL + i];
         }
     }
 }
@@ -807,6 +811,85 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_sr_persistent_ke
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Gathered multi-GPU solve (L2-sized active sets): every rank packs / loads / extrapolates only its own x-window of the
+// GLOBAL lattice, then the ranks exchange just the lattice segments the CG touches — the active segments of the planes a
+// rank owns plus every segment their stencils read — and each rank runs the whole (small) CG locally, with no
+// per-iteration traffic between GPUs.  One record per published segment:
+//     [int32 segment id, 12 bytes pad][mask_u[32] mask_v[32] mask_w[32] act[32]][7 coefficient + 3 x values][32 points]
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t gather_record_bytes(size_t esz) { return 16 + 128 + 320 * esz; }
+
+// flags[t] = 1 for every segment t that holds a computed row of the owned planes, and for every segment such a row's
+// stencil can read (row offsets 0, +-sy, +-sx, +sx-sy, -sx+sy with z-shifts -1..+1)
+__global__ void __launch_bounds__(256) visc3d_mark_export_kernel(Lat3 L, const uint8_t* __restrict__ act, long long seg_lo, long long seg_hi,
+                                                                 long long nseg_total, uint8_t* __restrict__ flags) {
+    const long long sg = seg_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sg >= seg_hi || !seg_flag(act, sg, nseg_total)) return;
+    const long long off[7] = {0, L.sy, -L.sy, L.sx, -L.sx, L.sx - L.sy, L.sy - L.sx};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const long long lo = sg * kSegPts + off[k] - 1, hi = sg * kSegPts + off[k] + kSegPts;   // first / last point touched
+        long long t0 = lo < 0 ? 0 : lo / kSegPts, t1 = hi / kSegPts;
+        if (t1 >= nseg_total) t1 = nseg_total - 1;
+        for (long long t = t0; t <= t1; ++t) flags[t] = 1;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) visc3d_export_kernel(long long NL, const T* __restrict__ coef, const T* __restrict__ xv, const uint8_t* __restrict__ mask,
+                                                                 const uint8_t* __restrict__ act, const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                 long long cap, char* __restrict__ records) {
+    const long long nseg = *nseg_p < cap ? *nseg_p : cap;
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const size_t rb = gather_record_bytes(sizeof(T));
+    for (long long k = w0; k < nseg; k += nw) {
+        const int sg = __ldg(seg + k);
+        char* rec = records + (size_t)k * rb;
+        const long long i = (long long)sg * kSegPts + lane;
+        const bool in = i < NL;
+        if (lane == 0) *reinterpret_cast<int*>(rec) = sg;
+        uint8_t* bytes = reinterpret_cast<uint8_t*>(rec + 16);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) bytes[c * 32 + lane] = in ? mask[c * NL + i] : (uint8_t)0;
+        bytes[96 + lane] = in ? act[i] : (uint8_t)0;
+        T* vals = reinterpret_cast<T*>(rec + 16 + 128);
+#pragma unroll
+        for (int p = 0; p < 7; ++p) vals[p * 32 + lane] = in ? coef[p * NL + i] : T(0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vals[(7 + c) * 32 + lane] = in ? xv[c * NL + i] : T(0);
+    }
+}
+
+// records of rank r: [r*stride, r*stride + counts[r]); the local rank's own block is skipped (its lattice already holds the data)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) visc3d_import_kernel(long long NL, T* __restrict__ coef, T* __restrict__ xv, uint8_t* __restrict__ mask, uint8_t* __restrict__ act,
+                                                                 const char* __restrict__ records, const long long* __restrict__ counts, int nranks,
+                                                                 long long stride, int skip_rank) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const size_t rb = gather_record_bytes(sizeof(T));
+    for (long long k = w0; k < (long long)nranks * stride; k += nw) {
+        const int r = (int)(k / stride);
+        if (r == skip_rank || k - r * stride >= counts[r]) continue;
+        const char* rec = records + (size_t)k * rb;
+        const long long i = (long long)(*reinterpret_cast<const int*>(rec)) * kSegPts + lane;
+        if (i >= NL) continue;
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(rec + 16);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) mask[c * NL + i] = bytes[c * 32 + lane];
+        act[i] = bytes[96 + lane];
+        const T* vals = reinterpret_cast<const T*>(rec + 16 + 128);
+#pragma unroll
+        for (int p = 0; p < 7; ++p) coef[p * NL + i] = vals[p * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xv[c * NL + i] = vals[(7 + c) * 32 + lane];
+    }
+}
+
 }  // namespace fs
 
 // =================================================================================================
@@ -846,6 +929,10 @@ struct fs_visc3d {
     SegList seg;     // sorted list of active 32-point lattice segments (rebuilt by every pack)
     int active_mode; // FS_ACTIVE_*
     long long active_rows;   // computed rows of the last pack (host copy, filled lazily)
+    // gathered multi-GPU solve / windowed inputs
+    bool windowed;       // pack / load / extrapolation work on the x-window L.wlo..L.whi of the lattice only
+    uint8_t* xflags;     // [segments] publish flags of the current solve
+    SegList xseg;        // segments this rank publishes (built from xflags)
 };
 
 // threads of the one-block-per-lattice-row kernels: a whole number of warps covering the row once, at most 512
@@ -865,7 +952,7 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     return L;
 }
 
-struct Visc3Layout { size_t coefs; size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
+struct Visc3Layout { size_t coefs, xflags, xlist, xscratch; size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -899,6 +986,10 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     // pre-scaled coefficient planes of the CG-loop apply (same guard bands as `coef`: the branch-free K1 reads neighbours of discarded lanes)
     p += guard;
     o.coefs = p; p = align_up(p + 7 * L.NL * esz, 256) + guard;
+    // gathered multi-GPU solve: publish flags (one byte per segment) and the list built from them
+    o.xflags = p; p = align_up(p + (size_t)((L.NL + kSegPts - 1) / kSegPts) + 64, 256);
+    o.xlist = p; p = align_up(p + SegList::list_bytes(L.NL), 256);
+    o.xscratch = p; p = align_up(p + SegList::scratch_bytes(L.NL), 256);
     o.total = p;
     return o;
 }
@@ -1124,9 +1215,13 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     if (s < 0) { delete h; return s; }
     s = h->seg.init(h->L.NL, h->ws + lay.seglist, h->ws + lay.segscratch);
     if (s < 0) { h->cg.destroy(); delete h; return s; }
+    s = h->xseg.init(h->L.NL, h->ws + lay.xlist, h->ws + lay.xscratch);
+    if (s < 0) { h->cg.destroy(); h->seg.destroy(); delete h; return s; }
+    h->xflags = (uint8_t*)(h->ws + lay.xflags);
+    h->windowed = false;
     h->cg.st_dev = h->st; h->cg.partials_dev = h->partials;
     cudaError_t e = cudaMemset(ws, 0, lay.total);     // cp.zeros semantics for every solver vector
-    if (e != cudaSuccess) { h->cg.destroy(); h->seg.destroy(); delete h; return fail(FS_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { h->cg.destroy(); h->seg.destroy(); h->xseg.destroy(); delete h; return fail(FS_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
     *out = h;
     return FS_OK;
 }
@@ -1137,6 +1232,7 @@ void fs_visc3d_destroy(fs_visc3d* h) {
     h->graph.destroy();
     h->cg.destroy();
     h->seg.destroy();
+    h->xseg.destroy();
     delete h;
 }
 
@@ -1163,7 +1259,8 @@ int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double 
     if (h->sparse_clean) {
         if (h->seg.nseg > 0) {
             const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 8);
-            FS_DISPATCH(h, visc3d_clear_kernel<T><<<grid, kThreads, 0, s>>>(h->L.NL, reinterpret_cast<T*>(h->vecs), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev));
+            FS_DISPATCH(h, visc3d_clear_kernel<T><<<grid, kThreads, 0, s>>>(h->L.NL, reinterpret_cast<T*>(h->vecs), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev,
+                                                                            h->windowed ? h->act : nullptr));
             FS_LAUNCH_CHECK();
         }
     } else {
@@ -1325,6 +1422,9 @@ static bool visc3d_use_sr(const fs_visc3d* h) {
     if (h->comm && !h->peers) return false;
     if (h->cg_mode == FS_CG_KERNELS || h->cg_mode == FS_CG_PERSISTENT) return false;
     if (h->cg_mode == FS_CG_KERNELS_SR || h->cg_mode == FS_CG_PERSISTENT_SR) return true;
+    // fp32 STORAGE (opt-in) keeps the two-reduction recurrence by default: s = w + beta*s accumulates the fp32 rounding of
+    // A p over the iterations, and on the tiny stiff fixtures the velocities then miss the 1e-4 bar (1.02e-4 measured)
+    if (h->dtype == FS_F32) return false;
     static int mode = -2;
     if (mode == -2) {
         const char* e = getenv("FLUIDSOLVER_B200_SR");
@@ -1554,6 +1654,102 @@ int fs_visc3d_read_stats(fs_visc3d* h, fs_cg_stats* stats, void* stream) {
     return FS_OK;
 }
 
+int fs_visc3d_set_window(fs_visc3d* h, int cell_lo, int cell_hi) {
+    if (!h) return fail(FS_ERR_ARG, "null handle");
+    if (h->comm) return fail(FS_ERR_STATE, "fs_visc3d_set_window: not on a slab handle (fs_visc3d_set_slab)");
+    if (cell_lo < 0 || cell_hi > h->L.nx || cell_hi - cell_lo < 1) return fail(FS_ERR_ARG, "fs_visc3d_set_window: bad cell range");
+    h->L.wlo = cell_lo; h->L.whi = cell_hi; h->L.wcells = cell_hi;
+    h->windowed = !(cell_lo == 0 && cell_hi == h->L.nx);
+    h->packed = false;
+    return FS_OK;
+}
+
+size_t fs_visc3d_gather_record_bytes(const fs_visc3d* h) { return h ? gather_record_bytes(h->esz) : 0; }
+int fs_visc3d_gather_reexport(fs_visc3d* h, void* records, int64_t cap, void* stream);
+
+int fs_visc3d_gather_export(fs_visc3d* h, const void* vx, const void* vy, const void* vz, int vel_dtype, const double* sphi, const double* lvol,
+                            double vol_norm, int own_lo, int own_hi, void* records, int64_t cap, int64_t* count, void* stream) {
+    if (!h || !vx || !vy || !vz || !sphi || !lvol || !records || !count) return fail(FS_ERR_ARG, "fs_visc3d_gather_export: null argument");
+    if (h->comm) return fail(FS_ERR_STATE, "fs_visc3d_gather_export: not on a slab handle");
+    const Lat3& L = h->L;
+    if (own_lo < L.wlo || own_hi > L.whi + 1 || own_hi <= own_lo) return fail(FS_ERR_ARG, "fs_visc3d_gather_export: owned planes outside the window");
+    // clean results need (sweeps + 1) = 4 window planes beyond the owned ones wherever the window does not end at the grid boundary
+    if ((L.wlo > 0 && own_lo - L.wlo < 4) || (L.whi < L.nx && L.whi - own_hi < 4))
+        return fail(FS_ERR_ARG, "fs_visc3d_gather_export: the window must extend 4 cells beyond the owned planes");
+    cudaStream_t s = (cudaStream_t)stream;
+    FS_TRY(fs_visc3d_pack(h, sphi, lvol, vol_norm, stream));                    // window planes only (+ wipes the previous solve's segments)
+    FS_TRY(fs_visc3d_load(h, FS_VEC_X, vx, vy, vz, vel_dtype, stream));
+    FS_TRY(fs_visc3d_extrapolate(h, FS_VEC_X, 3, stream));
+    FS_TRY(h->seg.finish());                                                    // (the list pack enqueued is not used: the global one follows the import)
+    const long long nseg_total = h->xseg.nseg_total;
+    FS_CUDA(cudaMemsetAsync(h->xflags, 0, (size_t)nseg_total, s));
+    const long long seg_lo = (long long)own_lo * L.sx / kSegPts;
+    long long seg_hi = ((long long)own_hi * L.sx + kSegPts - 1) / kSegPts;
+    if (seg_hi > nseg_total) seg_hi = nseg_total;
+    visc3d_mark_export_kernel<<<(unsigned)((seg_hi - seg_lo + 255) / 256), 256, 0, s>>>(L, h->act, seg_lo, seg_hi, nseg_total, h->xflags);
+    FS_LAUNCH_CHECK();
+    FS_TRY(h->xseg.enqueue(h->xflags, s, 1));
+    FS_TRY(h->xseg.finish());
+    *count = h->xseg.nseg;
+    if (h->xseg.nseg > cap) return FS_OK;       // nothing written: the caller grows its buffer and calls fs_visc3d_gather_reexport
+    return fs_visc3d_gather_reexport(h, records, cap, stream);
+}
+
+int fs_visc3d_gather_reexport(fs_visc3d* h, void* records, int64_t cap, void* stream) {
+    if (!h || !records) return fail(FS_ERR_ARG, "fs_visc3d_gather_reexport: null argument");
+    if (h->xseg.nseg > cap) return fail(FS_ERR_ARG, "fs_visc3d_gather_reexport: record buffer too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->xseg.nseg > 0) {
+        const int grid = seg_grid(h->xseg.nseg, kThreads / 32, kSMs * 8);
+        FS_DISPATCH(h, visc3d_export_kernel<T><<<grid, kThreads, 0, s>>>(h->L.NL, reinterpret_cast<const T*>(h->coef), vec_ptr<T>(h, FS_VEC_X), h->mask, h->act,
+                                                                         h->xseg.list, h->xseg.nseg_dev, (long long)cap, (char*)records));
+        FS_LAUNCH_CHECK();
+    }
+    return FS_OK;
+}
+
+int fs_visc3d_gather_import(fs_visc3d* h, const void* records, const int64_t* counts_dev, int nranks, int64_t stride, int skip_rank, void* stream) {
+    if (!h || !records || !counts_dev) return fail(FS_ERR_ARG, "fs_visc3d_gather_import: null argument");
+    if (nranks < 1 || stride < 0) return fail(FS_ERR_ARG, "fs_visc3d_gather_import: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (stride > 0) {
+        const long long total = (long long)nranks * stride;
+        long long blocks = (total + kThreads / 32 - 1) / (kThreads / 32);
+        if (blocks > kSMs * 8) blocks = kSMs * 8;
+        FS_DISPATCH(h, visc3d_import_kernel<T><<<(unsigned)blocks, kThreads, 0, s>>>(h->L.NL, reinterpret_cast<T*>(h->coef), vec_ptr<T>(h, FS_VEC_X), h->mask, h->act,
+                                                                                    (const char*)records, (const long long*)counts_dev, nranks, (long long)stride, skip_rank));
+        FS_LAUNCH_CHECK();
+    }
+    FS_TRY(h->seg.enqueue(h->act, s));          // the GLOBAL active list: identical on every rank
+    h->active_rows = -1;
+    h->packed = true;
+    return FS_OK;
+}
+
+int fs_visc3d_solve_packed(fs_visc3d* h, double dt, double mu, double rho, double cell_vol, void* vx, void* vy, void* vz, int vel_dtype,
+                           int own_lo, int own_hi, double tol, int64_t max_iter, fs_cg_stats* stats, void* stream) {
+    if (!h || !vx || !vy || !vz) return fail(FS_ERR_ARG, "fs_visc3d_solve_packed: null argument");
+    if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_solve_packed before pack / gather_import");
+    if (max_iter < 0) return fail(FS_ERR_ARG, "fs_visc3d_solve_packed: max_iter < 0");
+    if (vel_dtype != FS_F32 && vel_dtype != FS_F64) return fail(FS_ERR_ARG, "fs_visc3d_solve_packed: bad velocity dtype");
+    cudaStream_t s = (cudaStream_t)stream;
+    const double scale = dt / cell_vol / rho;
+    const double sm = scale * mu;
+    FS_TRY(visc3d_cg_begin_sparse(h, scale, mu, tol, max_iter, s));
+    int status = cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter + (visc3d_use_sr(h) ? 1 : 0), stats, s,
+                          visc3d_use_persistent(h) ? kCgBatchPersistent : kCgBatch);
+    if (status != FS_OK) return status;
+    const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 4);
+    if (vel_dtype == FS_F32) {
+        FS_DISPATCH(h, visc3d_store_active_kernel<T, float><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (float*)vx, (float*)vy, (float*)vz, own_lo, own_hi));
+    } else {
+        FS_DISPATCH(h, visc3d_store_active_kernel<T, double><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (double*)vx, (double*)vy, (double*)vz, own_lo, own_hi));
+    }
+    FS_LAUNCH_CHECK();
+    FS_CUDA(cudaStreamSynchronize(s));
+    return FS_OK;
+}
+
 int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_vol,
                     void* vx, void* vy, void* vz, int vel_dtype, const double* sphi, const double* lvol,
                     double tol, int64_t max_iter, fs_cg_stats* stats, void* stream) {
@@ -1576,9 +1772,9 @@ int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_
         // keeps the caller's value untouched (also when the solver stores fp32 and the caller fp64)
         const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 4);
         if (vel_dtype == FS_F32) {
-            FS_DISPATCH(h, visc3d_store_active_kernel<T, float><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (float*)vx, (float*)vy, (float*)vz));
+            FS_DISPATCH(h, visc3d_store_active_kernel<T, float><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (float*)vx, (float*)vy, (float*)vz, 0, h->L.X));
         } else {
-            FS_DISPATCH(h, visc3d_store_active_kernel<T, double><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (double*)vx, (double*)vy, (double*)vz));
+            FS_DISPATCH(h, visc3d_store_active_kernel<T, double><<<grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, FS_VEC_X), h->act, h->seg.list, h->seg.nseg_dev, (double*)vx, (double*)vy, (double*)vz, 0, h->L.X));
         }
         FS_LAUNCH_CHECK();
     }

@@ -73,15 +73,29 @@ class _Engine:
         self.lat = (X.value, Y.value, Zp.value)
         self.NL = NL.value
 
+    def close(self):
+        """Destroy the native handle and release the workspace (views into it become invalid)."""
+        if getattr(self, "h", None):
+            self.lib.fs_visc3d_destroy(self.h)
+            self.h = None
+        if getattr(self, "shared_ptr", None):
+            self.ws = None
+            self.lib.fs_shared_free(self.shared_ptr)
+            self.shared_ptr = None
+
+    def leak(self):
+        """Drop the handle but keep an IPC-exported workspace allocated: peers may still have it mapped."""
+        if getattr(self, "h", None):
+            self.lib.fs_visc3d_destroy(self.h)
+            self.h = None
+        self.shared_ptr = None
+
     def __del__(self):
         try:
-            if getattr(self, "h", None):
-                self.lib.fs_visc3d_destroy(self.h)
-                self.h = None
             if getattr(self, "shared_ptr", None):
-                self.ws = None
-                self.lib.fs_shared_free(self.shared_ptr)
-                self.shared_ptr = None
+                self.leak()              # never free exported memory without the collective close() of the owning solver
+            else:
+                self.close()
         except Exception:
             pass
 
@@ -138,9 +152,11 @@ def _engine(g, code):
     key = (tuple(g), code, torch.cuda.current_device())
     e = _engines.get(key)
     if e is None:
-        if len(_engines) > 4:
-            _engines.clear()
+        while len(_engines) >= 4:            # module-level functions reuse engines per grid; keep the 4 most recent
+            _engines.pop(next(iter(_engines)))
         e = _engines[key] = _Engine(g, code)
+    else:
+        _engines[key] = _engines.pop(key)    # most recently used last
     return e
 
 

@@ -73,6 +73,15 @@ _SIGS = {
     "fs_shared_close": (None, [c_void_p]),
     "fs_visc3d_set_peers": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(c_void_p)]),
     "fs_visc3d_peer_error": (c_int, [c_void_p]),
+    # gathered multi-GPU solve / windowed inputs
+    "fs_visc3d_set_window": (c_int, [c_void_p, c_int, c_int]),
+    "fs_visc3d_gather_record_bytes": (c_size_t, [c_void_p]),
+    "fs_visc3d_gather_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_double, c_int, c_int,
+                                        c_void_p, c_int64, POINTER(c_int64), c_void_p]),
+    "fs_visc3d_gather_reexport": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "fs_visc3d_gather_import": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "fs_visc3d_solve_packed": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_double, c_int64, POINTER(CgStats), c_void_p]),
     # viscosity 2-D
     "fs_visc2d_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "fs_visc2d_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_size_t]),

@@ -19,7 +19,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     import scenes
-    from solver.distributed import SlabPartition, SlabViscosityCGSolver3D, scatter_scene
+    from solver.distributed import GatheredViscosityCGSolver3D, SlabPartition, SlabViscosityCGSolver3D, scatter_scene
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
 
     ok = True
@@ -29,13 +29,23 @@ def main():
              (32, 100.0, torch.float64, (37, 24, 28), "p2p", "persistent", "fluid"), (32, 100.0, torch.float64, (37, 24, 28), "p2p", "kernels", "nonzero"),
              (32, 100.0, torch.float32, None, "p2p", "auto", "nonzero"), (32, 100.0, torch.float64, (37, 24, 28), "p2p", "persistent_sr", "nonzero"),
              (32, 100.0, torch.float64, (37, 24, 28), "p2p", "kernels_sr", "fluid"),
-             (32, 100.0, torch.float64, (37, 24, 28), "nccl", "auto", "fluid")]
+             (32, 100.0, torch.float64, (37, 24, 28), "nccl", "auto", "fluid"),
+             # gathered solve: set-up sharded, records all-gathered over NCCL, CG replicated (transport column = "gathered")
+             (48, 100.0, torch.float64, None, "gathered", "auto", "nonzero"), (32, 10.0, torch.float64, (67, 24, 28), "gathered", "auto", "fluid"),
+             (48, 100.0, torch.float32, None, "gathered", "auto", "nonzero")]
     for N, mu, dtype, g, transport, cg_mode, aset in cases:
         full = scenes.buckling(N, device="cuda", mu=mu, gres=g)
         gres = full["gres"]
-        part = SlabPartition(gres, world, rank)
-        sc = scatter_scene(full, part)
-        s = SlabViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype, transport=transport, cg_mode=cg_mode, active_set=aset)
+        if transport == "gathered":
+            if gres[0] < 2 * world:
+                continue
+            part = SlabPartition(gres, world, rank, ext=4)
+            sc = scatter_scene(full, part)
+            s = GatheredViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype, partition=part, cg_mode=cg_mode, active_set=aset)
+        else:
+            part = SlabPartition(gres, world, rank)
+            sc = scatter_scene(full, part)
+            s = SlabViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype, transport=transport, cg_mode=cg_mode, active_set=aset)
         v = [sc[k].clone() for k in ("vx", "vy", "vz")]
         s.solve(full["dt"], mu, full["rho"], *v, sc["sphi"], None, None, sc["lvol"])
         its = torch.tensor([s.iterations], device="cuda")
