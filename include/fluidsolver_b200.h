@@ -306,6 +306,34 @@ int fs_dens3d_displacement(int nx, int ny, int nz, double dt, const double* cell
 int fs_dens3d_gather(void* px_dev, int px_dtype, int64_t num_particles, const double* d_dev, int s0, int s1, int s2,
                      const double* bound_min3, const double* cell_size3, const double* grid_bias3, int axis, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Grid-side steps of the APIC time loop either side of the implicit solves: the kernels the notebook
+ * defines inline (3D_viscous_fluid_sim.ipynb code cells 2-7).  They produce the lvol / lphi / velocity / mass arrays the
+ * solvers consume and carry the result back to the particles, so a whole time step can stay on the device.
+ * Types are the notebook's: particle arrays fp64 (x, v, c* as (P,3) row-major; m as (P)), MAC grids fp32, level-set /
+ * volume grids fp64.  bound_min3 / cell_size3: 3 host doubles (bound_min is rounded to fp32 like the notebook's array).
+ * ---------------------------------------------------------------------------------------- */
+/* p2g (:279-344): zero-initialised mass / momentum grids in, mass and mass-weighted velocity (v / m where m > 0) out */
+int fs_grid_p2g(int nx, int ny, int nz, const double* bound_min3, const double* cell_size3, int64_t np,
+                const double* px, const double* pm, const double* pv, const double* cx, const double* cy, const double* cz,
+                float* mx, float* vx, float* my, float* vy, float* mz, float* vz, void* stream);
+/* g2p (:352-393): particle velocity and the three affine rows from the grid velocities */
+int fs_grid_g2p(int nx, int ny, int nz, const double* bound_min3, const double* cell_size3, int64_t np,
+                const double* px, double* pv, double* cx, double* cy, double* cz, const float* vx, const float* vy, const float* vz, void* stream);
+/* compute_fluid_levelset (:94-136): phi = fill, then min over particles of |x_cell - x_p| - radius in a 5^3 neighbourhood */
+int fs_grid_levelset(int nx, int ny, int nz, const double* bound_min3, const double* cell_size3, int64_t np, const double* px,
+                     double radius, double fill, double* phi, void* stream);
+/* compute_fluid_volume (:224-268) on the (rx,ry,rz) = 2*gres+1 node grid: trilinear splat of pvol, clamped to cell_vol */
+int fs_grid_fluid_volume(int rx, int ry, int rz, const double* bound_min3, const double* cell_size3, int64_t np, const double* px,
+                         double pvol, double cell_vol, double* vol, void* stream);
+/* extrapolate (:501-557): `sweeps` Jacobi sweeps into faces with zero mass, in place; workspace = generation bytes */
+size_t fs_grid_extrapolate_workspace_bytes(int nx, int ny, int nz);
+int fs_grid_extrapolate(int nx, int ny, int nz, int sweeps, float* vx, float* vy, float* vz, const float* mx, const float* my, const float* mz,
+                        void* workspace_dev, size_t workspace_bytes, void* stream);
+/* apply_boundary_condition (cell 5): dv from the old velocities (all three components), then v += dv */
+int fs_grid_boundary(int nx, int ny, int nz, double dx, float* vx, float* vy, float* vz, const float* mx, const float* my, const float* mz,
+                     const double* sphi, const double* sv, float* dvx, float* dvy, float* dvz, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

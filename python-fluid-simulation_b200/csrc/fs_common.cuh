@@ -716,7 +716,16 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_sr_seg_kernel(long long
 // Arrival is an acq_rel atomic (releases this block's writes — bar.sync before it makes that
 // cumulative over the block); waiters spin on an acquire load.
 // ---------------------------------------------------------------------------------------------
-struct GridBar { unsigned int count; unsigned int pad; unsigned long long result_ll[8]; };
+// Two-level arrival: the CTAs arrive in groups of kBarGroup on per-group counters (each on its own 128-byte line); the last
+// arriver of a group arrives on the top counter.  148 atomics on ONE address serialise in L2 (~15-27 cycles each, i.e. most
+// of a 1.2 us barrier); with 16-CTA groups at most 16 + 10 do.
+constexpr int kBarGroup = 16;
+constexpr int kBarMaxGroups = 64;
+struct GridBar {
+    unsigned int count; unsigned int pad; unsigned long long result_ll[8];
+    unsigned int pad2[14];
+    unsigned int gcount[kBarMaxGroups][32];      // per-group arrival counters, one per 128-byte line
+};
 
 __device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
     unsigned int r;
@@ -739,9 +748,22 @@ struct GridSync {
     unsigned int passed;     // barriers passed so far in this launch (identical in every thread of the grid)
     __device__ __forceinline__ void arrive_and_wait(bool system_scope) {   // thread 0 of the block only
         ++passed;
-        const unsigned int target = passed * gridDim.x;
         if (system_scope) fence_acq_rel_sys();                             // stores into a peer GPU need system scope
-        if (atom_add_acq_rel_gpu(&bar->count, 1u) + 1u < target) {
+        const unsigned int nb = gridDim.x;
+        if (nb <= (unsigned int)kBarGroup || nb > (unsigned int)(kBarGroup * kBarMaxGroups)) {      // small grids: one level
+            const unsigned int target = passed * nb;
+            if (atom_add_acq_rel_gpu(&bar->count, 1u) + 1u < target) {
+                while (ld_acquire_gpu(&bar->count) < target) { }
+            }
+            return;
+        }
+        const unsigned int g = blockIdx.x / kBarGroup, ngroups = (nb + kBarGroup - 1) / kBarGroup;
+        const unsigned int gsize = (g + 1 == ngroups) ? nb - g * kBarGroup : (unsigned int)kBarGroup;
+        const unsigned int target = passed * ngroups;
+        bool last = false;
+        if (atom_add_acq_rel_gpu(&bar->gcount[g][0], 1u) + 1u == passed * gsize)             // last of my group: arrive at the top
+            last = atom_add_acq_rel_gpu(&bar->count, 1u) + 1u == target;
+        if (!last) {
             while (ld_acquire_gpu(&bar->count) < target) { }
         }
     }
@@ -948,15 +970,38 @@ __device__ __forceinline__ void peer_allreduce2_block(double& a, double& b, Peer
     __syncthreads();
 }
 
+// two values through ONE pair of block barriers; totals valid in thread 0 (block_sum2) / in every thread (block_sum_all2)
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* sm /*>=64 doubles*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    a = warp_sum(a); b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { sm[warp] = a; sm[32 + warp] = b; }
+    __syncthreads();
+    if (warp == 0) {
+        a = warp_sum(lane < nwarps ? sm[lane] : 0.0);
+        b = warp_sum(lane < nwarps ? sm[32 + lane] : 0.0);
+    }
+}
+__device__ __forceinline__ void block_sum_all2(double& a, double& b, double* sm /*>=64 doubles*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    a = warp_sum(a); b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { sm[warp] = a; sm[32 + warp] = b; }
+    __syncthreads();
+    a = warp_sum(lane < nwarps ? sm[lane] : 0.0);
+    b = warp_sum(lane < nwarps ? sm[32 + lane] : 0.0);
+}
+
 // partials: 4 * gridDim.x doubles (two values, double-buffered by barrier parity)
 __device__ __forceinline__ void grid_allreduce2(double& v1, double& v2, double* partials, GridSync& gs,
                                                 PeerInfo* peers = nullptr, bool wrote_peer = false, unsigned int seq0 = 0, unsigned int seq1 = 0) {
-    __shared__ double sm[32];
+    __shared__ double sm[64];
     __shared__ double s_glob[2];
     const unsigned int nblocks = gridDim.x;
     double* slot = partials + (size_t)(gs.passed & 1u) * 2 * nblocks;
-    v1 = block_sum(v1, sm);
-    v2 = block_sum(v2, sm);
+    block_sum2(v1, v2, sm);
     if (threadIdx.x == 0) {
         slot[blockIdx.x] = v1;
         slot[nblocks + blockIdx.x] = v2;
@@ -967,8 +1012,7 @@ __device__ __forceinline__ void grid_allreduce2(double& v1, double& v2, double* 
     __syncthreads();
     double s1 = 0.0, s2 = 0.0;
     for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) { s1 += __ldcg(slot + i); s2 += __ldcg(slot + nblocks + i); }
-    s1 = block_sum_all(s1, sm);
-    s2 = block_sum_all(s2, sm);
+    block_sum_all2(s1, s2, sm);
     if (peers) peer_allreduce2_block(s1, s2, peers, seq0, seq1, s_glob, gs.bar->result_ll);
     v1 = s1; v2 = s2;
 }

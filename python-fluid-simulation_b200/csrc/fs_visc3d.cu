@@ -812,6 +812,194 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_sr_persistent_ke
 }
 
 // ---------------------------------------------------------------------------------------------
+// Single-reduction CG with the POINT-PRIVATE data resident in shared memory.  In this recurrence only r is ever read by
+// another thread (the stencil of the apply); p, s, w, x and the 16 pre-scaled coefficient values of a point are touched by
+// the lane that owns the point and by nobody else.  The warp -> segment assignment is static (warp g takes segments g,
+// g + nwarps, ...), so the first kResTrips-th trips of every warp keep all of that in shared memory for the whole launch:
+// 28 values per point (16 coefficients, p, s, w, x) + the activity byte = 7200 B per fp64 segment, 32 segments per CTA in
+// the 227 KB of a B200 SM = 4 736 segments on the chip (the 256^3 benchmark scene has 4 253).  Per iteration the L2 then
+// sees the r neighbourhood reads of phase A and one read + one write of r in phase B (about 27 MB instead of 62 MB on that
+// scene, whose iteration is L2-bandwidth-bound between its two grid barriers).  Segments beyond the resident trips run
+// through global memory exactly like visc3d_cg_sr_persistent_kernel.  p, s, x are loaded at kernel entry and written back
+// at exit (once per launch of up to 64 iterations), so the global state between launches is unchanged.
+// ---------------------------------------------------------------------------------------------
+constexpr int kResVals = 28;      // per point: 16 coefficients, p[3], s[3], w[3], x[3]
+template <typename T> __host__ __device__ constexpr size_t res_slot_bytes() { return (size_t)kResVals * 32 * sizeof(T) + 32; }
+
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) visc3d_cg_sr_resident_kernel(Visc3Dev<T> P, T* x, T* r, T* p, T* sv, T* w,
+                                                                                   const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                                   CgState* st, double* partials, GridBar* bar, int n_slots, int res_trips,
+                                                                                   unsigned long long* prof) {
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    constexpr int kWarps = THREADS / 32;
+    T* const svals = reinterpret_cast<T*>(res_smem);                                           // [res_trips*kWarps][kResVals][32]
+    uint8_t* const sact = res_smem + (size_t)res_trips * kWarps * kResVals * 32 * sizeof(T);    // [res_trips*kWarps][32]
+    const Lat3& L = P.L;
+    const long long NL = L.NL;
+    const long long stv[3] = {L.sx, L.sy, 1};
+    const int nseg = *nseg_p;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // Every CTA owns a CONTIGUOUS run of the (lattice-ordered) active list, so the y / z neighbours of its segments are
+    // mostly its own segments and hit in L1 during phase A; warp `warp` takes entries warp, warp + 16, ... of the run.
+    const long long chunk = ((long long)nseg + gridDim.x - 1) / gridDim.x;
+    const long long c_lo = (long long)blockIdx.x * chunk;
+    const long long c_hi = c_lo + chunk < nseg ? c_lo + chunk : nseg;
+    const long long gw = c_lo + warp, nw = kWarps;
+
+    // ---- prologue: point-private data of the resident trips -> shared memory
+    for (int j = 0; j < res_trips; ++j) {
+        const long long k = gw + (long long)j * nw;
+        if (k >= c_hi) break;
+        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+        const bool in = i < NL;
+        const long long jj = in ? i : (NL - 1);
+        T* S = svals + ((size_t)(j * kWarps + warp) * kResVals) * 32 + lane;
+        S[0 * 32] = __ldg(P.cs[0] + jj); S[1 * 32] = __ldg(P.cs[1] + jj); S[2 * 32] = __ldg(P.cs[2] + jj);
+        S[3 * 32] = __ldg(P.cs[3] + jj);
+        S[4 * 32] = __ldg(P.cs[3] + jj - stv[0]); S[5 * 32] = __ldg(P.cs[3] + jj - stv[1]); S[6 * 32] = __ldg(P.cs[3] + jj - stv[2]);
+        S[7 * 32] = __ldg(P.cs[4] + jj); S[8 * 32] = __ldg(P.cs[4] + jj + stv[1]); S[9 * 32] = __ldg(P.cs[4] + jj + stv[0]);
+        S[10 * 32] = __ldg(P.cs[5] + jj); S[11 * 32] = __ldg(P.cs[5] + jj + stv[2]); S[12 * 32] = __ldg(P.cs[5] + jj + stv[0]);
+        S[13 * 32] = __ldg(P.cs[6] + jj); S[14 * 32] = __ldg(P.cs[6] + jj + stv[2]); S[15 * 32] = __ldg(P.cs[6] + jj + stv[1]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            S[(16 + c) * 32] = in ? p[c * NL + i] : T(0);
+            S[(19 + c) * 32] = in ? sv[c * NL + i] : T(0);
+            S[(22 + c) * 32] = T(0);
+            S[(25 + c) * 32] = in ? x[c * NL + i] : T(0);
+        }
+        sact[(size_t)(j * kWarps + warp) * 32 + lane] = in ? (uint8_t)((unsigned int)__ldg(P.act + i) & kActCompute) : (uint8_t)0;
+    }
+    __syncwarp();
+
+    double delta = st->delta, gamma_old = st->delta_old, dl = st->dq, alpha_d = st->alpha, beta_d = st->beta;
+    bool first = st->sr_first != 0;
+    const double tol2 = st->tol2;
+    long long iter = st->iter;
+    const long long max_iter = st->max_iter;
+    int done = st->done;
+    GridSync gs{bar, 0u};
+    const bool stamp = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    int np = 0;
+    auto tick = [&]() {
+        if (stamp && np < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); prof[np++] = t; }
+    };
+    auto nb = [&](int comp, long long j) -> T { return r[comp * NL + j]; };      // coherent: other CTAs rewrote r before the last barrier
+    const PeerHot nohot = {};
+    for (int it = 0; it < n_slots && !done; ++it) {
+        tick();
+        // ---- phase A: w = A r, (r.r, w.r)
+        double rr = 0.0, wr = 0.0;
+        {
+            int j = 0;
+            for (long long k = gw; k < c_hi; k += nw, ++j) {
+                const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+                const bool in = i < NL;
+                const long long jj = in ? i : (NL - 1);
+                const T du = nb(0, jj), dv = nb(1, jj), dw = nb(2, jj);
+                T ru, rv, rw;
+                unsigned int a;
+                if (j < res_trips) {
+                    T* S = svals + ((size_t)(j * kWarps + warp) * kResVals) * 32 + lane;
+                    a = sact[(size_t)(j * kWarps + warp) * 32 + lane];
+                    auto cf = [&](int plane, int axis, int sign) -> T { return S[visc3_cslot(plane, axis, sign) * 32]; };
+                    ru = visc_row_scaled_cf<T, 3, 0>(jj, stv, S[0 * 32], du, cf, nb);
+                    rv = visc_row_scaled_cf<T, 3, 1>(jj, stv, S[1 * 32], dv, cf, nb);
+                    rw = visc_row_scaled_cf<T, 3, 2>(jj, stv, S[2 * 32], dw, cf, nb);
+                    S[22 * 32] = (a & 1u) ? ru : T(0);          // w stays in shared memory (zero on rows that are not computed)
+                    S[23 * 32] = (a & 2u) ? rv : T(0);
+                    S[24 * 32] = (a & 4u) ? rw : T(0);
+                } else {
+                    a = in ? ((unsigned int)__ldg(P.act + i) & kActCompute) : 0u;
+                    ru = visc_row_scaled<T, 3, 0>(P.cs, jj, stv, __ldg(P.cs[0] + jj), du, nb);
+                    rv = visc_row_scaled<T, 3, 1>(P.cs, jj, stv, __ldg(P.cs[1] + jj), dv, nb);
+                    rw = visc_row_scaled<T, 3, 2>(P.cs, jj, stv, __ldg(P.cs[2] + jj), dw, nb);
+                    if (a & 1u) w[i] = ru;
+                    if (a & 2u) w[NL + i] = rv;
+                    if (a & 4u) w[2 * NL + i] = rw;
+                }
+                if (a & 1u) { wr += (double)du * (double)ru; rr += (double)du * (double)du; }
+                if (a & 2u) { wr += (double)dv * (double)rv; rr += (double)dv * (double)dv; }
+                if (a & 4u) { wr += (double)dw * (double)rw; rr += (double)dw * (double)dw; }
+            }
+        }
+        tick();
+        grid_allreduce2(rr, wr, partials, gs);
+        tick();
+        delta = rr;
+        if (rr < tol2) done = 1;
+        else if (iter >= max_iter || !(rr == rr)) done = 2;
+        if (done) break;
+        dl = wr;
+        {
+            double a, b;
+            cg_sr_scalars(rr, wr, gamma_old, alpha_d, first, a, b);
+            alpha_d = a; beta_d = b;
+        }
+        gamma_old = rr;
+        first = false;
+        // ---- phase B: p = r + beta p, s = w + beta s, x += alpha p, r -= alpha s
+        {
+            const T alpha = (T)alpha_d, beta = (T)beta_d;
+            int j = 0;
+            for (long long k = gw; k < c_hi; k += nw, ++j) {
+                const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+                if (i >= NL) continue;
+                T rv[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) rv[c] = r[c * NL + i];
+                if (j < res_trips) {
+                    T* S = svals + ((size_t)(j * kWarps + warp) * kResVals) * 32 + lane;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const T pn = rv[c] + beta * S[(16 + c) * 32];
+                        const T sn = S[(22 + c) * 32] + beta * S[(19 + c) * 32];
+                        S[(16 + c) * 32] = pn;
+                        S[(19 + c) * 32] = sn;
+                        S[(25 + c) * 32] += alpha * pn;
+                        r[c * NL + i] = rv[c] - alpha * sn;
+                    }
+                } else {                               // beyond the resident trips: through global memory
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const long long e = c * NL + i;
+                        const T pn = rv[c] + beta * p[e];
+                        const T sn = w[e] + beta * sv[e];
+                        p[e] = pn;
+                        sv[e] = sn;
+                        x[e] += alpha * pn;
+                        r[e] = rv[c] - alpha * sn;
+                    }
+                }
+            }
+        }
+        iter += 1;
+        tick();
+        gs.sync();
+        tick();
+    }
+    // ---- epilogue: the resident p, s, x go back to global memory (w is scratch)
+    for (int j = 0; j < res_trips; ++j) {
+        const long long k = gw + (long long)j * nw;
+        if (k >= c_hi) break;
+        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+        if (i >= NL) continue;
+        const T* S = svals + ((size_t)(j * kWarps + warp) * kResVals) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            p[c * NL + i] = S[(16 + c) * 32];
+            sv[c * NL + i] = S[(19 + c) * 32];
+            x[c * NL + i] = S[(25 + c) * 32];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->delta = delta; st->delta_old = gamma_old; st->dq = dl; st->alpha = alpha_d; st->beta = beta_d;
+        st->iter = iter; st->done = done; st->sr_first = first ? 1 : 0;
+    }
+    (void)nohot;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Gathered multi-GPU solve (L2-sized active sets): every rank packs / loads / extrapolates only its own x-window of the
 // GLOBAL lattice, then the ranks exchange just the lattice segments the CG touches — the active segments of the planes a
 // rank owns plus every segment their stencils read — and each rank runs the whole (small) CG locally, with no
@@ -914,6 +1102,7 @@ struct fs_visc3d {
     char* d2;        // [3][NL] w = A r of the single-reduction CG; zero outside the active segments like r,d,q,b
     int cg_mode;     // FS_CG_*
     bool coop_failed; // a cooperative launch was refused on this context: use the stand-alone kernels from now on
+    bool resident_failed; // the shared-memory resident persistent kernel cannot run here (or is switched off)
     bool sparse_clean;   // r,d,q,b are zero outside the segments of the current active list (sparse begin / clear may be used)
     uint8_t* act;    // [NL] computed-row bits
     double* partials;
@@ -1205,6 +1394,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->work.count = (unsigned int*)(h->ws + lay.wcount);
     h->cg_mode = FS_CG_AUTO;
     h->coop_failed = false;
+    h->resident_failed = false;
     h->sparse_clean = true;          // the workspace is zeroed below and the list is empty
     h->grid_pts = lay.grid_pts;
     h->packed = false;
@@ -1483,8 +1673,67 @@ static bool visc3d_use_persistent(const fs_visc3d* h) {
 }
 
 // `n` = iteration slots (classic: iterations; single-reduction: an extra closing slot evaluates r.r of the last iterate)
+// Shared-memory resident form of the single-reduction persistent kernel (single GPU / gathered solve; FLUIDSOLVER_B200_RESIDENT=0
+// switches it off).  Returns 1 if it cannot run here (nothing enqueued), so that the caller falls back.
+static int visc3d_persistent_resident(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
+    static int env = -2;
+    if (env == -2) { const char* e = getenv("FLUIDSOLVER_B200_RESIDENT"); env = !e ? -1 : (e[0] == '0' ? 0 : 1); }
+    if (env == 0) return 1;
+    int dev = 0, smem_max = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 1;
+    const void* fn = nullptr;
+    size_t slot = 0;
+    static int threads_env = -1;
+    if (threads_env < 0) { const char* e = getenv("FLUIDSOLVER_B200_RESIDENT_THREADS"); threads_env = e ? atoi(e) : 0; }
+    const int kThreadsRes = threads_env == 1024 ? 1024 : 512;      // 1024 threads (64 registers) spill in the apply: 11.9 vs 8.1 us per iteration
+    FS_DISPATCH(h, { fn = kThreadsRes == 512 ? (const void*)visc3d_cg_sr_resident_kernel<T, 512> : (const void*)visc3d_cg_sr_resident_kernel<T, 1024>; slot = res_slot_bytes<T>(); });
+    const int kWarps = kThreadsRes / 32;
+    const int max_trips = (int)(((size_t)smem_max - 1024) / (kWarps * slot));       // 1 KB left for the static reduction scratch
+    if (max_trips < 1) return 1;
+    // grid first (it fixes the warp -> segment map), then as many resident trips as fit
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_trips * kWarps * slot)) != cudaSuccess) { cudaGetLastError(); return 1; }
+    const int cap = coop_max_blocks(fn, kThreadsRes, max_trips * kWarps * slot);
+    if (cap < 1) return 1;
+    int grid = seg_grid(h->seg.nseg, kWarps, cap < kSMs ? cap : kSMs);
+    if (const char* e = getenv("FLUIDSOLVER_B200_PERSIST_GRID")) { const int g = atoi(e); if (g >= 1 && g <= cap) grid = g; }
+    const long long chunk = ((long long)h->seg.nseg + grid - 1) / grid;        // segments per CTA (contiguous run of the list)
+    int trips = (int)((chunk + kWarps - 1) / kWarps);
+    if (trips < 1) trips = 1;
+    int res_trips = trips < max_trips ? trips : max_trips;
+    const size_t smem = (size_t)res_trips * kWarps * slot;
+    unsigned long long* prof = getenv("FLUIDSOLVER_B200_PROFILE") ? reinterpret_cast<unsigned long long*>(h->valid) : nullptr;
+    while (n > 0) {
+        int ni = (int)(n < (1 << 20) ? n : (1 << 20));
+        cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);
+        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+        FS_DISPATCH(h, {
+            Visc3Dev<T> P = dev_view<T>(h);
+            T* x = vec_ptr<T>(h, FS_VEC_X); T* r = vec_ptr<T>(h, FS_VEC_R); T* d = vec_ptr<T>(h, FS_VEC_D); T* q = vec_ptr<T>(h, FS_VEC_Q);
+            T* w = reinterpret_cast<T*>(h->d2);
+            const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
+            CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
+            void* args[] = {&P, &x, &r, &d, &q, &w, &seg, &nsegp, &st, &partials, &bar, &ni, &res_trips, &prof};
+            e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreadsRes), args, smem, s);
+        });
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported || e == cudaErrorInvalidValue) {
+            cudaGetLastError();
+            return 1;
+        }
+        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
+        FS_LAUNCH_CHECK();
+        n -= ni;
+    }
+    (void)sm;
+    return FS_OK;
+}
+
 static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
     const bool sr = visc3d_use_sr(h);
+    if (sr && !h->peers && !h->resident_failed) {
+        const int st = visc3d_persistent_resident(h, sm, n, s);
+        if (st != 1) return st;
+        h->resident_failed = true;              // not possible on this context: the global-memory form below takes over
+    }
     const void* fn = nullptr;
     FS_DISPATCH(h, fn = sr ? (h->peers ? (const void*)visc3d_cg_sr_persistent_kernel<T, true> : (const void*)visc3d_cg_sr_persistent_kernel<T, false>)
                            : (h->peers ? (const void*)visc3d_cg_persistent_kernel<T, true> : (const void*)visc3d_cg_persistent_kernel<T, false>));

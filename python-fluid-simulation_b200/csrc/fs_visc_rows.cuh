@@ -102,19 +102,20 @@ __device__ __forceinline__ T visc_row(const T* const* __restrict__ coef, long lo
 // so a row is one multiply and 14 fused multiply-adds instead of ~30 fp64 operations — what takes the operator apply off
 // the fp64 pipe (64 lanes per clock per SM on B200) and back onto the memory system.  Inside the loop d is zero on every
 // row that is not computed, so no neighbour masks (SURVEY A-1).
-template <typename T, int D, int A, class NB>
-__device__ __forceinline__ T visc_row_scaled(const T* const* __restrict__ cs, long long i, const long long* st, T diag, T own, NB nb) {
+// CF(plane, axis, sign) returns the coefficient of `plane` at i + sign*e_axis (sign = 0: at i itself); all three arguments
+// are compile-time constants after unrolling, so an accessor may map them to a fixed slot (shared-memory resident copy).
+template <typename T, int D, int A, class CF, class NB>
+__device__ __forceinline__ T visc_row_scaled_cf(long long i, const long long* st, T diag, T own, CF cf, NB nb) {
     T val = diag * own;
 #pragma unroll
     for (int ax = 0; ax < D; ++ax) {
         T hi, lo;
         if (ax == A) {
-            hi = __ldg(cs[D] + i);
-            lo = __ldg(cs[D] + i - st[A]);
+            hi = cf(D, 0, 0);
+            lo = cf(D, A, -1);
         } else {
-            const T* E = cs[D + A + ax];
-            hi = __ldg(E + i + st[ax]);
-            lo = __ldg(E + i);
+            hi = cf(D + A + ax, ax, +1);
+            lo = cf(D + A + ax, 0, 0);
         }
         val -= hi * nb(A, i + st[ax]);
         val -= lo * nb(A, i - st[ax]);
@@ -126,6 +127,22 @@ __device__ __forceinline__ T visc_row_scaled(const T* const* __restrict__ cs, lo
         }
     }
     return val;
+}
+
+template <typename T, int D, int A, class NB>
+__device__ __forceinline__ T visc_row_scaled(const T* const* __restrict__ cs, long long i, const long long* st, T diag, T own, NB nb) {
+    auto cf = [&](int plane, int axis, int sign) -> T { return __ldg(cs[plane] + i + (long long)sign * st[axis]); };
+    return visc_row_scaled_cf<T, D, A>(i, st, diag, own, cf, nb);
+}
+
+// Slot of coefficient (plane, axis, sign) in the 16-value per-point set of the 3-D scaled operator:
+// 0..2 diagonals; 3: 2sVc(i), 4..6: 2sVc(i - e_x / e_y / e_z); 7: sExy(i), 8: sExy(i+e_y), 9: sExy(i+e_x);
+// 10: sExz(i), 11: sExz(i+e_z), 12: sExz(i+e_x); 13: sEyz(i), 14: sEyz(i+e_z), 15: sEyz(i+e_y)
+__host__ __device__ constexpr int visc3_cslot(int plane, int axis, int sign) {
+    return plane == 3 ? (sign == 0 ? 3 : 4 + axis)
+         : plane == 4 ? (sign == 0 ? 7 : (axis == 1 ? 8 : 9))
+         : plane == 5 ? (sign == 0 ? 10 : (axis == 2 ? 11 : 12))
+                      : (sign == 0 ? 13 : (axis == 2 ? 14 : 15));
 }
 
 }  // namespace fs

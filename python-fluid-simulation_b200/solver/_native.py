@@ -122,6 +122,14 @@ _SIGS = {
     "fs_dens3d_displacement": (c_int, [c_int, c_int, c_int, c_double, POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fs_dens3d_gather": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_double),
                                  c_int, c_void_p]),
+    # grid-side steps of the time loop (notebook kernels)
+    "fs_grid_p2g": (c_int, [c_int, c_int, c_int, POINTER(c_double), POINTER(c_double), c_int64] + [c_void_p] * 12 + [c_void_p]),
+    "fs_grid_g2p": (c_int, [c_int, c_int, c_int, POINTER(c_double), POINTER(c_double), c_int64] + [c_void_p] * 8 + [c_void_p]),
+    "fs_grid_levelset": (c_int, [c_int, c_int, c_int, POINTER(c_double), POINTER(c_double), c_int64, c_void_p, c_double, c_double, c_void_p, c_void_p]),
+    "fs_grid_fluid_volume": (c_int, [c_int, c_int, c_int, POINTER(c_double), POINTER(c_double), c_int64, c_void_p, c_double, c_double, c_void_p, c_void_p]),
+    "fs_grid_extrapolate_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "fs_grid_extrapolate": (c_int, [c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "fs_grid_boundary": (c_int, [c_int, c_int, c_int, c_double] + [c_void_p] * 11 + [c_void_p]),
 }
 
 _lib = None
