@@ -334,6 +334,15 @@ int fs_grid_extrapolate(int nx, int ny, int nz, int sweeps, float* vx, float* vy
 int fs_grid_boundary(int nx, int ny, int nz, double dx, float* vx, float* vy, float* vz, const float* mx, const float* my, const float* mz,
                      const double* sphi, const double* sv, float* dvx, float* dvy, float* dvz, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Rigid-body signed distance field (solver/sdf3D.py:218-279).  rb_d: device table [nbodies][10][4] fp64 as
+ * built by sdf3D.generate_rb (:294-327); positions (npos,3) fp64 row-major.
+ * ---------------------------------------------------------------------------------------- */
+/* sd[p] = min over bodies (starting from 100, like the reference); vel[p] = velocity of that body where sd <= 0, else 0 */
+int fs_sdf3d_evaluate(const double* rb_d, int nbodies, int64_t npos, const double* pos_dev, double* sd_dev, double* vel_dev, void* stream);
+/* push every position out of (or, for flipped bodies, into) each body in table order, in place */
+int fs_sdf3d_project(const double* rb_d, int nbodies, int64_t npos, double* pos_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

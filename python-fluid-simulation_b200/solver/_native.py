@@ -130,6 +130,9 @@ _SIGS = {
     "fs_grid_extrapolate_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "fs_grid_extrapolate": (c_int, [c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
     "fs_grid_boundary": (c_int, [c_int, c_int, c_int, c_double] + [c_void_p] * 11 + [c_void_p]),
+    # rigid-body signed distance field (sdf3D)
+    "fs_sdf3d_evaluate": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fs_sdf3d_project": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None
