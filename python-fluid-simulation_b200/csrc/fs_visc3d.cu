@@ -87,6 +87,7 @@ template <typename T>
 __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const double* __restrict__ sphi, const double* __restrict__ lvol,
                                                           double vol_norm, T* __restrict__ coef /*[7][NL]*/, uint8_t* __restrict__ mask /*[3][NL]*/,
                                                           uint8_t* __restrict__ act /*[NL + 64]*/, uint8_t* __restrict__ rowflag /*[X*Y]*/,
+                                                          uint8_t* __restrict__ rownz /*[X*Y] in/out: the row's coefficient planes hold a non-zero*/,
                                                           int nonzero_only) {
     const int row = blockIdx.x + L.wlo * L.Y;        // x*Y + y
     int any_valid = 0;                               // does this lattice row hold any fluid face? (extrapolation sweep 1 skips far rows)
@@ -98,13 +99,19 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
     // start at the grid boundary, and on the closing plane of one that does not end there, they are not all present — those
     // planes get no activity bits from this rank (their owner supplies them)
     const bool act_ok = !((L.wlo > 0 && x == L.wlo) || (L.wcells < L.nx && x >= L.wcells));
-    const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
     // rows of these planes are computed by a neighbour slab and mirrored here (K2/K3 keep r and d current on them)
     const bool halo_x = (L.has_lo && x == 0) || (L.has_hi && x == L.nx - 1);
-    for (int z = threadIdx.x; z < L.Zp; z += blockDim.x) {
-        const long long i = (long long)row * L.Zp + z;
-        const long long f0 = frow + 2LL * z;         // fine node (2x,2y,2z)
-        const bool iz = z < L.nz, inz = z <= L.nz;
+    // Liquid-free lattice rows (all ten fine-grid volumes of every point zero: most of a typical scene) whose seven
+    // coefficient planes ALREADY hold zeros from the previous pack are not rewritten: a third of this kernel's traffic.
+    // Needs the row-wide verdict before the stores, i.e. one z per thread (rows longer than the block are always written).
+    const bool can_skip = L.Zp <= (int)blockDim.x;
+    const bool was_nz = rownz[row] != 0;
+    for (int z0 = 0; z0 < L.Zp; z0 += blockDim.x) {
+        const int z = z0 + threadIdx.x;
+        const bool live = z < L.Zp;                  // (all threads stay in the loop: block-wide vote below)
+        const long long i = (long long)row * L.Zp + (live ? z : 0);
+        const long long f0 = frow + 2LL * (live ? z : 0);         // fine node (2x,2y,2z)
+        const bool iz = live && z < L.nz, inz = live && z <= L.nz;
         // All ten fine-grid values of this lattice point are requested first (one memory latency), then normalised.
         // vol = lvol / vol_norm (:568): the fp64 division (~25 instructions) is skipped for the very common exact zeros, whose
         // quotient is the same zero; the empty volatile asm keeps ptxas from if-converting the branch (it otherwise evaluates
@@ -130,10 +137,11 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
         const double s_v = in_v ? sphi[f0 + fx + fz] : -1.0;
         const double s_w = in_w ? sphi[f0 + fx + fy] : -1.0;
         const T vc = norm(l_vc), exy = norm(l_exy), exz = norm(l_exz), eyz = norm(l_eyz);
+        T vface[3];
         unsigned int abits = 0;
         {
             const bool fluid = in_u && s_u >= 0.0;
-            T v = nan;
+            T v = T(0);
             const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 2;
             if (fluid && yz && x >= 1 && x <= L.u_xhi && act_ok) {    // (act_ok: fine plane 2x-1 is present)
                 v = norm(l_u);
@@ -142,12 +150,12 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
                 if (on) abits |= 1u;
             }
             if (fluid && halo_x && yz) abits |= 0x10u;
-            coef[0 * L.NL + i] = v;
-            mask[0 * L.NL + i] = fluid;
+            vface[0] = v;
+            if (live) mask[0 * L.NL + i] = fluid;
         }
         {
             const bool fluid = in_v && s_v >= 0.0;
-            T v = nan;
+            T v = T(0);
             const bool yz = y >= 1 && y <= L.ny - 1 && z >= 1 && z <= L.nz - 2;
             if (fluid && yz && x >= 1 && x <= L.nx - 2) {
                 v = norm(l_v);
@@ -156,12 +164,12 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
                 if (on) abits |= 2u;
             }
             if (fluid && halo_x && yz) abits |= 0x20u;
-            coef[1 * L.NL + i] = v;
-            mask[1 * L.NL + i] = fluid;
+            vface[1] = v;
+            if (live) mask[1 * L.NL + i] = fluid;
         }
         {
             const bool fluid = in_w && s_w >= 0.0;
-            T v = nan;
+            T v = T(0);
             const bool yz = y >= 1 && y <= L.ny - 2 && z >= 1 && z <= L.nz - 1;
             if (fluid && yz && x >= 1 && x <= L.nx - 2) {
                 v = norm(l_w);
@@ -170,16 +178,29 @@ __global__ void __launch_bounds__(512, 3) visc3d_pack_kernel(Lat3 L, const doubl
                 if (on) abits |= 4u;
             }
             if (fluid && halo_x && yz) abits |= 0x40u;
-            coef[2 * L.NL + i] = v;
-            mask[2 * L.NL + i] = fluid;
+            vface[2] = v;
+            if (live) mask[2 * L.NL + i] = fluid;
         }
         any_valid |= (in_u && s_u >= 0.0) || (in_v && s_v >= 0.0) || (in_w && s_w >= 0.0);
-        coef[3 * L.NL + i] = vc;
-        coef[4 * L.NL + i] = exy;
-        coef[5 * L.NL + i] = exz;
-        coef[6 * L.NL + i] = eyz;
-        act[i] = (uint8_t)(act_ok ? abits : 0u);
+        const int nz_pt = nz(vface[0]) || nz(vface[1]) || nz(vface[2]) || nz(vc) || nz(exy) || nz(exz) || nz(eyz);
+        bool write = true;
+        if (can_skip) {
+            const int nz_row = __syncthreads_or(nz_pt);
+            write = nz_row || was_nz;                // zero now and zero before: the planes already hold this row's zeros
+            if (threadIdx.x == 0) rownz[row] = (uint8_t)(nz_row != 0);
+        }
+        if (live && write) {
+            coef[0 * L.NL + i] = vface[0];
+            coef[1 * L.NL + i] = vface[1];
+            coef[2 * L.NL + i] = vface[2];
+            coef[3 * L.NL + i] = vc;
+            coef[4 * L.NL + i] = exy;
+            coef[5 * L.NL + i] = exz;
+            coef[6 * L.NL + i] = eyz;
+        }
+        if (live) act[i] = (uint8_t)(act_ok ? abits : 0u);
     }
+    if (!can_skip && threadIdx.x == 0) rownz[row] = 1;
     any_valid = __syncthreads_or(any_valid);
     if (threadIdx.x == 0) rowflag[row] = (uint8_t)(any_valid != 0);
 }
@@ -1099,6 +1120,7 @@ struct fs_visc3d {
     GridBar* bar;    // grid barrier of the persistent CG kernel
     ExtrapWork work; // extrapolation work lists
     uint8_t* rowflag; // [X*Y] lattice row holds a fluid face (written by pack, read by extrapolation sweep 1)
+    uint8_t* rownz;   // [X*Y] the row's coefficient planes hold a non-zero (pack skips rewriting rows that stay all-zero)
     char* d2;        // [3][NL] w = A r of the single-reduction CG; zero outside the active segments like r,d,q,b
     int cg_mode;     // FS_CG_*
     bool coop_failed; // a cooperative launch was refused on this context: use the stand-alone kernels from now on
@@ -1141,7 +1163,7 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     return L;
 }
 
-struct Visc3Layout { size_t coefs, xflags, xlist, xscratch; size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
+struct Visc3Layout { size_t coefs, xflags, xlist, xscratch, rownz; size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -1179,6 +1201,7 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     o.xflags = p; p = align_up(p + (size_t)((L.NL + kSegPts - 1) / kSegPts) + 64, 256);
     o.xlist = p; p = align_up(p + SegList::list_bytes(L.NL), 256);
     o.xscratch = p; p = align_up(p + SegList::scratch_bytes(L.NL), 256);
+    o.rownz = p; p = align_up(p + (size_t)L.X * L.Y, 256);
     o.total = p;
     return o;
 }
@@ -1384,6 +1407,7 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     h->bar = (GridBar*)(h->ws + lay.bar);
     h->d2 = h->ws + lay.d2;
     h->rowflag = (uint8_t*)(h->ws + lay.rowflag);
+    h->rownz = (uint8_t*)(h->ws + lay.rownz);
     h->work.cap = lay.wcap;
     if (const char* e = getenv("FLUIDSOLVER_B200_EXTRAP_CAP")) {   // test hook: tiny lists force the overflow fall-back
         const long long c = atoll(e);
@@ -1458,7 +1482,7 @@ int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double 
         FS_CUDA(cudaMemsetAsync(h->d2, 0, (size_t)3 * h->L.NL * h->esz, s));
         h->sparse_clean = true;
     }
-    FS_DISPATCH(h, visc3d_pack_kernel<T><<<(h->L.whi - h->L.wlo + 1) * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act, h->rowflag,
+    FS_DISPATCH(h, visc3d_pack_kernel<T><<<(h->L.whi - h->L.wlo + 1) * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act, h->rowflag, h->rownz,
                                                                                       h->active_mode == FS_ACTIVE_NONZERO ? 1 : 0));
     FS_LAUNCH_CHECK();
     FS_TRY(h->seg.enqueue(h->act, s));    // the list length (read back asynchronously) sizes the CG launches: see visc3d_list_ready
