@@ -343,6 +343,18 @@ int fs_sdf3d_evaluate(const double* rb_d, int nbodies, int64_t npos, const doubl
 /* push every position out of (or, for flipped bodies, into) each body in table order, in place */
 int fs_sdf3d_project(const double* rb_d, int nbodies, int64_t npos, double* pos_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * UNet surrogate (3D_viscous_fluid_sim.ipynb:844-913): the network input built in one pass and the gather
+ * of the velocity increments.  (X,Y,Z) = padded volume ("data_size"), pads = int((data_size - (2n+1)) / 2) like the notebook.
+ * ---------------------------------------------------------------------------------------- */
+/* out: fp32 [11][X][Y][Z] = dxdx dydy dzdz dxdy dxdz dydx dydz dzdx dzdy, solid flag (sphi <= 0; pad_solid outside the grid),
+ * lvol / cell_vol (the notebook passes 0.0125**3).  vx, vy, vz: fp32 MAC arrays; sphi, lvol: fp64 (2n+1)^3. */
+int fs_unet_features(int nx, int ny, int nz, int X, int Y, int Z, const float* vx, const float* vy, const float* vz,
+                     const double* sphi, const double* lvol, double cell_vol, float pad_solid, float* out, void* stream);
+/* dv{x,y,z}: fp32 MAC arrays <- net_out[3][X][Y][Z] at the staggered positions, divided by `divisor` (= int(1/DT)) */
+int fs_unet_gather(int nx, int ny, int nz, int X, int Y, int Z, const float* net_out, double divisor,
+                   float* dvx, float* dvy, float* dvz, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

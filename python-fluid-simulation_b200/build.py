@@ -45,10 +45,14 @@ def build_library(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libfluidsolver_b200.so")
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", target, "-ldl"]
+    tmp = target + ".building"            # linked next to the target, then renamed: a concurrent snapshot never sees a half-written .so
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", tmp, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, target)
     if verbose:
         print(r.stderr)
     return target

@@ -133,6 +133,9 @@ _SIGS = {
     # rigid-body signed distance field (sdf3D)
     "fs_sdf3d_evaluate": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fs_sdf3d_project": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    # UNet surrogate: input features and output gather
+    "fs_unet_features": (c_int, [c_int] * 6 + [c_void_p] * 5 + [c_double, ctypes.c_float, c_void_p, c_void_p]),
+    "fs_unet_gather": (c_int, [c_int] * 6 + [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None
