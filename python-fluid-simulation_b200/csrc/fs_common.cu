@@ -31,7 +31,7 @@ __global__ void cg_state_init_kernel(CgState* st, double tol2, long long max_ite
     st->red = 0.0;
     for (int i = 0; i < 4; ++i) st->counter[i] = 0;
     st->sr_first = 1;
-    st->pad_ = 0;
+    st->sr_parity = 0;
 }
 
 __global__ void cg_finish_kernel(CgState* st, int which) {

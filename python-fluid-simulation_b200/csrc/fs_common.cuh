@@ -72,7 +72,7 @@ struct CgState {
     unsigned int counter[4];  // last-block tickets (one per reducing kernel type)
     // single-reduction (Chronopoulos-Gear) CG: `first` = no search direction yet (beta = 0, alpha = gamma/(w.r))
     int sr_first;
-    int pad_;
+    int sr_parity;     // which w buffer the last K1s wrote (multi-GPU: iteration parity; single GPU: always 0)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -107,8 +107,11 @@ struct PeerHot {
     int has_lo, has_hi;
     char* q_lo[3];
     char* q_hi[3];
-    char* w_lo[3];     // the same planes of the neighbours' w = A r buffer (single-reduction CG)
-    char* w_hi[3];
+    // the same planes of the neighbours' w = A r buffers (single-reduction CG), [parity*3 + component].  With ONE cross-GPU
+    // synchronisation per iteration a fast rank is already pushing the boundary rows of iteration k+1 while a slow neighbour
+    // still reads those of iteration k in its update phase, so w is double-buffered by iteration parity.
+    char* w_lo[6];
+    char* w_hi[6];
     long long comp_len, halo_lo_end, halo_hi_begin, halo_hi_end;
     long long hb[6], he[6];   // the same halo rows as [begin,end) intervals of the flat 3-component index (empty if unused)
 };
@@ -645,7 +648,8 @@ __device__ __forceinline__ void cg_sr_scalars(double gamma, double dl, double ga
 }
 
 // bookkeeping after the (r.r, w.r) reduction of K1s (thread 0 of the finishing block)
-__device__ __forceinline__ void cg_sr_after_dots(CgState* st, double gamma, double dl) {
+__device__ __forceinline__ void cg_sr_after_dots(CgState* st, double gamma, double dl, int parity = 0) {
+    st->sr_parity = parity;
     st->delta = gamma;
     if (gamma < st->tol2) { st->done = 1; return; }
     if (st->iter >= st->max_iter || !(gamma == gamma)) { st->done = 2; return; }   // NaN: the reference would spin to max_iter
@@ -696,9 +700,10 @@ __device__ __forceinline__ void cg_update_sr_seg_body(long long comp_stride, lon
 template <typename T, int NCOMP>
 __global__ void __launch_bounds__(kVecThreads) cg_update_sr_seg_kernel(long long comp_stride, long long npts,
                                                                        const int* __restrict__ seg, const int* __restrict__ nseg_p,
-                                                                       T* x, T* r, T* p, T* sv, const T* w, CgState* st, int freeze) {
+                                                                       T* x, T* r, T* p, T* sv, const T* w /*[2][NCOMP][comp_stride]*/, CgState* st, int freeze) {
     if (*(volatile int*)&st->done) return;
     const double alpha_d = st->alpha, beta_d = st->beta;
+    w += (long long)st->sr_parity * NCOMP * comp_stride;           // the buffer the preceding K1s wrote
     cg_update_sr_seg_body<T, NCOMP>(comp_stride, npts, seg, *nseg_p, x, r, p, sv, w, (T)alpha_d, (T)beta_d);
     if (!freeze && blockIdx.x == 0 && threadIdx.x == 0) st->iter += 1;     // read by the next K1s (stream order)
 }

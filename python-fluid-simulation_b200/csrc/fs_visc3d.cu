@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_begin_kernel(Visc3Dev<T> P, T
 
 // zero r, d, q, b on the segments of the (previous) active list
 template <typename T>
-__global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T* __restrict__ vecs /*[5][3][NL]*/, T* __restrict__ d2 /*[3][NL]*/,
+__global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T* __restrict__ vecs /*[5][3][NL]*/, T* __restrict__ d2 /*[2][3][NL]*/,
                                                                 const int* __restrict__ seg, const int* __restrict__ nseg_p,
                                                                 uint8_t* __restrict__ act_clear /*gathered mode: also forget the activity bits, else null*/) {
     const int nseg = *nseg_p;
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_clear_kernel(long long NL, T*
 #pragma unroll
             for (int c = 0; c < 3; ++c) vecs[((long long)v * 3 + c) * NL + i] = T(0);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) d2[(long long)c * NL + i] = T(0);
+        for (int c = 0; c < 6; ++c) d2[(long long)c * NL + i] = T(0);        // both parities of w
         if (act_clear) act_clear[i] = 0;
     }
 }
@@ -616,7 +616,7 @@ template <> struct K1Occ<float> { static constexpr int value = 3; };
 // rows, and the boundary rows go to the neighbours' w planes instead of their q planes.
 template <typename T, bool DIST, bool COHERENT, bool SR = false>
 __device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T s, T s2, const T* d, T* q, const int* __restrict__ seg, int nseg,
-                                                        const PeerHot& hot, bool& wrote_peer, double* acc2_out = nullptr) {
+                                                        const PeerHot& hot, bool& wrote_peer, double* acc2_out = nullptr, int par = 0) {
     const Lat3& L = P.L;
     const long long NL = L.NL;
     const long long st[3] = {L.sx, L.sy, 1};
@@ -649,8 +649,8 @@ __device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T 
             // into the peers' memory over NVLink; the all-reduce that follows publishes them.  (The local halo
             // planes 0 and X-2 carry no computed row: their q is written by the NEIGHBOURS, never by this rank.)
             const long long lo0 = L.sx, hi0 = (long long)(L.X - 3) * L.sx;
-            char* const* plo = SR ? hot.w_lo : hot.q_lo;
-            char* const* phi = SR ? hot.w_hi : hot.q_hi;
+            char* const* plo = SR ? hot.w_lo + 3 * par : hot.q_lo;
+            char* const* phi = SR ? hot.w_hi + 3 * par : hot.q_hi;
             if (hot.has_lo && i >= lo0 && i < lo0 + L.sx) {
                 const long long o = i - lo0;
                 if (au) reinterpret_cast<T*>(plo[0])[o] = ru;
@@ -760,17 +760,19 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
 // form below has two grid barriers per iteration (one carrying the reduction) instead of three (two carrying one).
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool DIST>
-__global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot2_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ r, T* __restrict__ w,
+__global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot2_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ r, T* __restrict__ w /*[2][3][NL]*/,
                                                                                         const int* __restrict__ seg, const int* __restrict__ nseg_p,
                                                                                         CgState* st_, double* partials, PeerInfo* peers, PeerHot hot, int freeze) {
     if (*(volatile int*)&st_->done) return;
     bool wrote_peer = false;
     double rr = 0.0;
-    const double wr = visc3d_apply_dot_body<T, DIST, false, true>(P, s, s2, r, w, seg, *nseg_p, hot, wrote_peer, &rr);
+    const int par = DIST ? (int)(st_->iter & 1) : 0;           // (st->iter is stable here: only the update kernel advances it)
+    w += (long long)par * 3 * P.L.NL;
+    const double wr = visc3d_apply_dot_body<T, DIST, false, true>(P, s, s2, r, w, seg, *nseg_p, hot, wrote_peer, &rr, par);
     const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
     grid_sum2_finish(rr, wr, partials, &st_->counter[0], [=](double gamma, double dl) {
         if (freeze) return;                      // profiling hook: repeated launches leave the CG state alone
-        cg_sr_after_dots(st_, gamma, dl);
+        cg_sr_after_dots(st_, gamma, dl, par);
     }, (DIST && !freeze) ? peers : nullptr, block_wrote_peer);
 }
 
@@ -800,7 +802,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_sr_persistent_ke
         // phase A: w = A r, (r.r, w.r)
         bool wrote_peer = false;
         double rr = 0.0;
-        double wr = visc3d_apply_dot_body<T, DIST, true, true>(P, s, s2, r, w, seg, nseg, hot, wrote_peer, &rr);
+        const int par = DIST ? (int)(iter & 1) : 0;              // w is double-buffered by iteration parity (see PeerHot)
+        T* const wk = w + (long long)par * 3 * NL;
+        double wr = visc3d_apply_dot_body<T, DIST, true, true>(P, s, s2, r, wk, seg, nseg, hot, wrote_peer, &rr, par);
         const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
         tick();
         if (DIST) { ++seq0; ++seq1; }
@@ -819,7 +823,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_sr_persistent_ke
         gamma_old = rr;
         first = false;
         // phase B: p = r + beta p, s = w + beta s, x += alpha p, r -= alpha s   (halo rows included: they mirror the owner's)
-        cg_update_sr_seg_body<T, 3>(NL, NL, seg, nseg, x, r, p, sv, w, (T)alpha_d, (T)beta_d);
+        cg_update_sr_seg_body<T, 3>(NL, NL, seg, nseg, x, r, p, sv, wk, (T)alpha_d, (T)beta_d);
         iter += 1;
         tick();
         gs.sync();
@@ -1121,7 +1125,7 @@ struct fs_visc3d {
     ExtrapWork work; // extrapolation work lists
     uint8_t* rowflag; // [X*Y] lattice row holds a fluid face (written by pack, read by extrapolation sweep 1)
     uint8_t* rownz;   // [X*Y] the row's coefficient planes hold a non-zero (pack skips rewriting rows that stay all-zero)
-    char* d2;        // [3][NL] w = A r of the single-reduction CG; zero outside the active segments like r,d,q,b
+    char* d2;        // [2][3][NL] w = A r of the single-reduction CG (two iteration parities); zero outside the active segments like r,d,q,b
     int cg_mode;     // FS_CG_*
     bool coop_failed; // a cooperative launch was refused on this context: use the stand-alone kernels from now on
     bool resident_failed; // the shared-memory resident persistent kernel cannot run here (or is switched off)
@@ -1192,7 +1196,7 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     o.wcount = p; p = align_up(p + 4 * sizeof(unsigned int), 256);
     // w = A r buffer of the single-reduction CG, with the same guard bands as `vecs`
     p += guard;
-    o.d2 = p; p = align_up(p + 3 * L.NL * esz, 256) + guard;
+    o.d2 = p; p = align_up(p + 6 * L.NL * esz, 256) + guard;       // two parities (multi-GPU double buffering)
     o.rowflag = p; p = align_up(p + (size_t)L.X * L.Y, 256);
     // pre-scaled coefficient planes of the CG-loop apply (same guard bands as `coef`: the branch-free K1 reads neighbours of discarded lanes)
     p += guard;
@@ -1283,7 +1287,8 @@ int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int h
         Visc3Layout ln = visc3_layout(Ln, esz);
         for (int c = 0; c < 3; ++c) {
             pi.q_lo[c] = (char*)lo_ws + ln.vecs + (((size_t)FS_VEC_Q * 3 + c) * Ln.NL + (size_t)(Ln.X - 2) * Ln.sx) * esz;
-            h->hot.w_lo[c] = (char*)lo_ws + ln.d2 + ((size_t)c * Ln.NL + (size_t)(Ln.X - 2) * Ln.sx) * esz;
+            for (int par = 0; par < 2; ++par)
+                h->hot.w_lo[par * 3 + c] = (char*)lo_ws + ln.d2 + ((size_t)(par * 3 + c) * Ln.NL + (size_t)(Ln.X - 2) * Ln.sx) * esz;
         }
     }
     if (h->has_hi) {
@@ -1291,7 +1296,8 @@ int fs_visc3d_set_peers(fs_visc3d* h, void* lo_ws, int lo_nx, void* hi_ws, int h
         Visc3Layout ln = visc3_layout(Ln, esz);
         for (int c = 0; c < 3; ++c) {
             pi.q_hi[c] = (char*)hi_ws + ln.vecs + (((size_t)FS_VEC_Q * 3 + c) * Ln.NL) * esz;
-            h->hot.w_hi[c] = (char*)hi_ws + ln.d2 + ((size_t)c * Ln.NL) * esz;
+            for (int par = 0; par < 2; ++par)
+                h->hot.w_hi[par * 3 + c] = (char*)hi_ws + ln.d2 + ((size_t)(par * 3 + c) * Ln.NL) * esz;
         }
     }
     pi.comp_len = h->L.NL;
@@ -1479,7 +1485,7 @@ int fs_visc3d_pack(fs_visc3d* h, const double* sphi, const double* lvol, double 
         }
     } else {
         FS_CUDA(cudaMemsetAsync(h->vecs + (size_t)FS_VEC_R * 3 * h->L.NL * h->esz, 0, (size_t)12 * h->L.NL * h->esz, s));
-        FS_CUDA(cudaMemsetAsync(h->d2, 0, (size_t)3 * h->L.NL * h->esz, s));
+        FS_CUDA(cudaMemsetAsync(h->d2, 0, (size_t)6 * h->L.NL * h->esz, s));
         h->sparse_clean = true;
     }
     FS_DISPATCH(h, visc3d_pack_kernel<T><<<(h->L.whi - h->L.wlo + 1) * h->L.Y, row_block(h->L), 0, s>>>(h->L, sphi, lvol, vol_norm, reinterpret_cast<T*>(h->coef), h->mask, h->act, h->rowflag, h->rownz,
@@ -1821,7 +1827,8 @@ static int visc3d_cg_begin_sparse(fs_visc3d* h, double scale, double mu, double 
     FS_CUDA(cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s));
     if (h->peers) {   // belt and braces: the halo planes of q (and w) must read as zero until the neighbours store into them
         for (int c = 0; c < 3; ++c) {
-            char* comps[2] = {h->vecs + ((size_t)FS_VEC_Q * 3 + c) * h->L.NL * h->esz, h->d2 + (size_t)c * h->L.NL * h->esz};
+            char* comps[3] = {h->vecs + ((size_t)FS_VEC_Q * 3 + c) * h->L.NL * h->esz, h->d2 + (size_t)c * h->L.NL * h->esz,
+                              h->d2 + (size_t)(3 + c) * h->L.NL * h->esz};
             for (char* comp : comps) {
                 if (h->has_lo) FS_CUDA(cudaMemsetAsync(comp, 0, (size_t)h->L.sx * h->esz, s));
                 if (h->has_hi) FS_CUDA(cudaMemsetAsync(comp + (size_t)(h->L.X - 2) * h->L.sx * h->esz, 0, (size_t)h->L.sx * h->esz, s));

@@ -459,12 +459,23 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
     The HBM-bound variant of the same scene (active_set "fluid": every row the reference computes) runs on x-slabs with the
     collectives fused into the kernels and is reported beside it (`hbm_variant`), like in the N=1 line.  Both are checked
     against the single-GPU solver on the same scene inside the run (`parity`)."""
+    import faulthandler
     import scenes
     from bench import ClockSampler, counts, kernel_study
     from .ViscosityCGSolver3D import ViscosityCGSolver3D
 
     rank, world = dist.get_rank(), dist.get_world_size()
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # watchdog: a multi-GPU run that stalls (a peer died, a collective mismatched) dumps every thread's stack and exits
+    # instead of hanging until somebody's time limit
+    faulthandler.dump_traceback_later(float(os.environ.get("FLUIDSOLVER_B200_WATCHDOG_S", "420")), exit=True, file=sys.stderr)
+    t_start = time.time()
+    trace_on = os.environ.get("FLUIDSOLVER_B200_TRACE", "0") != "0"
+
+    def trace(msg):
+        if trace_on:
+            print(f"[bench r{rank} +{time.time() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
     tdtype = torch.float64 if args.dtype == "f64" else torch.float32
     esz = 8 if args.dtype == "f64" else 4
     n = args.size
@@ -513,12 +524,21 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
         """a converging solve (tol 1e-3) on the multi-GPU path and on the single-GPU solver (whole grid, this rank's GPU);
         every rank compares the planes it owns, the worst rank is reported"""
         keep = sol.max_iter
-        sol.max_iter = int(np.prod(g))
+        cap_it = 20000                            # (both sides bounded: a solve that stalls must fail the check, not hang the run)
+        sol.max_iter = cap_it
         v = [sc[k].clone() for k in ("vx", "vy", "vz")]
-        sol.solve(sc["dt"], args.mu, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"], tol=1e-3)
+        failed = False
+        try:
+            sol.solve(sc["dt"], args.mu, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"], tol=1e-3)
+        except ValueError:
+            failed = True
         ref = ViscosityCGSolver3D(g, bound, dtype=tdtype, active_set=active_set)
+        ref.max_iter = cap_it
         rv = [full[k].clone() for k in ("vx", "vy", "vz")]
-        ref.solve(full["dt"], args.mu, full["rho"], *rv, full["sphi"], None, None, full["lvol"], tol=1e-3)
+        try:
+            ref.solve(full["dt"], args.mu, full["rho"], *rv, full["sphi"], None, None, full["lvol"], tol=1e-3)
+        except ValueError:
+            failed = True
         worst = 0.0
         for a, b, kind in zip(v, rv, ("u", "v", "w")):
             lo, hi = part.owned_planes(kind)
@@ -530,14 +550,17 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
                "iters_equal": int(t[1].item()) == int(-t[2].item()) == int(ref.iterations),
                "iters_within_2pct": abs(sol.iterations - ref.iterations) <= max(1, round(0.02 * ref.iterations)),
                "delta_rel_diff": abs(sol.delta - ref.delta) / max(ref.delta, 1e-300), "owned_rel_l2": float(t[0].item())}
-        out["ok"] = bool(out["iters_within_2pct"] and int(t[1].item()) == int(-t[2].item()) and out["owned_rel_l2"] < 1e-4)
+        out["converged"] = not failed
+        out["ok"] = bool(not failed and out["iters_within_2pct"] and int(t[1].item()) == int(-t[2].item()) and out["owned_rel_l2"] < 1e-4)
         sol.max_iter = keep
         del ref
         torch.cuda.empty_cache()
         return out
 
+    trace(f"scene ready, mode={mode}")
     # ---- the default workload ----------------------------------------------------------------------------------
     solver, part, sc = make(mode, aset)
+    trace("solver built")
     config = dict(config, multi_gpu=(f"gathered: set-up sharded over {world} ranks (x-windows, 4-cell overlap), CG replicated on every rank "
                                      "(no inter-GPU traffic inside the iteration); records all-gathered over NCCL" if mode == "gathered" else
                                      f"x-slabs over {world} ranks, transport {solver.transport}: halo rows and the CG reduction fused into the kernels over peer memory"),
@@ -546,9 +569,11 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
     step = window_step(solver, sc, sc)
     for _ in range(max(args.warmup, 3)):
         step()
+    trace("warm-up done")
     l0 = N.launch_count()
     with ClockSampler(local) as clocks:
         ms = timed(step, args.steps)
+    trace(f"timed: {ms / args.steps:.3f} ms/step")
     launches = N.launch_count() - l0
     value = args.iters * args.steps / (ms * 1e-3)
 
@@ -572,10 +597,12 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
     with ClockSampler(local) as clocks_e2e:
         e2e_ms = timed(step_e2e, e2e_steps)
     e2e_value = args.iters * e2e_steps / (e2e_ms * 1e-3)
+    trace(f"e2e: {e2e_ms / e2e_steps:.3f} ms/step")
     del host
     tot = torch.tensor([float(h2d), float(d2h), float(launches)], dtype=torch.float64, device="cuda")
     dist.all_reduce(tot)
     par = parity(solver, part, sc, aset)
+    trace(f"parity: {par}")
 
     # per-iteration / per-kernel figures of rank 0's engine (gathered: the complete CG, identical on every rank)
     scale = sc["dt"] / solver.cell_vol / sc["rho"]
@@ -589,23 +616,29 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
         solver.max_iter = args.iters
         if rank == 0:
             kin = kernel_study(solver, solver._e.lib, N, torch, scale, args, esz)
+    trace("kernel study done")
     dist.barrier()
     published = getattr(solver, "published", None)
     solver.close()
     del solver, sc
     torch.cuda.empty_cache()
+    trace("default leg closed")
 
     # ---- HBM-bound variant of the same scene on slabs (every fluid row) -----------------------------------------------
     hbm_variant = None
     if getattr(args, "hbm_leg", 1) and aset == "nonzero":
         s2, p2, sc2 = make("slab", "fluid")
+        trace(f"slab solver built, starts={p2.starts}")
         s2.max_iter = args.iters
         st2 = window_step(s2, sc2, sc2)
         for _ in range(2):
             st2()
+        trace("slab warm-up done")
         with ClockSampler(local) as cl2:
             ms2 = timed(st2, max(2, min(args.steps, 5))) / max(2, min(args.steps, 5))
+        trace(f"slab timed: {ms2:.3f} ms/step")
         par2 = parity(s2, p2, sc2, "fluid")
+        trace(f"slab parity: {par2}")
         segs2 = s2._e.active_info()
         hbm_variant = {"what": "same scene and window, active_set='fluid' (every row the reference's kernels compute), x-slabs with fused collectives",
                        "value": args.iters / (ms2 * 1e-3), "unit": unit, "ms_per_step": ms2, "transport": s2.transport, "slab_starts": p2.starts,
@@ -637,6 +670,7 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
             "roofline": roofline, "hbm_variant": hbm_variant, "clocks": clocks.summary(),
         }
         print(json.dumps(line), file=getattr(args, "_json_out", None) or sys.stdout, flush=True)
+    faulthandler.cancel_dump_traceback_later()
     dist.barrier()
     ok = par["ok"] and (hbm_variant is None or hbm_variant["parity"]["ok"])
     flag = torch.tensor([1 if ok else 0], device="cuda")

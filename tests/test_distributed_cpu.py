@@ -139,3 +139,47 @@ def test_density_module_surface_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             Dn.DensityCGSolver3D(None, (8, 8, 8), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+
+
+def test_gathered_partition_windows():
+    """ext=4 windows of the gathered solve: every window covers its owned cells plus 4 (clipped at the grid), owned planes
+    tile the grid once, and the window arrays cut by slab() have the shapes the C ABI expects."""
+    from solver.distributed import GatheredViscosityCGSolver3D, SlabPartition
+    assert GatheredViscosityCGSolver3D.EXT == 4
+    for nx, world in ((48, 2), (48, 3), (64, 8), (37, 4), (256, 8)):
+        parts = [SlabPartition((nx, 5, 6), world, r, ext=4) for r in range(world)]
+        for p in parts:
+            assert p.e0 == max(0, p.c0 - 4) if p.has_lo else p.e0 == p.c0 == 0
+            assert p.e1 == min(nx, p.c1 + 4) if p.has_hi else p.e1 == p.c1 == nx
+            u = np.zeros((nx + 1, 5, 6))
+            fine = np.zeros((2 * nx + 1, 11, 13))
+            assert p.slab(u, "u").shape[0] == p.e1 - p.e0 + 1
+            assert p.slab(u[:-1], "v").shape[0] == p.e1 - p.e0
+            assert p.slab(fine, "fine").shape[0] == 2 * (p.e1 - p.e0) + 1
+        covered = []
+        for p in parts:
+            lo, hi = p.owned_planes("u")
+            covered += list(range(p.e0 + lo, p.e0 + hi))
+        assert covered == list(range(nx + 1))
+
+
+def test_new_module_surfaces_without_gpu():
+    """notebook_kernels / sdf3D / unet_surrogate expose the reference's names and argument lists (ipynb cells 2-7, 12; sdf3D.py)"""
+    import inspect
+    import notebook_kernels as K
+    import unet_surrogate as US
+    from solver import sdf3D as sdf
+    assert list(inspect.signature(K.p2g).parameters) == ["p", "g"]
+    assert list(inspect.signature(K.g2p).parameters) == ["p", "g"]
+    assert list(inspect.signature(K.compute_fluid_levelset).parameters) == ["p", "ls", "gdx"]
+    assert list(inspect.signature(K.compute_fluid_volume).parameters) == ["p", "fv", "pvol"]
+    assert list(inspect.signature(K.extrapolate).parameters) == ["gres", "num_iter", "vx", "vy", "vz", "mx", "my", "mz"]
+    assert list(inspect.signature(K.apply_boundary_condition).parameters) == ["g", "solid", "dx"]
+    assert list(inspect.signature(sdf.evaluate).parameters) == ["rb_d", "sd", "vel", "position"]
+    assert list(inspect.signature(sdf.project).parameters) == ["rb_d", "position"]
+    assert list(inspect.signature(sdf.generate_rb).parameters) == ["rb_d", "rb_map", "name", "rbparam", "flip", "center", "axis", "angle"]
+    assert list(inspect.signature(US.unet_solve).parameters)[:5] == ["vx", "vy", "vz", "sphi", "lvol"] and len(inspect.signature(US.unet_solve).parameters) == 19
+    assert US.default_data_size((48, 80, 48)) == (112, 176, 112)          # the notebook's hard-coded volume (ipynb cell 12)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            K.extrapolate((4, 4, 4), 1, *[np.zeros((5, 4, 4), dtype=np.float32)] * 6)
