@@ -273,7 +273,14 @@ struct ExtrapWork {
 
 __device__ __forceinline__ void extrap_push(const ExtrapWork& W, int which, unsigned int face) {
     if (W.cap == 0u) return;
-    const unsigned int k = atomicAdd(W.count + which, 1u);
+    // warp-aggregated: the lanes that reach this point together take ONE ticket range (hundreds of thousands of faces are
+    // recorded per sweep; one atomic per lane on a single counter serialised the list sweeps at ~50 us each)
+    const unsigned int m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(W.count + which, (unsigned int)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const unsigned int k = base + __popc(m & ((1u << lane) - 1u));
     if (k < W.cap) W.list[which][k] = face;
     else W.count[2] = 1u;                          // overflow: the next sweep falls back to a full pass
 }

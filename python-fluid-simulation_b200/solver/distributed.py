@@ -389,7 +389,13 @@ class GatheredViscosityCGSolver3D:
         if not self._dist:
             raise RuntimeError("solve() needs torch.distributed; use export_step / import_step / finish_step to emulate ranks")
         world = self.part.world
+        timing = os.environ.get("FLUIDSOLVER_B200_TIMING", "0") != "0"
+        if timing:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
         count, _ = self.export_step(vx, vy, vz, sphi, lvol)
+        if timing:
+            ev[1].record()
         self._count.fill_(count)
         if world > 1:
             dist.all_gather_into_tensor(self._counts, self._count, group=self.group)
@@ -405,10 +411,24 @@ class GatheredViscosityCGSolver3D:
             self._recv = torch.empty(int(need * 1.25) + 64, dtype=torch.uint8, device=A.device())
         if world > 1 and stride > 0:
             dist.all_gather_into_tensor(self._recv[:need], self._send[: stride * self._rec], group=self.group)
+            if timing:
+                ev[2].record()
             self.import_step(self._recv, self._counts, stride)
         else:
+            if timing:
+                ev[2].record()
             self.import_step(self._send, self._counts, stride)  # one rank: its own block is skipped, only the list is rebuilt
-        self.finish_step(dt, mu, rho, tol)
+        if timing:
+            ev[3].record()
+        try:
+            self.finish_step(dt, mu, rho, tol)
+        finally:
+            if timing:
+                ev[4].record()
+                torch.cuda.synchronize()
+                self.timing = {"export_ms": ev[0].elapsed_time(ev[1]), "exchange_ms": ev[1].elapsed_time(ev[2]), "import_ms": ev[2].elapsed_time(ev[3]),
+                               "cg_and_store_ms": ev[3].elapsed_time(ev[4]), "records_sent": int(count), "stride": int(stride),
+                               "exchange_MB": need / 1e6}
 
 
 def emulate_gathered_solve(solvers, scenes_per_rank, dt, mu, rho, tol=1e-3):
@@ -558,6 +578,42 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
         return out
 
     trace(f"scene ready, mode={mode}")
+    hbm_variant = None
+    want_variant = bool(getattr(args, "hbm_leg", 1)) and aset == "nonzero"
+    slab_first = os.environ.get("FLUIDSOLVER_B200_SLAB_FIRST", "0") != "0"
+    # ---- HBM-bound variant of the same scene on slabs (every fluid row) -----------------------------------------------
+    def run_slab_variant():
+        no_clocks = os.environ.get("FLUIDSOLVER_B200_NOCLOCKS", "0") != "0"
+        s2, p2, sc2 = make("slab", "fluid")
+        trace(f"slab solver built, starts={p2.starts}")
+        s2.max_iter = args.iters
+        st2 = window_step(s2, sc2, sc2)
+        for _ in range(2):
+            st2()
+        trace("slab warm-up done")
+        nst = max(2, min(args.steps, 5))
+        if no_clocks:
+            ms2 = timed(st2, nst) / nst
+            clk = None
+        else:
+            with ClockSampler(local) as cl2:
+                ms2 = timed(st2, nst) / nst
+            clk = cl2.summary()
+        trace(f"slab timed: {ms2:.3f} ms/step")
+        par2 = parity(s2, p2, sc2, "fluid")
+        trace(f"slab parity: {par2}")
+        segs2 = s2._e.active_info()
+        out = {"what": "same scene and window, active_set='fluid' (every row the reference's kernels compute), x-slabs with fused collectives",
+               "value": args.iters / (ms2 * 1e-3), "unit": unit, "ms_per_step": ms2, "transport": s2.transport, "slab_starts": p2.starts,
+               "segments_rank0": segs2[0], "parity": par2, "clocks": clk}
+        s2.close()
+        del s2, sc2
+        torch.cuda.empty_cache()
+        return out
+
+    if want_variant and slab_first:
+        hbm_variant = run_slab_variant()
+
     # ---- the default workload ----------------------------------------------------------------------------------
     solver, part, sc = make(mode, aset)
     trace("solver built")
@@ -573,7 +629,7 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
     l0 = N.launch_count()
     with ClockSampler(local) as clocks:
         ms = timed(step, args.steps)
-    trace(f"timed: {ms / args.steps:.3f} ms/step")
+    trace(f"timed: {ms / args.steps:.3f} ms/step; timing of the last solve: {getattr(solver, 'timing', None)}")
     launches = N.launch_count() - l0
     value = args.iters * args.steps / (ms * 1e-3)
 
@@ -624,27 +680,8 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
     torch.cuda.empty_cache()
     trace("default leg closed")
 
-    # ---- HBM-bound variant of the same scene on slabs (every fluid row) -----------------------------------------------
-    hbm_variant = None
-    if getattr(args, "hbm_leg", 1) and aset == "nonzero":
-        s2, p2, sc2 = make("slab", "fluid")
-        trace(f"slab solver built, starts={p2.starts}")
-        s2.max_iter = args.iters
-        st2 = window_step(s2, sc2, sc2)
-        for _ in range(2):
-            st2()
-        trace("slab warm-up done")
-        with ClockSampler(local) as cl2:
-            ms2 = timed(st2, max(2, min(args.steps, 5))) / max(2, min(args.steps, 5))
-        trace(f"slab timed: {ms2:.3f} ms/step")
-        par2 = parity(s2, p2, sc2, "fluid")
-        trace(f"slab parity: {par2}")
-        segs2 = s2._e.active_info()
-        hbm_variant = {"what": "same scene and window, active_set='fluid' (every row the reference's kernels compute), x-slabs with fused collectives",
-                       "value": args.iters / (ms2 * 1e-3), "unit": unit, "ms_per_step": ms2, "transport": s2.transport, "slab_starts": p2.starts,
-                       "segments_rank0": segs2[0], "parity": par2, "clocks": cl2.summary()}
-        s2.close()
-        del s2, sc2
+    if want_variant and not slab_first:
+        hbm_variant = run_slab_variant()
 
     if rank == 0:
         F, V7 = counts(n)

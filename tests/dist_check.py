@@ -33,6 +33,12 @@ def main():
              # gathered solve: set-up sharded, records all-gathered over NCCL, CG replicated (transport column = "gathered")
              (48, 100.0, torch.float64, None, "gathered", "auto", "nonzero"), (32, 10.0, torch.float64, (67, 24, 28), "gathered", "auto", "fluid"),
              (48, 100.0, torch.float32, None, "gathered", "auto", "nonzero")]
+    repeat = 1
+    if os.environ.get("DIST_CHECK_BIG"):      # diagnostic sizes (HBM-sized slabs, several segments per warp), two solves per object
+        big = int(os.environ["DIST_CHECK_BIG"])
+        cases = [(big, 100.0, torch.float64, None, "p2p", m, "fluid") for m in ("persistent_sr", "persistent", "kernels_sr", "kernels")]
+        cases.append((big, 100.0, torch.float64, None, "gathered", "auto", "nonzero"))
+        repeat = 2
     for N, mu, dtype, g, transport, cg_mode, aset in cases:
         full = scenes.buckling(N, device="cuda", mu=mu, gres=g)
         gres = full["gres"]
@@ -43,11 +49,29 @@ def main():
             sc = scatter_scene(full, part)
             s = GatheredViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype, partition=part, cg_mode=cg_mode, active_set=aset)
         else:
-            part = SlabPartition(gres, world, rank)
+            cost = None
+            if os.environ.get("DIST_CHECK_BALANCED"):     # the cost-balanced (uneven) cuts bench.py uses
+                from solver.distributed import plane_cost_active
+                cost = plane_cost_active(full["sphi"], full["lvol"], gres, aset)
+            part = SlabPartition(gres, world, rank, plane_cost=cost)
+            if rank == 0 and cost is not None:
+                print(f"[dist_check] slab starts {part.starts}", flush=True)
             sc = scatter_scene(full, part)
-            s = SlabViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype, transport=transport, cg_mode=cg_mode, active_set=aset)
-        v = [sc[k].clone() for k in ("vx", "vy", "vz")]
-        s.solve(full["dt"], mu, full["rho"], *v, sc["sphi"], None, None, sc["lvol"])
+            s = SlabViscosityCGSolver3D(gres, full["bound_size"], dtype=dtype, transport=transport, cg_mode=cg_mode, active_set=aset, partition=part)
+        if os.environ.get("DIST_CHECK_WINDOWS"):          # bench.py's pattern: fixed 200-iteration windows (tol = 0) first
+            s.max_iter = 200
+            for _ in range(int(os.environ["DIST_CHECK_WINDOWS"])):
+                try:
+                    s.solve(full["dt"], mu, full["rho"], sc["vx"], sc["vy"], sc["vz"], sc["sphi"], None, None, sc["lvol"], tol=0.0)
+                except ValueError:
+                    pass
+        s.max_iter = 5000
+        for _ in range(repeat):
+            v = [sc[k].clone() for k in ("vx", "vy", "vz")]
+            try:
+                s.solve(full["dt"], mu, full["rho"], *v, sc["sphi"], None, None, sc["lvol"])
+            except ValueError:
+                pass                              # not converged within the cap: reported as a mismatch below
         its = torch.tensor([s.iterations], device="cuda")
         allits = [torch.zeros_like(its) for _ in range(world)]
         dist.all_gather(allits, its)
