@@ -513,7 +513,10 @@ def bench_distributed(args, metric, unit, config, peak, peak_src):
             part = SlabPartition(g, world, rank, ext=GatheredViscosityCGSolver3D.EXT)
             sol = GatheredViscosityCGSolver3D(g, bound, dtype=tdtype, partition=part, active_set=active_set, cg_mode=getattr(args, "cg_mode", "auto"))
         else:
-            part = SlabPartition(g, world, rank, plane_cost=plane_cost_active(full["sphi"], full["lvol"], g, active_set) if balance else None)
+            # cost of an x-plane = its share of the once-per-solve passes (1) + the CG work of its active rows: a fully active plane
+            # costs ~4.2 us per iteration against ~3.5 us of set-up per plane (measured on B200), i.e. weight ~ 1.2 x iterations
+            part = SlabPartition(g, world, rank, plane_cost=plane_cost_active(full["sphi"], full["lvol"], g, active_set, cg_weight=1.2 * args.iters)
+                                 if balance else None)
             sol = SlabViscosityCGSolver3D(g, bound, dtype=tdtype, partition=part, active_set=active_set, cg_mode=getattr(args, "cg_mode", "auto"))
         return sol, part, scatter_scene(full, part)
 
