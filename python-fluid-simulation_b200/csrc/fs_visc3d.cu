@@ -766,8 +766,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
 // cg_update_sr_seg_kernel).  Two kernels and ONE reduction per iteration instead of three and two; the persistent
 // form below has two grid barriers per iteration (one carrying the reduction) instead of three (two carrying one).
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool DIST>
-__global__ void __launch_bounds__(kK1Threads, K1Occ<T>::value) visc3d_apply_dot2_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ r, T* __restrict__ w /*[2][3][NL]*/,
+template <typename T, bool DIST, int OCC = K1Occ<T>::value>
+__global__ void __launch_bounds__(kK1Threads, OCC) visc3d_apply_dot2_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ r, T* __restrict__ w /*[2][3][NL]*/,
                                                                                         const int* __restrict__ seg, const int* __restrict__ nseg_p,
                                                                                         CgState* st_, double* partials, PeerInfo* peers, PeerHot hot, int freeze) {
     if (*(volatile int*)&st_->done) return;
@@ -1625,6 +1625,15 @@ static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
 }
 // single-reduction CG: K1s (w = A r, r.r, w.r, alpha/beta on the device) and K2s (p, s, x, r in one pass)
 static int visc3d_k1s(fs_visc3d* h, double sm, cudaStream_t s, int freeze = 0) {
+    static int occ_env = -1;                     // experiment hook: FLUIDSOLVER_B200_K1OCC=3 -> 3 CTAs/SM (85 registers) for the fp64 K1s
+    if (occ_env < 0) { const char* e = getenv("FLUIDSOLVER_B200_K1OCC"); occ_env = e ? atoi(e) : 0; }
+    if (occ_env == 3 && !h->peers && h->dtype == FS_F64) {
+        const int grid3 = seg_grid(h->seg.nseg, kK1SegsPerBlock, kSMs * 3);
+        visc3d_apply_dot2_kernel<double, false, 3><<<grid3, kK1Threads, 0, s>>>(dev_view<double>(h), sm, 2 * sm, vec_ptr<double>(h, FS_VEC_R), reinterpret_cast<double*>(h->d2),
+                                                                               h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot, freeze);
+        FS_LAUNCH_CHECK();
+        return FS_OK;
+    }
     const int cap = kSMs * (h->dtype == FS_F32 ? K1Occ<float>::value : K1Occ<double>::value);
     const int grid = seg_grid(h->seg.nseg, kK1SegsPerBlock, cap);
     if (h->peers) {
