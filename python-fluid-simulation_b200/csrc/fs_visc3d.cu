@@ -281,7 +281,7 @@ __device__ __forceinline__ void extrap_push(const ExtrapWork& W, int which, unsi
     if (lane == leader) base = atomicAdd(W.count + which, (unsigned int)__popc(m));
     base = __shfl_sync(m, base, leader);
     const unsigned int k = base + __popc(m & ((1u << lane) - 1u));
-    if (k < W.cap) W.list[which][k] = face;
+    if (k < W.cap) (which ? W.list[1] : W.list[0])[k] = face;      // (no dynamic index into the by-value struct: that is a stack copy)
     else W.count[2] = 1u;                          // overflow: the next sweep falls back to a full pass
 }
 
@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, T*
     if (only_if_overflow && (W.cap == 0u || W.count[2] == 0u)) return;
     const int nrows = L.X * L.Y;
     const unsigned int sw = (unsigned int)sweep;
+    const uint32_t swv = sw * 0x01010101u;           // (sweep <= 250: fits a byte)
     for (long long g = g_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < g_end; g += (long long)gridDim.x * blockDim.x) {
         const long long i4 = g * 4;
         if (rowflag) {
@@ -337,41 +338,61 @@ __global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, T*
         if (bytes_all_nonzero(own[0]) && bytes_all_nonzero(own[1]) && bytes_all_nonzero(own[2])) continue;
         int x, y, z0;
         lat_decode(L, i4, x, y, z0);
+        // the generation words of the four x/y neighbour groups and the two z-adjacent bytes, requested for all three
+        // components before any of them is looked at (one memory latency instead of three)
+        uint32_t nb[3][4];
+        unsigned int zl[3], zr[3];
+        bool need[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            if (bytes_all_nonzero(own[c])) continue;
             int s0, s1, s2;
             comp_shape(L, c, s0, s1, s2);
-            if (!(x >= 1 && x <= s0 - 2 && y >= 1 && y <= s1 - 2)) continue;
+            need[c] = !bytes_all_nonzero(own[c]) && x >= 1 && x <= s0 - 2 && y >= 1 && y <= s1 - 2;
+            const uint8_t* va = valid_all + c * L.NL + i4;
+            nb[c][0] = need[c] ? *reinterpret_cast<const uint32_t*>(va + L.sx) : 0u;
+            nb[c][1] = need[c] ? *reinterpret_cast<const uint32_t*>(va - L.sx) : 0u;
+            nb[c][2] = need[c] ? *reinterpret_cast<const uint32_t*>(va + L.sy) : 0u;
+            nb[c][3] = need[c] ? *reinterpret_cast<const uint32_t*>(va - L.sy) : 0u;
+            zl[c] = (need[c] && z0 > 0) ? va[-1] : 0u;
+            zr[c] = (need[c] && z0 + 4 < L.Zp) ? va[4] : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (!need[c]) continue;
+            // deep inside the solid every neighbour generation is 0: nothing can be filled (most groups that get here)
+            if ((nb[c][0] | nb[c][1] | nb[c][2] | nb[c][3] | own[c] | zl[c] | zr[c]) == 0u) continue;
+            int s0, s1, s2;
+            comp_shape(L, c, s0, s1, s2);
             T* v = v_all + c * L.NL;
             uint8_t* va = valid_all + c * L.NL;
-            const uint32_t xp = *reinterpret_cast<const uint32_t*>(va + i4 + L.sx), xm = *reinterpret_cast<const uint32_t*>(va + i4 - L.sx);
-            const uint32_t yp = *reinterpret_cast<const uint32_t*>(va + i4 + L.sy), ym = *reinterpret_cast<const uint32_t*>(va + i4 - L.sy);
-            const unsigned int zl = z0 > 0 ? va[i4 - 1] : 0u;
-            const unsigned int zr = z0 + 4 < L.Zp ? va[i4 + 4] : 0u;
-            auto ok = [&](unsigned int gg) { return gg >= 1u && gg <= sw; };
+            // Which of the four faces can be filled is decided on whole words (byte-wise SIMD compares: 0xff where the
+            // generation g satisfies 1 <= g <= sweep), so a warp that only grazes the fluid/solid interface — nearly every warp
+            // that gets here — pays one short loop trip per candidate instead of the fully unrolled 4-face body.
+            auto okw = [&](uint32_t w) { return __vcmpgeu4(w, 0x01010101u) & __vcmpleu4(w, swv); };
+            auto okb = [&](unsigned int gg) { return gg >= 1u && gg <= sw; };
+            const uint32_t oxp = okw(nb[c][0]), oxm = okw(nb[c][1]), oyp = okw(nb[c][2]), oym = okw(nb[c][3]);
+            const uint32_t oown = okw(own[c]);
+            const uint32_t ozp = (oown >> 8) | (okb(zr[c]) ? 0xff000000u : 0u);       // byte k: face k+1 of the group, or the next group's first
+            const uint32_t ozm = (oown << 8) | (okb(zl[c]) ? 0x000000ffu : 0u);       // byte k: face k-1, or the previous group's last
+            uint32_t cand = __vcmpeq4(own[c], 0u) & (oxp | oxm | oyp | oym | ozp | ozm);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int z = z0 + k;
-                if (((own[c] >> (8 * k)) & 0xffu) != 0u || !(z >= 1 && z <= s2 - 2)) continue;
-                const long long i = i4 + k;
-                const unsigned int gxp = (xp >> (8 * k)) & 0xffu, gxm = (xm >> (8 * k)) & 0xffu;
-                const unsigned int gyp = (yp >> (8 * k)) & 0xffu, gym = (ym >> (8 * k)) & 0xffu;
-                const unsigned int gzp = k < 3 ? (own[c] >> (8 * (k < 3 ? k + 1 : 0))) & 0xffu : zr;
-                const unsigned int gzm = k > 0 ? (own[c] >> (8 * (k > 0 ? k - 1 : 0))) & 0xffu : zl;
+            for (int k = 0; k < 4; ++k)
+                if (!(z0 + k >= 1 && z0 + k <= s2 - 2)) cand &= ~(0xffu << (8 * k));
+            while (cand) {
+                const int sh = (__ffs((int)cand) - 1) & ~7;
+                cand &= ~(0xffu << sh);
+                const long long i = i4 + (sh >> 3);
                 T val = T(0);
-                int count = 0;                            // +x,-x,+y,-y,+z,-z  (:19-36)
-                if (ok(gxp)) { val += v[i + L.sx]; ++count; }
-                if (ok(gxm)) { val += v[i - L.sx]; ++count; }
-                if (ok(gyp)) { val += v[i + L.sy]; ++count; }
-                if (ok(gym)) { val += v[i - L.sy]; ++count; }
-                if (ok(gzp)) { val += v[i + 1]; ++count; }
-                if (ok(gzm)) { val += v[i - 1]; ++count; }
-                if (count > 0) {
-                    v[i] = val / (T)count;
-                    va[i] = (uint8_t)(sweep + 1);
-                    if (push_to >= 0) extrap_push(W, push_to, (unsigned int)(c * L.NL + i));
-                }
+                int count = 0;                                // +x,-x,+y,-y,+z,-z  (:19-36)
+                if ((oxp >> sh) & 1u) { val += v[i + L.sx]; ++count; }
+                if ((oxm >> sh) & 1u) { val += v[i - L.sx]; ++count; }
+                if ((oyp >> sh) & 1u) { val += v[i + L.sy]; ++count; }
+                if ((oym >> sh) & 1u) { val += v[i - L.sy]; ++count; }
+                if ((ozp >> sh) & 1u) { val += v[i + 1]; ++count; }
+                if ((ozm >> sh) & 1u) { val += v[i - 1]; ++count; }
+                v[i] = val / (T)count;
+                va[i] = (uint8_t)(sweep + 1);
+                if (push_to >= 0) extrap_push(W, push_to, (unsigned int)(c * L.NL + i));
             }
         }
     }
@@ -385,21 +406,21 @@ __global__ void __launch_bounds__(kThreads) visc3d_extrapolate_list_kernel(Lat3 
     if (W.count[2] != 0u) return;                  // overflowed: the full-pass fall-back does this sweep
     const unsigned int n = W.count[from];
     const unsigned int sw = (unsigned int)sweep;
-    const long long off[6] = {L.sx, -L.sx, L.sy, -L.sy, 1, -1};
-    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const unsigned int face = W.list[from][e];
+    // one thread per (recorded face, direction): the six probes of a face are independent memory round trips
+    const unsigned long long n6 = 6ull * n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long e6 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e6 < n6; e6 += stride) {
+        const unsigned int e = (unsigned int)(e6 / 6ull), k = (unsigned int)(e6 - 6ull * e);
+        const unsigned int face = (from ? W.list[1] : W.list[0])[e];
         const int c = (int)(face / (unsigned int)L.NL);
         const long long i = (long long)(face - (unsigned int)c * (unsigned int)L.NL);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const long long j = i + off[k];
-            if (j < 0 || j >= L.NL) continue;
-            if (valid_all[c * L.NL + j] != 0) continue;
-            int x, y, z;
-            lat_decode(L, j, x, y, z);
-            if (extrap_try_fill<T>(L, v_all, valid_all, c, j, x, y, z, sw) && push_to >= 0)
-                extrap_push(W, push_to, (unsigned int)(c * L.NL + j));
-        }
+        const long long step = k < 2u ? L.sx : k < 4u ? L.sy : 1;
+        const long long j = (k & 1u) ? i - step : i + step;
+        if (j < 0 || j >= L.NL) continue;
+        if (valid_all[c * L.NL + j] != 0) continue;
+        int x, y, z;
+        lat_decode(L, j, x, y, z);
+        if (extrap_try_fill<T>(L, v_all, valid_all, c, j, x, y, z, sw) && push_to >= 0)
+            extrap_push(W, push_to, (unsigned int)(c * L.NL + j));
     }
 }
 
@@ -1566,7 +1587,7 @@ int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
         } else {
             const int from = (k - 2) & 1;
             if (push_to >= 0) FS_CUDA(cudaMemsetAsync(W.count + push_to, 0, sizeof(unsigned int), s));
-            FS_DISPATCH(h, visc3d_extrapolate_list_kernel<T><<<kSMs * 4, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, from, push_to));
+            FS_DISPATCH(h, visc3d_extrapolate_list_kernel<T><<<kSMs * 16, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, from, push_to));
             FS_LAUNCH_CHECK();
             FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<kSMs * 8, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, -1, 1, nullptr, g_begin, g_end));   // only if a list overflowed
             FS_LAUNCH_CHECK();
