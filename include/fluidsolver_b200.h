@@ -95,6 +95,13 @@ int fs_abi_version(void);
 const char* fs_last_error(void);
 /* number of kernels this library has launched in the calling process (bench bookkeeping) */
 int64_t fs_launch_count(void);
+/* Tuning switches of the kernels (the programmatic form of the FLUIDSOLVER_B200_* environment variables; they select between
+ * result-equivalent implementations and never change what is computed).  value < 0 restores the default.
+ *   "resident_form" : 0 = persistent CG through global memory, 1 / 2 = first / second shared-memory resident kernel
+ *   "llred"         : 0 / 1 = counter-based / flag-in-data grid reduction in the second resident kernel
+ *   "k1_prefetch"   : 0 / 1 = L2 prefetch of the next segment in the stand-alone K1s (HBM-sized active sets)
+ * Returns FS_OK, or FS_ERR_ARG for an unknown name. */
+int fs_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------
  * Viscosity, 3-D  (ViscosityCGSolver3D)

@@ -191,9 +191,30 @@ void CgHost::destroy() {
     }
 }
 
+// tuning switches: explicit setting (fs_set_option) > environment variable > built-in default (-1)
+static int g_opt[OPT_COUNT] = {-2, -2, -2};
+static const char* const kOptEnv[OPT_COUNT] = {"FLUIDSOLVER_B200_RESIDENT", "FLUIDSOLVER_B200_LLRED", "FLUIDSOLVER_B200_K1PF"};
+static const char* const kOptName[OPT_COUNT] = {"resident_form", "llred", "k1_prefetch"};
+
+int tuning(int which) {
+    if (which < 0 || which >= OPT_COUNT) return -1;
+    if (g_opt[which] == -2) {
+        const char* e = getenv(kOptEnv[which]);
+        g_opt[which] = (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : -1;
+    }
+    return g_opt[which];
+}
+
 }  // namespace fs
 
 extern "C" {
+
+int fs_set_option(const char* name, int value) {
+    if (!name) return fs::fail(FS_ERR_ARG, "fs_set_option: null name");
+    for (int k = 0; k < fs::OPT_COUNT; ++k)
+        if (strcmp(name, fs::kOptName[k]) == 0) { fs::g_opt[k] = value < 0 ? -1 : value; return FS_OK; }
+    return fs::fail(FS_ERR_ARG, "fs_set_option: unknown option '%s'", name);
+}
 
 int fs_abi_version(void) { return FS_ABI_VERSION; }
 const char* fs_last_error(void) { return fs::g_err; }

@@ -47,6 +47,8 @@ template <typename T> struct Visc3Dev {
     const uint8_t* act;      // per lattice point: bit c set <=> row c is computed (same information as the NaN tags, 1 byte)
 };
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void lat_decode(const Lat3& L, long long i, int& x, int& y, int& z) {
     if (L.NL < 0x7fffffffLL) {                       // 32-bit divisions (the common case) are several times cheaper
         const unsigned int u = (unsigned int)i, zp = (unsigned int)L.Zp, yy = (unsigned int)L.Y;
@@ -630,6 +632,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_scale_kernel(Visc3Dev<T> P, T
 // (fixed order, deterministic).
 // ---------------------------------------------------------------------------------------------
 constexpr int kK1Threads = 256;
+constexpr int kK1PrefetchDefault = 0;     // L2 prefetch of the next trip in the stand-alone K1s when FLUIDSOLVER_B200_K1PF is not set
 constexpr int kK1SegsPerBlock = kK1Threads / 32;
 // CTAs per SM: the fp64 body keeps 43 loaded values (86 registers) in flight, so it gets 128 registers per thread
 // (2 CTAs/SM); with an 80-register cap (3 CTAs/SM) ptxas split the loads into dependent phases and the dense-scene
@@ -644,7 +647,7 @@ template <> struct K1Occ<float> { static constexpr int value = 3; };
 // rows, and the boundary rows go to the neighbours' w planes instead of their q planes.
 template <typename T, bool DIST, bool COHERENT, bool SR = false>
 __device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T s, T s2, const T* d, T* q, const int* __restrict__ seg, int nseg,
-                                                        const PeerHot& hot, bool& wrote_peer, double* acc2_out = nullptr, int par = 0) {
+                                                        const PeerHot& hot, bool& wrote_peer, double* acc2_out = nullptr, int par = 0, int pf = 0) {
     const Lat3& L = P.L;
     const long long NL = L.NL;
     const long long st[3] = {L.sx, L.sy, 1};
@@ -659,6 +662,17 @@ __device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T 
         {
             const long long k2 = k + nw;
             sg_n = k2 < nseg ? __ldg(seg + k2) : 0;
+        }
+        if (pf) {
+            // HBM-sized lists: pull the lines the NEXT trip of this warp touches first into L2 now (hint only, no register
+            // held, no warp stalled): its seven coefficient words and the x+1 plane of d, i.e. everything of that trip that
+            // no earlier trip has requested yet.  The trip then waits for L2, not for DRAM.
+            const long long ip = (long long)sg_n * kSegPts + lane;
+            if (ip < NL) {
+                prefetch_l2(P.cs[0] + ip); prefetch_l2(P.cs[1] + ip); prefetch_l2(P.cs[2] + ip); prefetch_l2(P.cs[3] + ip);
+                prefetch_l2(P.cs[4] + ip + L.sx); prefetch_l2(P.cs[5] + ip + L.sx); prefetch_l2(P.cs[6] + ip + L.sy);
+                prefetch_l2(d + ip + L.sx); prefetch_l2(d + NL + ip + L.sx); prefetch_l2(d + 2 * NL + ip + L.sx);
+            }
         }
         const bool in = i < NL;
         const long long j = in ? i : (NL - 1);
@@ -790,13 +804,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
 template <typename T, bool DIST, int OCC = K1Occ<T>::value>
 __global__ void __launch_bounds__(kK1Threads, OCC) visc3d_apply_dot2_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ r, T* __restrict__ w /*[2][3][NL]*/,
                                                                                         const int* __restrict__ seg, const int* __restrict__ nseg_p,
-                                                                                        CgState* st_, double* partials, PeerInfo* peers, PeerHot hot, int freeze) {
+                                                                                        CgState* st_, double* partials, PeerInfo* peers, PeerHot hot, int freeze, int pf) {
     if (*(volatile int*)&st_->done) return;
     bool wrote_peer = false;
     double rr = 0.0;
     const int par = DIST ? (int)(st_->iter & 1) : 0;           // (st->iter is stable here: only the update kernel advances it)
     w += (long long)par * 3 * P.L.NL;
-    const double wr = visc3d_apply_dot_body<T, DIST, false, true>(P, s, s2, r, w, seg, *nseg_p, hot, wrote_peer, &rr, par);
+    const double wr = visc3d_apply_dot_body<T, DIST, false, true>(P, s, s2, r, w, seg, *nseg_p, hot, wrote_peer, &rr, par, pf);
     const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
     grid_sum2_finish(rr, wr, partials, &st_->counter[0], [=](double gamma, double dl) {
         if (freeze) return;                      // profiling hook: repeated launches leave the CG state alone
@@ -1053,6 +1067,191 @@ __global__ void __launch_bounds__(THREADS, 1) visc3d_cg_sr_resident_kernel(Visc3
 }
 
 // ---------------------------------------------------------------------------------------------
+// Second form of the resident kernel: the residual of the CTA's own points is kept in shared memory as well (31 values per
+// point), and so are the segment ids, so phase B touches global memory only to STORE the new r for the neighbours' stencils —
+// no dependent L2 read in it any more (the first form spends two sequential round trips there: segment id, then r, per
+// trip).  Slots are addressed by the position of a segment in the CTA's run, so exactly `chunk` slots are needed: 29 of
+// 7 972 B for the 4 253 segments of the 256^3 benchmark scene = 231 KB of the 227 KiB an SM offers.  Positions beyond
+// `res_slots` (longer lists) run through global memory as before.  LL = the flag-in-data reduction (grid_allreduce2_ll).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRes2Vals = 31;     // per point: 16 coefficients, p[3], s[3], w[3], x[3], r[3]
+constexpr int kResidentFormDefault = 1;   // which resident kernel runs when FLUIDSOLVER_B200_RESIDENT is not set
+constexpr bool kLLRedDefault = false;     // flag-in-data reduction when FLUIDSOLVER_B200_LLRED is not set
+constexpr int kRes2Threads = 512;
+template <typename T> __host__ __device__ constexpr size_t res2_slot_bytes() { return (size_t)kRes2Vals * 32 * sizeof(T) + 32 + sizeof(int); }
+
+template <typename T, bool LL>
+__global__ void __launch_bounds__(kRes2Threads, 1) visc3d_cg_sr_resident2_kernel(Visc3Dev<T> P, T* x, T* r, T* p, T* sv, T* w,
+                                                                                        const int* __restrict__ seg, const int* __restrict__ nseg_p,
+                                                                                        CgState* st, double* partials, GridBar* bar, int n_slots, int res_slots,
+                                                                                        LLRed ll, unsigned long long* prof) {
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    constexpr int kWarps = kRes2Threads / 32;
+    T* const svals = reinterpret_cast<T*>(res_smem);                                            // [res_slots][kRes2Vals][32]
+    uint8_t* const sact = res_smem + (size_t)res_slots * kRes2Vals * 32 * sizeof(T);            // [res_slots][32]
+    int* const sseg = reinterpret_cast<int*>(sact + (size_t)res_slots * 32);                    // [res_slots]
+    const Lat3& L = P.L;
+    const long long NL = L.NL;
+    const long long stv[3] = {L.sx, L.sy, 1};
+    const int nseg = *nseg_p;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // contiguous run of the (lattice-ordered) active list per CTA; position li of the run belongs to warp li % kWarps
+    const long long chunk = ((long long)nseg + gridDim.x - 1) / gridDim.x;
+    const long long c_lo = (long long)blockIdx.x * chunk;
+    const int n_own = (int)((c_lo + chunk < nseg ? c_lo + chunk : (long long)nseg) - c_lo);     // (<= 0 for CTAs past the end of the list)
+
+    // ---- prologue: point-private data of the resident positions -> shared memory
+    for (int li = warp; li < n_own && li < res_slots; li += kWarps) {
+        const int sg = __ldg(seg + c_lo + li);
+        const long long i = (long long)sg * kSegPts + lane;
+        const bool in = i < NL;
+        const long long jj = in ? i : (NL - 1);
+        T* S = svals + ((size_t)li * kRes2Vals) * 32 + lane;
+        S[0 * 32] = __ldg(P.cs[0] + jj); S[1 * 32] = __ldg(P.cs[1] + jj); S[2 * 32] = __ldg(P.cs[2] + jj);
+        S[3 * 32] = __ldg(P.cs[3] + jj);
+        S[4 * 32] = __ldg(P.cs[3] + jj - stv[0]); S[5 * 32] = __ldg(P.cs[3] + jj - stv[1]); S[6 * 32] = __ldg(P.cs[3] + jj - stv[2]);
+        S[7 * 32] = __ldg(P.cs[4] + jj); S[8 * 32] = __ldg(P.cs[4] + jj + stv[1]); S[9 * 32] = __ldg(P.cs[4] + jj + stv[0]);
+        S[10 * 32] = __ldg(P.cs[5] + jj); S[11 * 32] = __ldg(P.cs[5] + jj + stv[2]); S[12 * 32] = __ldg(P.cs[5] + jj + stv[0]);
+        S[13 * 32] = __ldg(P.cs[6] + jj); S[14 * 32] = __ldg(P.cs[6] + jj + stv[2]); S[15 * 32] = __ldg(P.cs[6] + jj + stv[1]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            S[(16 + c) * 32] = in ? p[c * NL + i] : T(0);
+            S[(19 + c) * 32] = in ? sv[c * NL + i] : T(0);
+            S[(22 + c) * 32] = T(0);
+            S[(25 + c) * 32] = in ? x[c * NL + i] : T(0);
+            S[(28 + c) * 32] = in ? r[c * NL + i] : T(0);
+        }
+        sact[(size_t)li * 32 + lane] = in ? (uint8_t)((unsigned int)__ldg(P.act + i) & kActCompute) : (uint8_t)0;
+        if (lane == 0) sseg[li] = sg;
+    }
+    __syncwarp();
+
+    double delta = st->delta, gamma_old = st->delta_old, dl = st->dq, alpha_d = st->alpha, beta_d = st->beta;
+    bool first = st->sr_first != 0;
+    const double tol2 = st->tol2;
+    long long iter = st->iter;
+    const long long max_iter = st->max_iter;
+    int done = st->done;
+    GridSync gs{bar, 0u};
+    const bool stamp = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    int np = 0;
+    auto tick = [&]() {
+        if (stamp && np < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); prof[np++] = t; }
+    };
+    auto nb = [&](int comp, long long j) -> T { return r[comp * NL + j]; };      // coherent: other CTAs rewrote r before the last barrier
+    for (int it = 0; it < n_slots && !done; ++it) {
+        tick();
+        // ---- phase A: w = A r, (r.r, w.r)
+        double rr = 0.0, wr = 0.0;
+        for (int li = warp; li < n_own; li += kWarps) {
+            const bool res = li < res_slots;
+            const int sg = res ? sseg[li] : __ldg(seg + c_lo + li);
+            const long long i = (long long)sg * kSegPts + lane;
+            const bool in = i < NL;
+            const long long jj = in ? i : (NL - 1);
+            const T du = nb(0, jj), dv = nb(1, jj), dw = nb(2, jj);
+            T ru, rv, rw;
+            unsigned int a;
+            if (res) {
+                T* S = svals + ((size_t)li * kRes2Vals) * 32 + lane;
+                a = sact[(size_t)li * 32 + lane];
+                auto cf = [&](int plane, int axis, int sign) -> T { return S[visc3_cslot(plane, axis, sign) * 32]; };
+                ru = visc_row_scaled_cf<T, 3, 0>(jj, stv, S[0 * 32], du, cf, nb);
+                rv = visc_row_scaled_cf<T, 3, 1>(jj, stv, S[1 * 32], dv, cf, nb);
+                rw = visc_row_scaled_cf<T, 3, 2>(jj, stv, S[2 * 32], dw, cf, nb);
+                S[22 * 32] = (a & 1u) ? ru : T(0);          // w stays in shared memory (zero on rows that are not computed)
+                S[23 * 32] = (a & 2u) ? rv : T(0);
+                S[24 * 32] = (a & 4u) ? rw : T(0);
+            } else {
+                a = in ? ((unsigned int)__ldg(P.act + i) & kActCompute) : 0u;
+                ru = visc_row_scaled<T, 3, 0>(P.cs, jj, stv, __ldg(P.cs[0] + jj), du, nb);
+                rv = visc_row_scaled<T, 3, 1>(P.cs, jj, stv, __ldg(P.cs[1] + jj), dv, nb);
+                rw = visc_row_scaled<T, 3, 2>(P.cs, jj, stv, __ldg(P.cs[2] + jj), dw, nb);
+                if (a & 1u) w[i] = ru;
+                if (a & 2u) w[NL + i] = rv;
+                if (a & 4u) w[2 * NL + i] = rw;
+            }
+            if (a & 1u) { wr += (double)du * (double)ru; rr += (double)du * (double)du; }
+            if (a & 2u) { wr += (double)dv * (double)rv; rr += (double)dv * (double)dv; }
+            if (a & 4u) { wr += (double)dw * (double)rw; rr += (double)dw * (double)dw; }
+        }
+        tick();
+        if constexpr (LL) grid_allreduce2_ll(rr, wr, ll);
+        else grid_allreduce2(rr, wr, partials, gs);
+        tick();
+        delta = rr;
+        if (rr < tol2) done = 1;
+        else if (iter >= max_iter || !(rr == rr)) done = 2;
+        if (done) break;
+        dl = wr;
+        {
+            double a, b;
+            cg_sr_scalars(rr, wr, gamma_old, alpha_d, first, a, b);
+            alpha_d = a; beta_d = b;
+        }
+        gamma_old = rr;
+        first = false;
+        // ---- phase B: p = r + beta p, s = w + beta s, x += alpha p, r -= alpha s
+        {
+            const T alpha = (T)alpha_d, beta = (T)beta_d;
+            for (int li = warp; li < n_own; li += kWarps) {
+                if (li < res_slots) {                 // everything from shared memory; the new r also goes out for the neighbours
+                    const long long i = (long long)sseg[li] * kSegPts + lane;
+                    const bool in = i < NL;
+                    T* S = svals + ((size_t)li * kRes2Vals) * 32 + lane;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const T rc = S[(28 + c) * 32];
+                        const T pn = rc + beta * S[(16 + c) * 32];
+                        const T sn = S[(22 + c) * 32] + beta * S[(19 + c) * 32];
+                        const T rn = rc - alpha * sn;
+                        S[(16 + c) * 32] = pn;
+                        S[(19 + c) * 32] = sn;
+                        S[(25 + c) * 32] += alpha * pn;
+                        S[(28 + c) * 32] = rn;
+                        if (in) r[c * NL + i] = rn;
+                    }
+                } else {                              // beyond the resident positions: through global memory
+                    const long long i = (long long)__ldg(seg + c_lo + li) * kSegPts + lane;
+                    if (i >= NL) continue;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const long long e = c * NL + i;
+                        const T rc = r[e];
+                        const T pn = rc + beta * p[e];
+                        const T sn = w[e] + beta * sv[e];
+                        p[e] = pn;
+                        sv[e] = sn;
+                        x[e] += alpha * pn;
+                        r[e] = rc - alpha * sn;
+                    }
+                }
+            }
+        }
+        iter += 1;
+        tick();
+        gs.sync();
+        tick();
+    }
+    // ---- epilogue: the resident p, s, x go back to global memory (w is scratch, r is current there already)
+    for (int li = warp; li < n_own && li < res_slots; li += kWarps) {
+        const long long i = (long long)sseg[li] * kSegPts + lane;
+        if (i >= NL) continue;
+        const T* S = svals + ((size_t)li * kRes2Vals) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            p[c * NL + i] = S[(16 + c) * 32];
+            sv[c * NL + i] = S[(19 + c) * 32];
+            x[c * NL + i] = S[(25 + c) * 32];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->delta = delta; st->delta_old = gamma_old; st->dq = dl; st->alpha = alpha_d; st->beta = beta_d;
+        st->iter = iter; st->done = done; st->sr_first = first ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Gathered multi-GPU solve (L2-sized active sets): every rank packs / loads / extrapolates only its own x-window of the
 // GLOBAL lattice, then the ranks exchange just the lattice segments the CG touches — the active segments of the planes a
 // rank owns plus every segment their stencils read — and each rank runs the whole (small) CG locally, with no
@@ -1176,6 +1375,8 @@ struct fs_visc3d {
     bool windowed;       // pack / load / extrapolation work on the x-window L.wlo..L.whi of the lattice only
     uint8_t* xflags;     // [segments] publish flags of the current solve
     SegList xseg;        // segments this rank publishes (built from xflags)
+    unsigned long long* ll_slots;   // flag-in-data reduction slots (grid_allreduce2_ll), zero at creation, never reset in normal use
+    unsigned int ll_seq;            // last sequence number handed to a launch
 };
 
 // threads of the one-block-per-lattice-row kernels: a whole number of warps covering the row once, at most 512
@@ -1195,7 +1396,7 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     return L;
 }
 
-struct Visc3Layout { size_t coefs, xflags, xlist, xscratch, rownz; size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
+struct Visc3Layout { size_t coefs, xflags, xlist, xscratch, rownz, llred; size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -1234,6 +1435,7 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     o.xlist = p; p = align_up(p + SegList::list_bytes(L.NL), 256);
     o.xscratch = p; p = align_up(p + SegList::scratch_bytes(L.NL), 256);
     o.rownz = p; p = align_up(p + (size_t)L.X * L.Y, 256);
+    o.llred = p; p = align_up(p + kLLRedBytes, 256);
     o.total = p;
     return o;
 }
@@ -1466,6 +1668,8 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     s = h->xseg.init(h->L.NL, h->ws + lay.xlist, h->ws + lay.xscratch);
     if (s < 0) { h->cg.destroy(); h->seg.destroy(); delete h; return s; }
     h->xflags = (uint8_t*)(h->ws + lay.xflags);
+    h->ll_slots = (unsigned long long*)(h->ws + lay.llred);
+    h->ll_seq = 0;
     h->windowed = false;
     h->cg.st_dev = h->st; h->cg.partials_dev = h->partials;
     cudaError_t e = cudaMemset(ws, 0, lay.total);     // cp.zeros semantics for every solver vector
@@ -1648,19 +1852,23 @@ static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
 static int visc3d_k1s(fs_visc3d* h, double sm, cudaStream_t s, int freeze = 0) {
     static int occ_env = -1;                     // experiment hook: FLUIDSOLVER_B200_K1OCC=3 -> 3 CTAs/SM (85 registers) for the fp64 K1s
     if (occ_env < 0) { const char* e = getenv("FLUIDSOLVER_B200_K1OCC"); occ_env = e ? atoi(e) : 0; }
+    // L2 prefetch of the next trip (FLUIDSOLVER_B200_K1PF=0/1): only pays when the list is HBM-sized
+    const int pf_opt = tuning(OPT_K1PF);
+    const int pf_on = pf_opt < 0 ? kK1PrefetchDefault : pf_opt;       // 2 = also on lists that fit in L2 (tests)
+    const int pf = (pf_on == 2 || (pf_on == 1 && (double)h->seg.nseg * kSegPts * (13.0 * h->esz) > 64e6)) ? 1 : 0;
     if (occ_env == 3 && !h->peers && h->dtype == FS_F64) {
         const int grid3 = seg_grid(h->seg.nseg, kK1SegsPerBlock, kSMs * 3);
         visc3d_apply_dot2_kernel<double, false, 3><<<grid3, kK1Threads, 0, s>>>(dev_view<double>(h), sm, 2 * sm, vec_ptr<double>(h, FS_VEC_R), reinterpret_cast<double*>(h->d2),
-                                                                               h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot, freeze);
+                                                                               h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot, freeze, pf);
         FS_LAUNCH_CHECK();
         return FS_OK;
     }
     const int cap = kSMs * (h->dtype == FS_F32 ? K1Occ<float>::value : K1Occ<double>::value);
     const int grid = seg_grid(h->seg.nseg, kK1SegsPerBlock, cap);
     if (h->peers) {
-        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, h->peers, h->hot, freeze));
+        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, h->peers, h->hot, freeze, pf));
     } else {
-        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot, freeze));
+        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot, freeze, pf));
     }
     FS_LAUNCH_CHECK();
     return FS_OK;
@@ -1743,9 +1951,6 @@ static bool visc3d_use_persistent(const fs_visc3d* h) {
 // Shared-memory resident form of the single-reduction persistent kernel (single GPU / gathered solve; FLUIDSOLVER_B200_RESIDENT=0
 // switches it off).  Returns 1 if it cannot run here (nothing enqueued), so that the caller falls back.
 static int visc3d_persistent_resident(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
-    static int env = -2;
-    if (env == -2) { const char* e = getenv("FLUIDSOLVER_B200_RESIDENT"); env = !e ? -1 : (e[0] == '0' ? 0 : 1); }
-    if (env == 0) return 1;
     int dev = 0, smem_max = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 1;
     const void* fn = nullptr;
@@ -1794,12 +1999,81 @@ static int visc3d_persistent_resident(fs_visc3d* h, double sm, long long n, cuda
     return FS_OK;
 }
 
+// Second resident form (visc3d_cg_sr_resident2_kernel: r resident as well, slots by run position, optional flag-in-data
+// reduction).  FLUIDSOLVER_B200_RESIDENT=1 keeps the first form, FLUIDSOLVER_B200_LLRED=0 the counter-based reduction.
+// Returns 1 if it cannot run here (nothing enqueued).
+static int resident_form() {
+    const int v = tuning(OPT_RESIDENT_FORM);
+    return v < 0 ? kResidentFormDefault : v;
+}
+static bool llred_enabled() {
+    const int v = tuning(OPT_LLRED);
+    return v < 0 ? kLLRedDefault : v != 0;
+}
+
+static int visc3d_persistent_resident2(fs_visc3d* h, long long n, cudaStream_t s) {
+    int dev = 0, smem_max = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 1;
+    const bool ll = llred_enabled();
+    const void* fn = nullptr;
+    size_t slot = 0;
+    FS_DISPATCH(h, { fn = ll ? (const void*)visc3d_cg_sr_resident2_kernel<T, true> : (const void*)visc3d_cg_sr_resident2_kernel<T, false>; slot = res2_slot_bytes<T>(); });
+    const int kWarps = kRes2Threads / 32;
+    const int max_slots = (int)(((size_t)smem_max - 1024) / slot);                  // 1 KB left for the static reduction scratch
+    if (max_slots < 1) return 1;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_slots * slot)) != cudaSuccess) { cudaGetLastError(); return 1; }
+    const int cap = coop_max_blocks(fn, kRes2Threads, max_slots * slot);
+    if (cap < 1) return 1;
+    int grid = seg_grid(h->seg.nseg, kWarps, cap < kSMs ? cap : kSMs);
+    if (const char* e = getenv("FLUIDSOLVER_B200_PERSIST_GRID")) { const int g = atoi(e); if (g >= 1 && g <= cap) grid = g; }
+    if (grid > kLLMaxBlocks) grid = kLLMaxBlocks;
+    const long long chunk = ((long long)h->seg.nseg + grid - 1) / grid;             // run length per CTA
+    int res_slots = (int)(chunk < max_slots ? chunk : max_slots);
+    if (res_slots < 1) res_slots = 1;
+    const size_t smem = (size_t)res_slots * slot;
+    unsigned long long* prof = getenv("FLUIDSOLVER_B200_PROFILE") ? reinterpret_cast<unsigned long long*>(h->valid) : nullptr;
+    while (n > 0) {
+        int ni = (int)(n < (1 << 20) ? n : (1 << 20));
+        cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);
+        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+        if (h->ll_seq > 0xE0000000u) {               // sequence numbers about to wrap: start over on clean slots
+            e = cudaMemsetAsync(h->ll_slots, 0, kLLRedBytes, s);
+            if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+            h->ll_seq = 0;
+        }
+        LLRed llr;
+        llr.slots = h->ll_slots;
+        llr.seq = h->ll_seq;
+        h->ll_seq += (unsigned int)ni + 2u;          // a launch performs at most ni reductions
+        FS_DISPATCH(h, {
+            Visc3Dev<T> P = dev_view<T>(h);
+            T* x = vec_ptr<T>(h, FS_VEC_X); T* r = vec_ptr<T>(h, FS_VEC_R); T* d = vec_ptr<T>(h, FS_VEC_D); T* q = vec_ptr<T>(h, FS_VEC_Q);
+            T* w = reinterpret_cast<T*>(h->d2);
+            const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
+            CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
+            void* args[] = {&P, &x, &r, &d, &q, &w, &seg, &nsegp, &st, &partials, &bar, &ni, &res_slots, &llr, &prof};
+            e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kRes2Threads), args, smem, s);
+        });
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported || e == cudaErrorInvalidValue) {
+            cudaGetLastError();
+            return 1;
+        }
+        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
+        FS_LAUNCH_CHECK();
+        n -= ni;
+    }
+    return FS_OK;
+}
+
 static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
     const bool sr = visc3d_use_sr(h);
     if (sr && !h->peers && !h->resident_failed) {
-        const int st = visc3d_persistent_resident(h, sm, n, s);
+        const int form = resident_form();
+        int st = 1;
+        if (form == 2) st = visc3d_persistent_resident2(h, n, s);
+        if (st == 1 && form != 0) st = visc3d_persistent_resident(h, sm, n, s);
         if (st != 1) return st;
-        h->resident_failed = true;              // not possible on this context: the global-memory form below takes over
+        if (form != 0) h->resident_failed = true;   // not possible on this context: the global-memory form below takes over
     }
     const void* fn = nullptr;
     FS_DISPATCH(h, fn = sr ? (h->peers ? (const void*)visc3d_cg_sr_persistent_kernel<T, true> : (const void*)visc3d_cg_sr_persistent_kernel<T, false>)

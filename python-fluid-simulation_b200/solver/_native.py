@@ -36,6 +36,7 @@ _SIGS = {
     "fs_abi_version": (c_int, []),
     "fs_last_error": (c_char_p, []),
     "fs_launch_count": (c_int64, []),
+    "fs_set_option": (c_int, [c_char_p, c_int]),
     # viscosity 3-D
     "fs_visc3d_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fs_visc3d_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_size_t]),
@@ -178,3 +179,8 @@ def check(status, what):
 
 def launch_count():
     return int(load().fs_launch_count())
+
+
+def set_option(name, value):
+    """Tuning switch of the kernels (see fs_set_option in include/fluidsolver_b200.h); ``value < 0`` restores the default."""
+    check(load().fs_set_option(name.encode(), int(value)), f"fs_set_option({name})")
