@@ -98,8 +98,10 @@ int64_t fs_launch_count(void);
 /* Tuning switches of the kernels (the programmatic form of the FLUIDSOLVER_B200_* environment variables; they select between
  * result-equivalent implementations and never change what is computed).  value < 0 restores the default.
  *   "resident_form" : 0 = persistent CG through global memory, 1 / 2 = first / second shared-memory resident kernel
- *   "llred"         : 0 / 1 = counter-based / flag-in-data grid reduction in the second resident kernel
- *   "k1_prefetch"   : 0 / 1 = L2 prefetch of the next segment in the stand-alone K1s (HBM-sized active sets)
+ *   "k1_block"      : n = trips of consecutive segments a CTA of the stand-alone K1s takes before it jumps ahead by the grid
+ *                     (0 = interleaved); applies to HBM-sized active sets, 1000 + n to every size
+ *   "k1_tile"       : 0 / 1 = off / on: dense lattices run the stand-alone K1s as a shared-memory tiled kernel that marches
+ *                     along x (2 = on every lattice, tests)
  * Returns FS_OK, or FS_ERR_ARG for an unknown name. */
 int fs_set_option(const char* name, int value);
 

@@ -193,8 +193,11 @@ void CgHost::destroy() {
 
 // tuning switches: explicit setting (fs_set_option) > environment variable > built-in default (-1)
 static int g_opt[OPT_COUNT] = {-2, -2, -2};
-static const char* const kOptEnv[OPT_COUNT] = {"FLUIDSOLVER_B200_RESIDENT", "FLUIDSOLVER_B200_LLRED", "FLUIDSOLVER_B200_K1PF"};
-static const char* const kOptName[OPT_COUNT] = {"resident_form", "llred", "k1_prefetch"};
+static const char* const kOptEnv[OPT_COUNT] = {"FLUIDSOLVER_B200_RESIDENT", "FLUIDSOLVER_B200_K1BLOCK", "FLUIDSOLVER_B200_K1TILE"};
+static const char* const kOptName[OPT_COUNT] = {"resident_form", "k1_block", "k1_tile"};
+
+static int g_opt_epoch = 0;
+int tuning_epoch() { return g_opt_epoch; }
 
 int tuning(int which) {
     if (which < 0 || which >= OPT_COUNT) return -1;
@@ -212,7 +215,7 @@ extern "C" {
 int fs_set_option(const char* name, int value) {
     if (!name) return fs::fail(FS_ERR_ARG, "fs_set_option: null name");
     for (int k = 0; k < fs::OPT_COUNT; ++k)
-        if (strcmp(name, fs::kOptName[k]) == 0) { fs::g_opt[k] = value < 0 ? -1 : value; return FS_OK; }
+        if (strcmp(name, fs::kOptName[k]) == 0) { fs::g_opt[k] = value < 0 ? -1 : value; ++fs::g_opt_epoch; return FS_OK; }
     return fs::fail(FS_ERR_ARG, "fs_set_option: unknown option '%s'", name);
 }
 

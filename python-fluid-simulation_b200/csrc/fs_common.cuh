@@ -54,8 +54,9 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int coop_max_blocks(const void* fn, int threads, size_t dyn_smem = 0);
 
 // tuning switches (fs_set_option / FLUIDSOLVER_B200_* environment variables): -1 = not set, use the built-in default
-enum { OPT_RESIDENT_FORM = 0, OPT_LLRED = 1, OPT_K1PF = 2, OPT_COUNT = 3 };
+enum { OPT_RESIDENT_FORM = 0, OPT_K1BLOCK = 1, OPT_K1TILE = 2, OPT_COUNT = 3 };
 int tuning(int which);
+int tuning_epoch();      // bumped by every fs_set_option call: captured iteration graphs are keyed on it
 
 // ---------------------------------------------------------------------------------------------
 // device-resident CG control block: alpha/beta/convergence live on the GPU so the iteration
@@ -728,6 +729,10 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_sr_seg_kernel(long long
 // (A two-level arrival — 16-CTA groups on separate lines, the last arriver of a group arriving at a top counter — was
 // measured and rejected: the second dependent atomic round trip costs more than the serialisation of 148 arrivals on one
 // line saves; plain barrier 1.21 -> 1.84 us, reducing barrier 2.72 -> 3.58 us on B200.)
+// (Also measured and rejected: a counter-free reduction in which every block posts its partial sums as flag-in-data words
+// (4 data bytes + sequence number) and thread t of EVERY block polls block t's words — no atomic, no separate read of the
+// partials.  148 blocks x 148 pollers hammer the ~40 L2 lines of the slots: reducing barrier 2.56 -> 4.78 us, and the
+// following plain barrier 1.17 -> 1.90 us, on the 256^3 benchmark scene.)
 struct GridBar { unsigned int count; unsigned int pad; unsigned long long result_ll[8]; };
 
 __device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
@@ -1004,72 +1009,6 @@ __device__ __forceinline__ void grid_allreduce2(double& v1, double& v2, double* 
     for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) { s1 += __ldcg(slot + i); s2 += __ldcg(slot + nblocks + i); }
     block_sum_all2(s1, s2, sm);
     if (peers) peer_allreduce2_block(s1, s2, peers, seq0, seq1, s_glob, gs.bar->result_ll);
-    v1 = s1; v2 = s2;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Flag-in-data grid all-reduce (single GPU).  grid_allreduce2 above costs an atomic round trip to the arrival counter, the
-// release of the spinning thread and THEN a read of the partials (another L2 round trip).  Here the partials are their own
-// arrival flags: every block posts its two sums as four 8-byte words carrying 4 data bytes + a 4-byte sequence number (the
-// LL idea of the NVLink mailbox above), and thread t of every block polls block t's words until they carry this
-// reduction's sequence number — one store and one polled read on the critical path, no counter.  The partials are then
-// summed in a fixed order (the same order in every block: identical bits everywhere, as before).
-//
-// Ordering: a block posts only after its phase's loads have returned (their values are in the sums), and nobody leaves
-// before it has seen every post, so everything a block writes AFTER the reduction (r in phase B) happens after every read
-// of phase A — the WAR edge a reduction must cover.  The RAW edge (phase B's stores -> the next phase A's loads) stays with
-// the acq_rel counter barrier (GridSync::sync).  Slots are double-buffered by sequence parity and never reset: the host
-// hands every launch a fresh range of sequence numbers.  Bounded spin (a lost block yields NaN -> status "not converged").
-// Needs gridDim.x <= kLLMaxBlocks and blockDim.x >= kLLMaxBlocks.
-// ---------------------------------------------------------------------------------------------
-constexpr int kLLMaxBlocks = 256;
-constexpr size_t kLLRedBytes = (size_t)2 * kLLMaxBlocks * 4 * sizeof(unsigned long long);
-
-struct LLRed {
-    unsigned long long* slots;   // [2 parities][kLLMaxBlocks][4 words]
-    unsigned int seq;            // sequence number of the last reduction (identical in every thread of the grid)
-};
-
-__device__ __forceinline__ void grid_allreduce2_ll(double& v1, double& v2, LLRed& ll) {
-    __shared__ double sm[64];
-    __shared__ double sm2[2][kLLMaxBlocks / 32];
-    const unsigned int nblocks = gridDim.x;
-    const unsigned int seq = ++ll.seq;
-    unsigned long long* base = ll.slots + (size_t)(seq & 1u) * kLLMaxBlocks * 4;
-    const unsigned long long tag = (unsigned long long)seq << 32;
-    block_sum2(v1, v2, sm);
-    if (threadIdx.x == 0) {
-        const unsigned long long b1 = (unsigned long long)__double_as_longlong(v1), b2 = (unsigned long long)__double_as_longlong(v2);
-        unsigned long long* s = base + (size_t)blockIdx.x * 4;
-        st_relaxed_gpu_u64(s + 0, tag | (b1 & 0xffffffffull));
-        st_relaxed_gpu_u64(s + 1, tag | (b1 >> 32));
-        st_relaxed_gpu_u64(s + 2, tag | (b2 & 0xffffffffull));
-        st_relaxed_gpu_u64(s + 3, tag | (b2 >> 32));
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp < kLLMaxBlocks / 32) {
-        double a = 0.0, b = 0.0;
-        if (threadIdx.x < nblocks) {
-            const unsigned long long* s = base + (size_t)threadIdx.x * 4;
-            unsigned long long w0, w1, w2, w3;
-            bool ok = true;
-            const long long t0 = clock64();
-            for (;;) {
-                w0 = ld_relaxed_gpu_u64(s + 0); w1 = ld_relaxed_gpu_u64(s + 1); w2 = ld_relaxed_gpu_u64(s + 2); w3 = ld_relaxed_gpu_u64(s + 3);
-                if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq && (unsigned int)(w2 >> 32) == seq && (unsigned int)(w3 >> 32) == seq) break;
-                if (clock64() - t0 > 4000000000LL) { ok = false; break; }       // ~2 s: a block never posted
-            }
-            a = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
-            b = __longlong_as_double((long long)(((w3 & 0xffffffffull) << 32) | (w2 & 0xffffffffull)));
-            if (!ok) a = b = __longlong_as_double(0x7ff8000000000000LL);
-        }
-        a = warp_sum(a); b = warp_sum(b);
-        if (lane == 0) { sm2[0][warp] = a; sm2[1][warp] = b; }
-    }
-    __syncthreads();
-    double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLLMaxBlocks / 32; ++w) { s1 += sm2[0][w]; s2 += sm2[1][w]; }
     v1 = s1; v2 = s2;
 }
 

@@ -82,7 +82,6 @@ __device__ __forceinline__ double edge_in_fraction(double l, double r) {
 // Persistent grid (kPressBlocksPerSM CTAs per SM), grid-stride over the cells with the fastest axis across the warp, one
 // deterministic block reduction at the very end (a reduction per 256 cells made the first version barrier-bound).
 constexpr int kPressBlocksPerSM = 6;
-constexpr bool kPressLLRedDefault = false;   // flag-in-data reductions in the persistent kernel when "llred" / FLUIDSOLVER_B200_LLRED is not set
 
 // OP selects the operator: OP_PRESSURE = PressureCGSolver*.matvecmul_kernel (diagonal weighted by the face fractions);
 // OP_DENSITY = DensityCGSolver3D.matvecmul_kernel (:117-194): unit diagonal contributions, and the -z off-diagonal term
@@ -222,14 +221,11 @@ __device__ __forceinline__ double press_apply_seg_body(const Grid<D>& g, const d
     return acc;
 }
 
-// LL = the two reductions use the flag-in-data form (grid_allreduce2_ll: no counter round trip, no separate read of the
-// partials).  Both only have to order reads before later writes (K1's reads of d before K3 rewrites it), which the data
-// dependency of the posted sums gives; the barrier after K3 (writes of d -> K1's reads) stays the acq_rel counter barrier.
-template <int D, int OP, bool LL>
+template <int D, int OP>
 __global__ void __launch_bounds__(kPersistThreads, 1) press_cg_persistent_kernel(Grid<D> g, double* x, double* r, double* d, double* q, PressW<D> W,
                                                                                  const double* __restrict__ lphi, const int* __restrict__ seg,
                                                                                  const int* __restrict__ nseg_p, CgState* st, double* partials,
-                                                                                 GridBar* bar, int n_iters, LLRed ll) {
+                                                                                 GridBar* bar, int n_iters) {
     const int nseg = *nseg_p;
     double delta = st->delta, delta_old = st->delta_old, dq = st->dq, alpha_d = st->alpha, beta_d = st->beta;
     const double tol2 = st->tol2;
@@ -241,13 +237,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) press_cg_persistent_kernel
     hot.has_lo = hot.has_hi = 0;
     for (int it = 0; it < n_iters && !done; ++it) {
         double acc = press_apply_seg_body<D, OP>(g, d, q, W, lphi, seg, nseg);
-        if constexpr (LL) { double z = 0.0; grid_allreduce2_ll(acc, z, ll); dq = acc; }
-        else dq = grid_allreduce(acc, partials, gs);
+        dq = grid_allreduce(acc, partials, gs);
         alpha_d = delta / dq;
         acc = cg_update_xr_seg_body<double, 1, false>(g.ncells, g.ncells, seg, nseg, x, r, d, q, alpha_d, hot);
-        double rr;
-        if constexpr (LL) { double z = 0.0; grid_allreduce2_ll(acc, z, ll); rr = acc; }
-        else rr = grid_allreduce(acc, partials, gs);
+        const double rr = grid_allreduce(acc, partials, gs);
         delta_old = delta;
         delta = rr;
         iter += 1;
@@ -399,11 +392,9 @@ struct fs_press {
     GridBar* bar;
     bool use_list;         // the current solve iterates on the active list with the persistent kernel
     int op;                // OP_PRESSURE / OP_DENSITY
-    unsigned long long* ll_slots;   // flag-in-data reduction slots (zero at creation), see grid_allreduce2_ll
-    unsigned int ll_seq;            // last sequence number handed to a launch
 };
 
-struct PressLayout { size_t st, act, seglist, segscratch, bar, llred, total; };
+struct PressLayout { size_t st, act, seglist, segscratch, bar, total; };
 
 static PressLayout press_layout(long long ncells) {
     PressLayout o;
@@ -415,7 +406,6 @@ static PressLayout press_layout(long long ncells) {
     o.seglist = p; p = align_up(p + SegList::list_bytes(ncells), 256);
     o.segscratch = p; p = align_up(p + SegList::scratch_bytes(ncells), 256);
     o.bar = p; p = align_up(p + sizeof(GridBar), 256);
-    o.llred = p; p = align_up(p + kLLRedBytes, 256);
     o.total = p;
     return o;
 }
@@ -491,39 +481,26 @@ static int press_prepare_list(fs_press* h, const double* x, const double* d, con
 
 static int press_persistent(fs_press* h, double* x, double* d, double* r, double* q, const double* wx, const double* wy, const double* wz,
                             const double* lphi, long long n, cudaStream_t s) {
-    const int llopt = tuning(OPT_LLRED);
-    const bool ll = llopt < 0 ? kPressLLRedDefault : llopt != 0;
-    const void* fn3 = h->op == OP_DENSITY ? (ll ? (const void*)press_cg_persistent_kernel<3, OP_DENSITY, true> : (const void*)press_cg_persistent_kernel<3, OP_DENSITY, false>)
-                                          : (ll ? (const void*)press_cg_persistent_kernel<3, OP_PRESSURE, true> : (const void*)press_cg_persistent_kernel<3, OP_PRESSURE, false>);
-    const void* fn = h->nz > 0 ? fn3 : (ll ? (const void*)press_cg_persistent_kernel<2, OP_PRESSURE, true> : (const void*)press_cg_persistent_kernel<2, OP_PRESSURE, false>);
+    const void* fn3 = h->op == OP_DENSITY ? (const void*)press_cg_persistent_kernel<3, OP_DENSITY> : (const void*)press_cg_persistent_kernel<3, OP_PRESSURE>;
+    const void* fn = h->nz > 0 ? fn3 : (const void*)press_cg_persistent_kernel<2, OP_PRESSURE>;
     const int cap = coop_max_blocks(fn, kPersistThreads);      // SMs of this context x resident CTAs per SM
     if (cap < 1) { h->use_list = false; return 1; }
-    int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, cap < kSMs ? cap : kSMs);
-    if (grid > kLLMaxBlocks) grid = kLLMaxBlocks;
+    const int grid = seg_grid(h->seg.nseg, kPersistThreads / 32, cap < kSMs ? cap : kSMs);
     while (n > 0) {
         int ni = (int)(n < (1 << 20) ? n : (1 << 20));
         cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);
         if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-        if (h->ll_seq > 0xE0000000u) {               // sequence numbers about to wrap: start over on clean slots
-            e = cudaMemsetAsync(h->ll_slots, 0, kLLRedBytes, s);
-            if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-            h->ll_seq = 0;
-        }
-        LLRed llr;
-        llr.slots = h->ll_slots;
-        llr.seq = h->ll_seq;
-        h->ll_seq += 2u * (unsigned int)ni + 2u;     // two reductions per iteration
         const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
         CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
         if (h->nz > 0) {
             Grid<3> g = make_grid<3>(h->nx, h->ny, h->nz);
             PressW<3> W = mkW<3>(wx, wy, wz);
-            void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni, &llr};
+            void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni};
             e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args, 0, s);
         } else {
             Grid<2> g = make_grid<2>(h->nx, h->ny, 0);
             PressW<2> W = mkW<2>(wx, wy, nullptr);
-            void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni, &llr};
+            void* args[] = {&g, &x, &r, &d, &q, &W, &lphi, &seg, &nsegp, &st, &partials, &bar, &ni};
             e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args, 0, s);
         }
         if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported) {
@@ -573,8 +550,6 @@ int fs_press_create(fs_press** out, int nx, int ny, int nz, void* ws, size_t ws_
     h->st = (CgState*)((char*)ws + lay.st);
     h->act = (uint8_t*)((char*)ws + lay.act);
     h->bar = (GridBar*)((char*)ws + lay.bar);
-    h->ll_slots = (unsigned long long*)((char*)ws + lay.llred);
-    h->ll_seq = 0;
     h->use_list = false;
     h->grid = (int)((h->ncells + kPT - 1) / kPT);
     for (int k = 0; k < 9; ++k) h->gkey[k] = nullptr;

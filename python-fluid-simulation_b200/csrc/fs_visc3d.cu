@@ -47,8 +47,6 @@ template <typename T> struct Visc3Dev {
     const uint8_t* act;      // per lattice point: bit c set <=> row c is computed (same information as the NaN tags, 1 byte)
 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 __device__ __forceinline__ void lat_decode(const Lat3& L, long long i, int& x, int& y, int& z) {
     if (L.NL < 0x7fffffffLL) {                       // 32-bit divisions (the common case) are several times cheaper
         const unsigned int u = (unsigned int)i, zp = (unsigned int)L.Zp, yy = (unsigned int)L.Y;
@@ -632,7 +630,8 @@ __global__ void __launch_bounds__(kThreads) visc3d_scale_kernel(Visc3Dev<T> P, T
 // (fixed order, deterministic).
 // ---------------------------------------------------------------------------------------------
 constexpr int kK1Threads = 256;
-constexpr int kK1PrefetchDefault = 0;     // L2 prefetch of the next trip in the stand-alone K1s when FLUIDSOLVER_B200_K1PF is not set
+constexpr int kK1TileDefault = 0;         // shared-memory tiled K1s on dense lattices when "k1_tile" / FLUIDSOLVER_B200_K1TILE is not set
+constexpr int kK1BlockDefault = 0;        // consecutive trips per CTA block in the stand-alone K1s on HBM-sized lists (0 = interleaved)
 constexpr int kK1SegsPerBlock = kK1Threads / 32;
 // CTAs per SM: the fp64 body keeps 43 loaded values (86 registers) in flight, so it gets 128 registers per thread
 // (2 CTAs/SM); with an 80-register cap (3 CTAs/SM) ptxas split the loads into dependent phases and the dense-scene
@@ -647,7 +646,7 @@ template <> struct K1Occ<float> { static constexpr int value = 3; };
 // rows, and the boundary rows go to the neighbours' w planes instead of their q planes.
 template <typename T, bool DIST, bool COHERENT, bool SR = false>
 __device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T s, T s2, const T* d, T* q, const int* __restrict__ seg, int nseg,
-                                                        const PeerHot& hot, bool& wrote_peer, double* acc2_out = nullptr, int par = 0, int pf = 0) {
+                                                        const PeerHot& hot, bool& wrote_peer, double* acc2_out = nullptr, int par = 0, int blk = 0) {
     const Lat3& L = P.L;
     const long long NL = L.NL;
     const long long st[3] = {L.sx, L.sy, 1};
@@ -656,24 +655,24 @@ __device__ __forceinline__ double visc3d_apply_dot_body(const Visc3Dev<T>& P, T 
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     double acc = 0.0, acc2 = 0.0;
     auto nb = [&](int comp, long long j) -> T { return COHERENT ? d[comp * NL + j] : __ldg(d + comp * NL + j); };
-    int sg_n = w0 < nseg ? __ldg(seg + w0) : 0;
-    for (long long k = w0; k < nseg; k += nw) {
+    // Warp -> list position of trip q.  blk == 0: interleaved over the whole grid (warp g takes g, g + nw, ...).
+    // blk > 0 (HBM-sized lists): a CTA takes `blk` consecutive trips of blockDim/32 CONSECUTIVE list entries — consecutive
+    // lattice rows — before it jumps ahead by the grid: the y-neighbour rows of one trip are the own rows of the next, so
+    // they are served by L1 instead of L2 (the stand-alone apply runs at the L2 throughput cap, not at the HBM one), while
+    // all CTAs still sweep the same few x-planes together (x-neighbour reuse through L2, DRAM traffic unchanged).
+    const int wl = threadIdx.x >> 5, wc = blockDim.x >> 5;
+    const long long span = (long long)blk * wc;
+    auto kof = [&](long long trip) -> long long {
+        if (blk <= 0) return w0 + trip * nw;
+        const long long m = trip / blk, t = trip - m * blk;
+        return (m * gridDim.x + blockIdx.x) * span + t * wc + wl;
+    };
+    long long k = kof(0);
+    int sg_n = k < nseg ? __ldg(seg + k) : 0;
+    for (long long trip = 0; k < nseg; ++trip) {
         const long long i = (long long)sg_n * kSegPts + lane;
-        {
-            const long long k2 = k + nw;
-            sg_n = k2 < nseg ? __ldg(seg + k2) : 0;
-        }
-        if (pf) {
-            // HBM-sized lists: pull the lines the NEXT trip of this warp touches first into L2 now (hint only, no register
-            // held, no warp stalled): its seven coefficient words and the x+1 plane of d, i.e. everything of that trip that
-            // no earlier trip has requested yet.  The trip then waits for L2, not for DRAM.
-            const long long ip = (long long)sg_n * kSegPts + lane;
-            if (ip < NL) {
-                prefetch_l2(P.cs[0] + ip); prefetch_l2(P.cs[1] + ip); prefetch_l2(P.cs[2] + ip); prefetch_l2(P.cs[3] + ip);
-                prefetch_l2(P.cs[4] + ip + L.sx); prefetch_l2(P.cs[5] + ip + L.sx); prefetch_l2(P.cs[6] + ip + L.sy);
-                prefetch_l2(d + ip + L.sx); prefetch_l2(d + NL + ip + L.sx); prefetch_l2(d + 2 * NL + ip + L.sx);
-            }
-        }
+        k = kof(trip + 1);                         // (strictly increasing in trip: the loop ends at the first position past the list)
+        sg_n = k < nseg ? __ldg(seg + k) : 0;
         const bool in = i < NL;
         const long long j = in ? i : (NL - 1);
         const unsigned int a = in ? ((unsigned int)__ldg(P.act + i) & kActCompute) : 0u;
@@ -804,18 +803,123 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_persistent_kerne
 template <typename T, bool DIST, int OCC = K1Occ<T>::value>
 __global__ void __launch_bounds__(kK1Threads, OCC) visc3d_apply_dot2_kernel(Visc3Dev<T> P, T s, T s2, const T* __restrict__ r, T* __restrict__ w /*[2][3][NL]*/,
                                                                                         const int* __restrict__ seg, const int* __restrict__ nseg_p,
-                                                                                        CgState* st_, double* partials, PeerInfo* peers, PeerHot hot, int freeze, int pf) {
+                                                                                        CgState* st_, double* partials, PeerInfo* peers, PeerHot hot, int freeze, int blk) {
     if (*(volatile int*)&st_->done) return;
     bool wrote_peer = false;
     double rr = 0.0;
     const int par = DIST ? (int)(st_->iter & 1) : 0;           // (st->iter is stable here: only the update kernel advances it)
     w += (long long)par * 3 * P.L.NL;
-    const double wr = visc3d_apply_dot_body<T, DIST, false, true>(P, s, s2, r, w, seg, *nseg_p, hot, wrote_peer, &rr, par, pf);
+    const double wr = visc3d_apply_dot_body<T, DIST, false, true>(P, s, s2, r, w, seg, *nseg_p, hot, wrote_peer, &rr, par, blk);
     const bool block_wrote_peer = DIST ? (__syncthreads_or(wrote_peer ? 1 : 0) != 0) : false;
     grid_sum2_finish(rr, wr, partials, &st_->counter[0], [=](double gamma, double dl) {
         if (freeze) return;                      // profiling hook: repeated launches leave the CG state alone
         cg_sr_after_dots(st_, gamma, dl, par);
     }, (DIST && !freeze) ? peers : nullptr, block_wrote_peer);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1t: the stand-alone single-reduction apply for DENSE lattices as a shared-memory tiled kernel that marches along x.
+//
+// The list kernel above fetches, per 32-point segment, 17 row-lines of r and 13 of coefficients from L2 (a third of its 43
+// loads hit in L1): on a dense 256^3 lattice that is 4.4 GB through the L2 -> SM crossbar per launch against 1.75 GB of
+// algorithmic (= DRAM) bytes, and the kernel sits at the measured crossbar limit (~6 300 B/clk for the chip), not at the
+// HBM limit.  Here a CTA owns `ty` consecutive lattice rows — a CONTIGUOUS range of `ty * Zp` points in every x-plane, for
+// every array alike — and walks `xl` planes of them: the three components of r of planes x-1, x, x+1 (the range plus a
+// halo of one row + one element on either side, which covers every in-plane stencil offset) sit in a four-deep ring of
+// shared-memory buffers filled by cp.async two planes ahead, so each r value crosses the crossbar (ty + 2) / ty times
+// instead of ~6, and all 27 neighbour reads become shared-memory reads at compile-time offsets.  The coefficients are
+// still read from global memory (each is used by one point and its direct neighbours, which L1 serves within a plane).
+// Work items (row block, plane chunk) are handed out by an atomic counter, x-chunk major, so the CTAs running together
+// cover neighbouring row blocks of the same planes and the halo rows are shared through L2 (DRAM traffic unchanged).
+// Arithmetic per point is that of the list kernel (same evaluator, same order); only the reduction tree differs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kK1tThreads = 512;
+constexpr int kK1tPlanes = 16;            // x-planes per work item (two warm-up planes of r are loaded on top)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T> __host__ __device__ constexpr int k1t_halo(int Zp) { return Zp + 4; }     // one row + one element, 16-byte multiple
+
+template <typename T>
+__global__ void __launch_bounds__(kK1tThreads, 1) visc3d_apply_dot2_tile_kernel(Visc3Dev<T> P, const T* __restrict__ r, T* __restrict__ w,
+                                                                               CgState* st_, double* partials, int ty, int xl, int freeze) {
+    if (*(volatile int*)&st_->done) return;
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    T* const sm = reinterpret_cast<T*>(tile_smem);              // [4 planes][3 components][Ls]
+    __shared__ int s_item;
+    const Lat3& L = P.L;
+    const long long NL = L.NL;
+    const long long stv[3] = {L.sx, L.sy, 1};
+    const int Zp = L.Zp;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int H = k1t_halo<T>(Zp);
+    const int tile = ty * Zp;                                   // lattice points of one plane step
+    const int Ls = tile + 2 * H;                                // staged range per component and plane
+    const int nyb = (L.Y + ty - 1) / ty;
+    const int x_first = 1, x_end = L.nx;                        // planes 1 .. nx-1 can hold computed rows
+    const int nxc = (x_end - x_first + xl - 1) / xl;
+    const int nitems = nyb * nxc;
+    double rr = 0.0, wr = 0.0;
+    for (;;) {
+        __syncthreads();                                        // everybody is done with the previous item (its buffers, s_item)
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(&st_->counter[3], 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= nitems) break;
+        const int xc = item / nyb, yb = item - xc * nyb;
+        const int xa = x_first + xc * xl;
+        const int xb = xa + xl < x_end ? xa + xl : x_end;       // planes [xa, xb)
+        const long long row0 = (long long)yb * tile;            // offset of the row block inside a plane
+        auto issue = [&](int p) {                               // plane p of r, three components -> ring buffer p & 3
+            T* dst = sm + (size_t)(p & 3) * 3 * Ls;
+            const T* src = r + (long long)p * L.sx + row0 - H;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                for (int e = threadIdx.x * VEC; e < Ls; e += kK1tThreads * VEC) cp_async16(dst + c * Ls + e, src + c * NL + e);
+            cp_async_commit();
+        };
+        issue(xa - 1); issue(xa); issue(xa + 1);
+        for (int x = xa; x < xb; ++x) {
+            if (x + 2 <= xb) issue(x + 2); else cp_async_commit();   // (an empty group keeps the group count uniform)
+            cp_async_wait<1>();                                 // everything but the newest group has landed: planes <= x+1
+            __syncthreads();
+            const T* bm = sm + (size_t)((x - 1) & 3) * 3 * Ls + H;
+            const T* b0 = sm + (size_t)(x & 3) * 3 * Ls + H;
+            const T* bp = sm + (size_t)((x + 1) & 3) * 3 * Ls + H;
+            for (int t = threadIdx.x; t < tile; t += kK1tThreads) {
+                if (row0 + t >= L.sx) break;                    // last row block of a plane: rows beyond the lattice
+                const long long i = (long long)x * L.sx + row0 + t;
+                const unsigned int a = (unsigned int)__ldg(P.act + i) & kActCompute;
+                if (a == 0u) continue;
+                auto cf = [&](int plane, int axis, int sign) -> T { return __ldg(P.cs[plane] + i + (long long)sign * stv[axis]); };
+                auto nbu = [&](int comp, int p, int m) -> T {   // component comp at i + e_p - e_m: all offsets are compile-time
+                    const int dx = (p == 0 ? 1 : 0) - (m == 0 ? 1 : 0);
+                    const int off = ((p == 1 ? 1 : 0) - (m == 1 ? 1 : 0)) * Zp + ((p == 2 ? 1 : 0) - (m == 2 ? 1 : 0));
+                    const T* b = dx > 0 ? bp : (dx < 0 ? bm : b0);
+                    return b[comp * Ls + t + off];
+                };
+                const T cu = __ldg(P.cs[0] + i), cv = __ldg(P.cs[1] + i), cw = __ldg(P.cs[2] + i);      // row diagonals
+                const T du = b0[t], dv = b0[Ls + t], dw = b0[2 * Ls + t];
+                const T ru = visc_row_scaled_u<T, 3, 0>(cu, du, cf, nbu);
+                const T rv = visc_row_scaled_u<T, 3, 1>(cv, dv, cf, nbu);
+                const T rw = visc_row_scaled_u<T, 3, 2>(cw, dw, cf, nbu);
+                if (a & 1u) { w[i] = ru; wr += (double)du * (double)ru; rr += (double)du * (double)du; }
+                if (a & 2u) { w[NL + i] = rv; wr += (double)dv * (double)rv; rr += (double)dv * (double)dv; }
+                if (a & 4u) { w[2 * NL + i] = rw; wr += (double)dw * (double)rw; rr += (double)dw * (double)dw; }
+            }
+            __syncthreads();                                    // buffer (x-1) & 3 is refilled by the next step's issue
+        }
+    }
+    grid_sum2_finish(rr, wr, partials, &st_->counter[0], [=](double gamma, double dl) {
+        st_->counter[3] = 0;                                    // work counter of the next launch (every block has left its loop)
+        if (freeze) return;
+        cg_sr_after_dots(st_, gamma, dl, 0);
+    });
 }
 
 template <typename T, bool DIST>
@@ -1072,19 +1176,18 @@ __global__ void __launch_bounds__(THREADS, 1) visc3d_cg_sr_resident_kernel(Visc3
 // no dependent L2 read in it any more (the first form spends two sequential round trips there: segment id, then r, per
 // trip).  Slots are addressed by the position of a segment in the CTA's run, so exactly `chunk` slots are needed: 29 of
 // 7 972 B for the 4 253 segments of the 256^3 benchmark scene = 231 KB of the 227 KiB an SM offers.  Positions beyond
-// `res_slots` (longer lists) run through global memory as before.  LL = the flag-in-data reduction (grid_allreduce2_ll).
+// `res_slots` (longer lists) run through global memory as before.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRes2Vals = 31;     // per point: 16 coefficients, p[3], s[3], w[3], x[3], r[3]
 constexpr int kResidentFormDefault = 1;   // which resident kernel runs when FLUIDSOLVER_B200_RESIDENT is not set
-constexpr bool kLLRedDefault = false;     // flag-in-data reduction when FLUIDSOLVER_B200_LLRED is not set
 constexpr int kRes2Threads = 512;
 template <typename T> __host__ __device__ constexpr size_t res2_slot_bytes() { return (size_t)kRes2Vals * 32 * sizeof(T) + 32 + sizeof(int); }
 
-template <typename T, bool LL>
+template <typename T>
 __global__ void __launch_bounds__(kRes2Threads, 1) visc3d_cg_sr_resident2_kernel(Visc3Dev<T> P, T* x, T* r, T* p, T* sv, T* w,
                                                                                         const int* __restrict__ seg, const int* __restrict__ nseg_p,
                                                                                         CgState* st, double* partials, GridBar* bar, int n_slots, int res_slots,
-                                                                                        LLRed ll, unsigned long long* prof) {
+                                                                                        unsigned long long* prof) {
     extern __shared__ __align__(16) unsigned char res_smem[];
     constexpr int kWarps = kRes2Threads / 32;
     T* const svals = reinterpret_cast<T*>(res_smem);                                            // [res_slots][kRes2Vals][32]
@@ -1176,8 +1279,7 @@ __global__ void __launch_bounds__(kRes2Threads, 1) visc3d_cg_sr_resident2_kernel
             if (a & 4u) { wr += (double)dw * (double)rw; rr += (double)dw * (double)dw; }
         }
         tick();
-        if constexpr (LL) grid_allreduce2_ll(rr, wr, ll);
-        else grid_allreduce2(rr, wr, partials, gs);
+        grid_allreduce2(rr, wr, partials, gs);
         tick();
         delta = rr;
         if (rr < tol2) done = 1;
@@ -1375,8 +1477,7 @@ struct fs_visc3d {
     bool windowed;       // pack / load / extrapolation work on the x-window L.wlo..L.whi of the lattice only
     uint8_t* xflags;     // [segments] publish flags of the current solve
     SegList xseg;        // segments this rank publishes (built from xflags)
-    unsigned long long* ll_slots;   // flag-in-data reduction slots (grid_allreduce2_ll), zero at creation, never reset in normal use
-    unsigned int ll_seq;            // last sequence number handed to a launch
+    int k1t_smem;        // dynamic shared memory the tiled K1s may use on this device (0: not available)
 };
 
 // threads of the one-block-per-lattice-row kernels: a whole number of warps covering the row once, at most 512
@@ -1396,7 +1497,7 @@ static Lat3 make_lat3(int nx, int ny, int nz) {
     return L;
 }
 
-struct Visc3Layout { size_t coefs, xflags, xlist, xscratch, rownz, llred; size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
+struct Visc3Layout { size_t coefs, xflags, xlist, xscratch, rownz; size_t coef, vecs, mask, valid, act, partials, st, seglist, segscratch, bar, wlist, wcount, d2, rowflag, total; int grid_pts; unsigned int wcap; };
 
 static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     Visc3Layout o;
@@ -1435,7 +1536,6 @@ static Visc3Layout visc3_layout(const Lat3& L, size_t esz) {
     o.xlist = p; p = align_up(p + SegList::list_bytes(L.NL), 256);
     o.xscratch = p; p = align_up(p + SegList::scratch_bytes(L.NL), 256);
     o.rownz = p; p = align_up(p + (size_t)L.X * L.Y, 256);
-    o.llred = p; p = align_up(p + kLLRedBytes, 256);
     o.total = p;
     return o;
 }
@@ -1668,8 +1768,16 @@ int fs_visc3d_create(fs_visc3d** out, int nx, int ny, int nz, int dtype, void* w
     s = h->xseg.init(h->L.NL, h->ws + lay.xlist, h->ws + lay.xscratch);
     if (s < 0) { h->cg.destroy(); h->seg.destroy(); delete h; return s; }
     h->xflags = (uint8_t*)(h->ws + lay.xflags);
-    h->ll_slots = (unsigned long long*)(h->ws + lay.llred);
-    h->ll_seq = 0;
+    h->k1t_smem = 0;
+    {   // opt the tiled K1s into the large shared-memory carve-out now (not inside a stream capture later)
+        int dev = 0, smem_max = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && smem_max > 2048) {
+            cudaError_t ea = cudaSuccess;
+            FS_DISPATCH(h, ea = cudaFuncSetAttribute((const void*)visc3d_apply_dot2_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024));
+            if (ea == cudaSuccess) h->k1t_smem = smem_max - 1024;
+        }
+        cudaGetLastError();
+    }
     h->windowed = false;
     h->cg.st_dev = h->st; h->cg.partials_dev = h->partials;
     cudaError_t e = cudaMemset(ws, 0, lay.total);     // cp.zeros semantics for every solver vector
@@ -1848,27 +1956,56 @@ static int visc3d_k3(fs_visc3d* h, cudaStream_t s) {
     FS_DISPATCH(h, FS_TRY((cg_launch_update_d_seg<T, 3>(h->L.NL, h->L.NL, h->seg, vec_ptr<T>(h, FS_VEC_D), vec_ptr<T>(h, FS_VEC_R), h->st, s))));
     return FS_OK;
 }
+// Shared-memory tiled form of the stand-alone K1s (visc3d_apply_dot2_tile_kernel) for dense lattices on a single GPU.
+// "k1_tile" / FLUIDSOLVER_B200_K1TILE: 0 = off, 1 = on when at least 60 % of the lattice segments are active, 2 = on every
+// lattice (tests).  Returns 1 when it does not apply (nothing enqueued).
+static int visc3d_k1t(fs_visc3d* h, double sm, cudaStream_t s, int freeze) {
+    const int opt = tuning(OPT_K1TILE);
+    const int v = opt < 0 ? kK1TileDefault : opt;
+    const int mode = v % 10, ty_req = (v / 10) % 100, xl_req = v / 1000;     // (experiments: 1000*planes + 10*rows + mode)
+    if (mode == 0 || h->peers || h->comm || h->k1t_smem <= 0) return 1;
+    if (mode != 2 && (double)h->seg.nseg < 0.6 * (double)h->seg.nseg_total) return 1;
+    if (h->L.nx < 2) return 1;
+    const int Zp = h->L.Zp;
+    const long long halo = h->dtype == FS_F32 ? k1t_halo<float>(Zp) : k1t_halo<double>(Zp);
+    // rows per block: the largest that fits four planes x three components
+    long long ty = ((long long)h->k1t_smem / (12 * (long long)h->esz) - 2 * halo) / Zp;
+    if (ty > 16) ty = 16;
+    if (ty_req > 0 && ty_req < ty) ty = ty_req;
+    if (ty > h->L.Y) ty = h->L.Y;
+    if (ty < 2) return 1;                          // rows too long for a useful block: the list kernel handles it
+    const size_t smem = (size_t)12 * (size_t)(ty * Zp + 2 * halo) * h->esz;
+    const int xl = xl_req > 0 ? xl_req : kK1tPlanes;
+    const int nyb = (int)((h->L.Y + ty - 1) / ty), nxc = (h->L.nx - 1 + xl - 1) / xl;
+    const long long nitems = (long long)nyb * nxc;
+    const int grid = (int)(nitems < kSMs ? nitems : kSMs);
+    const int tyi = (int)ty;
+    FS_DISPATCH(h, visc3d_apply_dot2_tile_kernel<T><<<grid, kK1tThreads, smem, s>>>(dev_view<T>(h), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->st, h->partials, tyi, xl, freeze));
+    FS_LAUNCH_CHECK();
+    (void)sm;
+    return FS_OK;
+}
+
 // single-reduction CG: K1s (w = A r, r.r, w.r, alpha/beta on the device) and K2s (p, s, x, r in one pass)
 static int visc3d_k1s(fs_visc3d* h, double sm, cudaStream_t s, int freeze = 0) {
-    static int occ_env = -1;                     // experiment hook: FLUIDSOLVER_B200_K1OCC=3 -> 3 CTAs/SM (85 registers) for the fp64 K1s
-    if (occ_env < 0) { const char* e = getenv("FLUIDSOLVER_B200_K1OCC"); occ_env = e ? atoi(e) : 0; }
-    // L2 prefetch of the next trip (FLUIDSOLVER_B200_K1PF=0/1): only pays when the list is HBM-sized
-    const int pf_opt = tuning(OPT_K1PF);
-    const int pf_on = pf_opt < 0 ? kK1PrefetchDefault : pf_opt;       // 2 = also on lists that fit in L2 (tests)
-    const int pf = (pf_on == 2 || (pf_on == 1 && (double)h->seg.nseg * kSegPts * (13.0 * h->esz) > 64e6)) ? 1 : 0;
-    if (occ_env == 3 && !h->peers && h->dtype == FS_F64) {
-        const int grid3 = seg_grid(h->seg.nseg, kK1SegsPerBlock, kSMs * 3);
-        visc3d_apply_dot2_kernel<double, false, 3><<<grid3, kK1Threads, 0, s>>>(dev_view<double>(h), sm, 2 * sm, vec_ptr<double>(h, FS_VEC_R), reinterpret_cast<double*>(h->d2),
-                                                                               h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot, freeze, pf);
-        FS_LAUNCH_CHECK();
-        return FS_OK;
+    {
+        const int st = visc3d_k1t(h, sm, s, freeze);           // dense lattice: shared-memory tiled form
+        if (st != 1) return st;
     }
+    // Warp -> segment mapping of the stand-alone apply: "k1_block" / FLUIDSOLVER_B200_K1BLOCK = consecutive trips per CTA
+    // block (0 = interleaved).  Blocking only pays on HBM-sized lists (it trades L2 requests for L1 hits); lists that fit in
+    // L2 run through the persistent kernels anyway.
+    const bool big = (double)h->seg.nseg * kSegPts * (13.0 * h->esz) > 64e6;
+    const int blk_opt = tuning(OPT_K1BLOCK);
+    int blk = blk_opt < 0 ? kK1BlockDefault : blk_opt;
+    if (blk >= 1000) blk -= 1000;                // 1000 + n: also on small lists (tests)
+    else if (!big) blk = 0;
     const int cap = kSMs * (h->dtype == FS_F32 ? K1Occ<float>::value : K1Occ<double>::value);
     const int grid = seg_grid(h->seg.nseg, kK1SegsPerBlock, cap);
     if (h->peers) {
-        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, h->peers, h->hot, freeze, pf));
+        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, true><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, h->peers, h->hot, freeze, blk));
     } else {
-        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot, freeze, pf));
+        FS_DISPATCH(h, visc3d_apply_dot2_kernel<T, false><<<grid, kK1Threads, 0, s>>>(dev_view<T>(h), (T)sm, (T)(2 * sm), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->seg.list, h->seg.nseg_dev, h->st, h->partials, nullptr, h->hot, freeze, blk));
     }
     FS_LAUNCH_CHECK();
     return FS_OK;
@@ -1999,25 +2136,20 @@ static int visc3d_persistent_resident(fs_visc3d* h, double sm, long long n, cuda
     return FS_OK;
 }
 
-// Second resident form (visc3d_cg_sr_resident2_kernel: r resident as well, slots by run position, optional flag-in-data
-// reduction).  FLUIDSOLVER_B200_RESIDENT=1 keeps the first form, FLUIDSOLVER_B200_LLRED=0 the counter-based reduction.
-// Returns 1 if it cannot run here (nothing enqueued).
+// Second resident form (visc3d_cg_sr_resident2_kernel: r resident as well, slots by run position); "resident_form" /
+// FLUIDSOLVER_B200_RESIDENT = 1 selects the first form, 0 the global-memory kernel.  Returns 1 if it cannot run here
+// (nothing enqueued).
 static int resident_form() {
     const int v = tuning(OPT_RESIDENT_FORM);
     return v < 0 ? kResidentFormDefault : v;
-}
-static bool llred_enabled() {
-    const int v = tuning(OPT_LLRED);
-    return v < 0 ? kLLRedDefault : v != 0;
 }
 
 static int visc3d_persistent_resident2(fs_visc3d* h, long long n, cudaStream_t s) {
     int dev = 0, smem_max = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 1;
-    const bool ll = llred_enabled();
     const void* fn = nullptr;
     size_t slot = 0;
-    FS_DISPATCH(h, { fn = ll ? (const void*)visc3d_cg_sr_resident2_kernel<T, true> : (const void*)visc3d_cg_sr_resident2_kernel<T, false>; slot = res2_slot_bytes<T>(); });
+    FS_DISPATCH(h, { fn = (const void*)visc3d_cg_sr_resident2_kernel<T>; slot = res2_slot_bytes<T>(); });
     const int kWarps = kRes2Threads / 32;
     const int max_slots = (int)(((size_t)smem_max - 1024) / slot);                  // 1 KB left for the static reduction scratch
     if (max_slots < 1) return 1;
@@ -2026,7 +2158,6 @@ static int visc3d_persistent_resident2(fs_visc3d* h, long long n, cudaStream_t s
     if (cap < 1) return 1;
     int grid = seg_grid(h->seg.nseg, kWarps, cap < kSMs ? cap : kSMs);
     if (const char* e = getenv("FLUIDSOLVER_B200_PERSIST_GRID")) { const int g = atoi(e); if (g >= 1 && g <= cap) grid = g; }
-    if (grid > kLLMaxBlocks) grid = kLLMaxBlocks;
     const long long chunk = ((long long)h->seg.nseg + grid - 1) / grid;             // run length per CTA
     int res_slots = (int)(chunk < max_slots ? chunk : max_slots);
     if (res_slots < 1) res_slots = 1;
@@ -2036,22 +2167,13 @@ static int visc3d_persistent_resident2(fs_visc3d* h, long long n, cudaStream_t s
         int ni = (int)(n < (1 << 20) ? n : (1 << 20));
         cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);
         if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-        if (h->ll_seq > 0xE0000000u) {               // sequence numbers about to wrap: start over on clean slots
-            e = cudaMemsetAsync(h->ll_slots, 0, kLLRedBytes, s);
-            if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-            h->ll_seq = 0;
-        }
-        LLRed llr;
-        llr.slots = h->ll_slots;
-        llr.seq = h->ll_seq;
-        h->ll_seq += (unsigned int)ni + 2u;          // a launch performs at most ni reductions
         FS_DISPATCH(h, {
             Visc3Dev<T> P = dev_view<T>(h);
             T* x = vec_ptr<T>(h, FS_VEC_X); T* r = vec_ptr<T>(h, FS_VEC_R); T* d = vec_ptr<T>(h, FS_VEC_D); T* q = vec_ptr<T>(h, FS_VEC_Q);
             T* w = reinterpret_cast<T*>(h->d2);
             const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
             CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
-            void* args[] = {&P, &x, &r, &d, &q, &w, &seg, &nsegp, &st, &partials, &bar, &ni, &res_slots, &llr, &prof};
+            void* args[] = {&P, &x, &r, &d, &q, &w, &seg, &nsegp, &st, &partials, &bar, &ni, &res_slots, &prof};
             e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kRes2Threads), args, smem, s);
         });
         if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported || e == cudaErrorInvalidValue) {
@@ -2117,7 +2239,8 @@ static int visc3d_iterations(fs_visc3d* h, double sm, long long n, cudaStream_t 
         if (st != 1) return st;                      // 1 = cooperative launch impossible here, nothing was enqueued
     }
     const bool graph_ok = !(h->comm && !h->peers);
-    return cg_enqueue_iterations(h->graph, graph_ok, sm, n, [&](cudaStream_t ss) { return visc3d_iteration(h, sm, ss); }, s, seg_level(h->seg.nseg));
+    return cg_enqueue_iterations(h->graph, graph_ok, sm, n, [&](cudaStream_t ss) { return visc3d_iteration(h, sm, ss); }, s,
+                                 seg_level(h->seg.nseg) * 4096 + (tuning_epoch() & 4095));
 }
 
 // pre-scaled coefficients of the CG-loop apply for this solve's operator (scale*mu) on the current active list

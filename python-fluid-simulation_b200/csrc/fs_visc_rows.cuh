@@ -104,8 +104,11 @@ __device__ __forceinline__ T visc_row(const T* const* __restrict__ coef, long lo
 // row that is not computed, so no neighbour masks (SURVEY A-1).
 // CF(plane, axis, sign) returns the coefficient of `plane` at i + sign*e_axis (sign = 0: at i itself); all three arguments
 // are compile-time constants after unrolling, so an accessor may map them to a fixed slot (shared-memory resident copy).
-template <typename T, int D, int A, class CF, class NB>
-__device__ __forceinline__ T visc_row_scaled_cf(long long i, const long long* st, T diag, T own, CF cf, NB nb) {
+// NBU(comp, p, m) returns component `comp` at i + e_p - e_m (p, m = axis numbers, -1 = no shift): the unit-vector form of
+// the neighbour accessor, so that a caller whose data does not sit at a flat lattice index (a shared-memory tile with
+// x-planes in separate ring buffers) can resolve every offset at compile time.
+template <typename T, int D, int A, class CF, class NBU>
+__device__ __forceinline__ T visc_row_scaled_u(T diag, T own, CF cf, NBU nbu) {
     T val = diag * own;
 #pragma unroll
     for (int ax = 0; ax < D; ++ax) {
@@ -117,16 +120,22 @@ __device__ __forceinline__ T visc_row_scaled_cf(long long i, const long long* st
             hi = cf(D + A + ax, ax, +1);
             lo = cf(D + A + ax, 0, 0);
         }
-        val -= hi * nb(A, i + st[ax]);
-        val -= lo * nb(A, i - st[ax]);
+        val -= hi * nbu(A, ax, -1);
+        val -= lo * nbu(A, -1, ax);
         if (ax != A) {                       // cross-component terms of component B = ax
-            val -= hi * nb(ax, i + st[ax]);
-            val += hi * nb(ax, i + st[ax] - st[A]);
-            val += lo * nb(ax, i);
-            val -= lo * nb(ax, i - st[A]);
+            val -= hi * nbu(ax, ax, -1);
+            val += hi * nbu(ax, ax, A);
+            val += lo * nbu(ax, -1, -1);
+            val -= lo * nbu(ax, -1, A);
         }
     }
     return val;
+}
+
+template <typename T, int D, int A, class CF, class NB>
+__device__ __forceinline__ T visc_row_scaled_cf(long long i, const long long* st, T diag, T own, CF cf, NB nb) {
+    auto nbu = [&](int comp, int p, int m) -> T { return nb(comp, i + (p >= 0 ? st[p] : 0) - (m >= 0 ? st[m] : 0)); };
+    return visc_row_scaled_u<T, D, A>(diag, own, cf, nbu);
 }
 
 template <typename T, int D, int A, class NB>

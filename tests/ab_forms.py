@@ -3,8 +3,9 @@
     python tests/ab_forms.py [N]
 
   * default scene (buckling N^3, mu=100): per-iteration time of the persistent CG window, whole-step rate, phase timeline and
-    the iterate after a fixed 200-iteration solve for resident_form in {0, 1, 2} x llred in {0, 1};
-  * dense scene (viscous column N^3, fluid rows): K1s / K2s alone and the iteration, with and without the L2 prefetch.
+    the iterate after a fixed 200-iteration solve for resident_form in {0, 1, 2};
+  * dense scene (viscous column N^3, fluid rows) and the benchmark scene with every fluid row visited: K1s alone and the
+    iteration for the forms of the stand-alone apply (k1_block, k1_tile).
 One JSON line per configuration on stdout."""
 import ctypes
 import json
@@ -71,10 +72,9 @@ sc = scenes.buckling(n, device="cuda", mu=MU)
 s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], cg_mode="persistent_sr")
 scale = sc["dt"] / s.cell_vol / sc["rho"]
 ref = None
-for form, ll in ((1, 0), (2, 0), (2, 1), (0, 0), (1, 0)):
+for form in (1, 2, 0, 1, 2):
     try:
         N.set_option("resident_form", form)
-        N.set_option("llred", ll)
         fixed_solve(s, sc, 200)
         it, delta = s.iterations, float(s.delta)
         x = [a.double().cpu().numpy().copy() for a in (s.x_x, s.x_y, s.x_z)]
@@ -85,13 +85,12 @@ for form, ll in ((1, 0), (2, 0), (2, 1), (0, 0), (1, 0)):
         ms_win = timed(lambda: N.check(lib.fs_visc3d_cg_enqueue(s._e.h, scale, MU, 512, stream()), "window"), 2)
         ms_step = timed(lambda: fixed_solve(s, sc, 200), 5)
         tl = timeline(s, scale)
-        emit(scene=f"buckling-{n}", resident_form=form, llred=ll, iterations=it, delta=delta, delta_rel_vs_first=abs(delta - ref[0]) / abs(ref[0]),
+        emit(scene=f"buckling-{n}", resident_form=form, iterations=it, delta=delta, delta_rel_vs_first=abs(delta - ref[0]) / abs(ref[0]),
              x_rel_l2_vs_first=err, cg_iteration_us=1e3 * ms_win / 512, ms_per_step=ms_step, iters_per_s=200 / (ms_step * 1e-3), phases_us=tl,
              segments=s.active_info()[0])
     except Exception as e:                                      # keep going: the other forms are still worth their numbers
-        emit(scene=f"buckling-{n}", resident_form=form, llred=ll, error=repr(e))
-for k in ("resident_form", "llred"):
-    N.set_option(k, -1)
+        emit(scene=f"buckling-{n}", resident_form=form, error=repr(e))
+N.set_option("resident_form", -1)
 del s, sc
 torch.cuda.empty_cache()
 
@@ -102,23 +101,48 @@ scale = col["dt"] / s.cell_vol / col["rho"]
 F = 3 * n * n * (n + 1)
 V7 = F + n ** 3 + 3 * (n + 1) * (n + 1) * n
 ref = None
-for pf in (0, 1, 0, 1):
+T = lambda rows, planes: 1000 * planes + 10 * rows + 1
+for blk, tile in ((0, 0), (4, 0), (0, 1), (0, T(4, 16)), (0, T(5, 16)), (0, T(6, 16)), (0, T(7, 8)), (0, T(7, 32)), (0, T(3, 16)), (0, 0)):
     try:
-        N.set_option("k1_prefetch", pf)
+        N.set_option("k1_block", blk)
+        N.set_option("k1_tile", tile)
         fixed_solve(s, col, 20)
         delta = float(s.delta)
         x = [a.double().cpu().numpy().copy() for a in (s.x_x, s.x_y, s.x_z)]
         if ref is None:
             ref = (delta, x)
-        same = all(np.array_equal(a, b) for a, b in zip(x, ref[1])) and delta == ref[0]
+        err = max(float(np.linalg.norm(a - b) / np.linalg.norm(b)) for a, b in zip(x, ref[1]))
         k = {}
         for which, name in ((1, "K1s"), (2, "K2s")):
             N.check(lib.fs_visc3d_kernel_enqueue(s._e.h, which, scale, MU, 3, stream()), "warm")
             k[name] = timed(lambda: N.check(lib.fs_visc3d_kernel_enqueue(s._e.h, which, scale, MU, 30, stream()), "time"), 1) / 30
         N.check(lib.fs_visc3d_cg_enqueue(s._e.h, scale, MU, 8, stream()), "warm")
         it_ms = timed(lambda: N.check(lib.fs_visc3d_cg_enqueue(s._e.h, scale, MU, 30, stream()), "window"), 1) / 30
-        emit(scene=f"column-{n}", k1_prefetch=pf, bit_identical_to_first=bool(same), K1s_ms=k["K1s"], K2s_ms=k["K2s"], iteration_ms=it_ms,
-             K1s_GBps=(2 * F + V7) * 8 / (k["K1s"] * 1e-3) / 1e9, iteration_GBps=(11 * F + V7) * 8 / (it_ms * 1e-3) / 1e9, segments=s.active_info()[0])
+        emit(scene=f"column-{n}", k1_block=blk, k1_tile=tile, delta_rel_vs_first=abs(delta - ref[0]) / abs(ref[0]), x_rel_l2_vs_first=err,
+             K1s_ms=k["K1s"], K2s_ms=k["K2s"], iteration_ms=it_ms, K1s_frac_of_peak=(2 * F + V7) * 8 / (k["K1s"] * 1e-3) / 1e9 / 6548.2,
+             iteration_frac_of_peak=(11 * F + V7) * 8 / (it_ms * 1e-3) / 1e9 / 6548.2, segments=s.active_info()[0])
     except Exception as e:
-        emit(scene=f"column-{n}", k1_prefetch=pf, error=repr(e))
-N.set_option("k1_prefetch", -1)
+        emit(scene=f"column-{n}", k1_block=blk, k1_tile=tile, error=repr(e))
+N.set_option("k1_block", -1)
+N.set_option("k1_tile", -1)
+del s, col
+torch.cuda.empty_cache()
+
+# ---- buckling scene, every fluid row (20 % of the segments, runs of 1-1.5 KB): the same mappings --------------------------
+sc = scenes.buckling(n, device="cuda", mu=MU)
+s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], cg_mode="kernels_sr", active_set="fluid")
+scale = sc["dt"] / s.cell_vol / sc["rho"]
+for blk in (0, 2, 4, 6, 0):
+    try:
+        N.set_option("k1_block", blk)
+        fixed_solve(s, sc, 20)
+        segs = s.active_info()[0]
+        N.check(lib.fs_visc3d_kernel_enqueue(s._e.h, 1, scale, MU, 3, stream()), "warm")
+        k1 = timed(lambda: N.check(lib.fs_visc3d_kernel_enqueue(s._e.h, 1, scale, MU, 30, stream()), "time"), 1) / 30
+        N.check(lib.fs_visc3d_cg_enqueue(s._e.h, scale, MU, 8, stream()), "warm")
+        it_ms = timed(lambda: N.check(lib.fs_visc3d_cg_enqueue(s._e.h, scale, MU, 60, stream()), "window"), 1) / 60
+        emit(scene=f"buckling-{n}-fluid", k1_block=blk, delta=float(s.delta), K1s_ms=k1, iteration_ms=it_ms, segments=segs,
+             K1s_frac_of_peak_active_bytes=segs * 32 * (13 * 8 + 1) / (k1 * 1e-3) / 1e9 / 6548.2)
+    except Exception as e:
+        emit(scene=f"buckling-{n}-fluid", k1_block=blk, error=repr(e))
+N.set_option("k1_block", -1)

@@ -1,7 +1,7 @@
-"""GPU: the implementation switches of the persistent single-reduction CG (fs_set_option) select between result-equivalent
-kernels — global-memory form, first and second shared-memory resident form, counter-based or flag-in-data grid reduction,
-L2 prefetch in the stand-alone K1s.  Every combination must give the iterates of the default path and the reference's
-iteration counts (ViscosityCGSolver3D.py:588-612)."""
+"""GPU: the implementation switches behind fs_set_option select between result-equivalent kernels — the persistent
+single-reduction CG through global memory or through the first / second shared-memory resident kernel; the stand-alone K1s
+with interleaved or blocked warp -> segment mapping, or as the shared-memory tiled kernel for dense lattices.  Every form
+must give the iterates of the others and the reference's iteration counts (ViscosityCGSolver3D.py:588-612)."""
 import numpy as np
 import pytest
 import torch
@@ -10,14 +10,14 @@ from conftest import load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-FORMS = [(0, 0), (1, 0), (2, 0), (2, 1)]          # (resident_form, llred)
+FORMS = [0, 1, 2]          # resident_form: global-memory kernel, first / second shared-memory resident kernel
 
 
 @pytest.fixture(autouse=True)
 def _restore_options():
     from solver import _native as N
     yield
-    for k in ("resident_form", "llred", "k1_prefetch"):
+    for k in ("resident_form", "k1_block", "k1_tile"):
         N.set_option(k, -1)
 
 
@@ -46,11 +46,10 @@ def test_forms_agree_on_fixed_window(grid, monkeypatch):
         monkeypatch.setenv("FLUIDSOLVER_B200_PERSIST_GRID", grid)
     sc = scenes.buckling(40, device="cuda", mu=50.0, gres=(40, 44, 36))
     out = {}
-    for form, ll in FORMS:
+    for form in FORMS:
         N.set_option("resident_form", form)
-        N.set_option("llred", ll)
-        out[(form, ll)] = _solve(sc, 50.0, max_iter=100, tol=0.0)
-    it0, d0, x0, _ = out[(0, 0)]
+        out[form] = _solve(sc, 50.0, max_iter=100, tol=0.0)
+    it0, d0, x0, _ = out[0]
     assert it0 == 100
     for key, (it, d, x, _) in out.items():
         assert it == it0, key
@@ -61,13 +60,12 @@ def test_forms_agree_on_fixed_window(grid, monkeypatch):
             assert rel_l2(a, b) < 1e-6, key
 
 
-@pytest.mark.parametrize("form,ll", FORMS)
+@pytest.mark.parametrize("form", FORMS)
 @pytest.mark.parametrize("tag", ["visc3d_solve_8x10x8", "visc3d_solve_stiff_6x8x6"])
-def test_forms_vs_reference_fixture(tag, form, ll):
+def test_forms_vs_reference_fixture(tag, form):
     from solver import _native as N
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
     N.set_option("resident_form", form)
-    N.set_option("llred", ll)
     f = load_golden(tag)
     s = ViscosityCGSolver3D(f["gres"], f["bound_size"], cg_mode="persistent_sr")
     v = [torch.as_tensor(f[k]).cuda() for k in ("vx", "vy", "vz")]
@@ -79,16 +77,14 @@ def test_forms_vs_reference_fixture(tag, form, ll):
         assert rel_l2(a.cpu().numpy(), f[f"v{n}_new"]) < 1e-4
 
 
-@pytest.mark.parametrize("form,ll", [(2, 0), (2, 1)])
-def test_second_form_converged_solve_and_repeated_solves(form, ll):
-    """Converged solves (several cooperative launches each, sequence numbers carried from launch to launch and from solve to
-    solve on the same handle) against the NumPy oracle."""
+@pytest.mark.parametrize("form", [1, 2])
+def test_resident_forms_converged_and_repeated_solves(form):
+    """Converged solves (several cooperative launches each) repeated on the same handle, against the NumPy oracle."""
     import scenes
     from oracle import numpy_oracle as O
     from solver import _native as N
     from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
     N.set_option("resident_form", form)
-    N.set_option("llred", ll)
     sc = scenes.buckling(24, device="cuda", mu=10.0)
     s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], cg_mode="persistent_sr")
     ref = O.ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
@@ -102,17 +98,54 @@ def test_second_form_converged_solve_and_repeated_solves(form, ll):
             assert rel_l2(a.cpu().numpy(), b) < 1e-4
 
 
-def test_k1_prefetch_changes_no_bit():
-    """The L2 prefetch of the stand-alone K1s is a hint: bit-identical iterates with and without it (value 2 forces it on
-    lists below the HBM-size threshold)."""
+def _solve_dtype(sc, mu, dtype, **kw):
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    s = ViscosityCGSolver3D(sc["gres"], sc["bound_size"], cg_mode="kernels_sr", active_set="fluid", dtype=dtype)
+    s.max_iter = kw.get("max_iter", 60)
+    v = [sc[k].clone() for k in ("vx", "vy", "vz")]
+    try:
+        s.solve(sc["dt"], mu, sc["rho"], *v, sc["sphi"], None, None, sc["lvol"], tol=0.0)
+    except ValueError:
+        pass
+    return s.iterations, float(s.delta), [a.double().cpu().numpy().copy() for a in (s.x_x, s.x_y, s.x_z)]
+
+
+@pytest.mark.parametrize("blk", [1, 3, 8])
+def test_k1_blocked_mapping_agrees(blk):
+    """Blocked warp -> segment mapping of the stand-alone K1s (1000 + n forces it on a list below the HBM-size threshold):
+    every active segment is visited exactly once — same delta and iterate as the interleaved mapping, up to the rounding of
+    a different reduction tree."""
     import scenes
     from solver import _native as N
     sc = scenes.buckling(40, device="cuda", mu=50.0, gres=(36, 40, 44))
-    res = {}
-    for pf in (0, 2):
-        N.set_option("k1_prefetch", pf)
-        res[pf] = _solve(sc, 50.0, max_iter=60, tol=0.0, cg_mode="kernels_sr", active_set="fluid")
-    assert res[0][0] == res[2][0] == 60
-    assert res[0][1] == res[2][1]
-    for a, b in zip(res[0][2], res[2][2]):
-        assert np.array_equal(a, b)
+    N.set_option("k1_block", 0)
+    N.set_option("k1_tile", 0)
+    it0, d0, x0 = _solve_dtype(sc, 50.0, torch.float64)
+    N.set_option("k1_block", 1000 + blk)
+    it, d, x = _solve_dtype(sc, 50.0, torch.float64)
+    assert it0 == it == 60
+    assert abs(d - d0) <= 1e-6 * abs(d0), (d, d0)
+    for a, b in zip(x, x0):
+        assert rel_l2(a, b) < 1e-9
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("rows,planes", [(0, 0), (2, 3), (3, 16), (5, 1)])
+@pytest.mark.parametrize("gres", [(36, 40, 44), (21, 17, 30)])
+def test_k1_tiled_kernel_agrees_with_list_kernel(gres, rows, planes, dtype):
+    """The shared-memory tiled K1s (forced on: mode 2; row-block height and planes per work item varied, incl. blocks that
+    overhang the last lattice row and single-plane items) computes the same w = A r and dot products as the list kernel:
+    identical CG trajectory up to the rounding of the reduction tree."""
+    import scenes
+    from solver import _native as N
+    sc = scenes.buckling(gres[0], device="cuda", mu=50.0, gres=gres)
+    N.set_option("k1_block", 0)
+    N.set_option("k1_tile", 0)
+    it0, d0, x0 = _solve_dtype(sc, 50.0, dtype)
+    N.set_option("k1_tile", 1000 * planes + 10 * rows + 2)
+    it, d, x = _solve_dtype(sc, 50.0, dtype)
+    assert it0 == it == 60
+    tol_d, tol_x = (1e-6, 1e-8) if dtype == torch.float64 else (1e-2, 1e-4)     # (rounding of the reduction tree, amplified over 60 stiff iterations)
+    assert abs(d - d0) <= tol_d * abs(d0), (d, d0)
+    for a, b in zip(x, x0):
+        assert rel_l2(a, b) < tol_x
