@@ -445,7 +445,8 @@ def kernel_study(solver, lib, N, torch, scale, args, esz, win=None):
     modes = {N.CG_KERNELS: "kernels", N.CG_PERSISTENT: "persistent", N.CG_KERNELS_SR: "kernels_sr", N.CG_PERSISTENT_SR: "persistent_sr"}
     return {"iter_ms": iter_ms, "kernel_ms": kern, "kernel_bytes": kbytes, "iter_bytes": sum(kbytes.values()), "working_set": pts * (22 * esz + 1),
             "persistent": persistent, "sr": sr, "mode": modes[mode],
-            "persistent_name": ("visc3d_cg_sr_persistent_kernel (phases A: apply + both dots, B: fused update; one cooperative launch per 64 iterations)" if sr else
+            "persistent_name": ("visc3d_cg_sr_resident2_kernel (phases A: apply + both dots, B: fused update; point-private data, r and segment ids resident in "
+                                "shared memory; one cooperative launch per 64 iterations)" if sr else
                                 "visc3d_cg_persistent_kernel (K1+K2+K3 phases of one cooperative launch per 64 iterations)"),
             "active": {"mode": "fluid" if solver._e.active_mode_name == "fluid" else "nonzero", "segments": segs, "segments_total": segs_total,
                        "computed_rows": rows, "cg_working_set_MB": pts * (22 * esz + 1) / 1e6}}

