@@ -51,7 +51,7 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """SM clocks / throttle reasons sampled DURING the timed region: NVML in-process every ~2 ms when available (the timed
+    """SM clocks / throttle reasons sampled DURING the timed region: NVML in-process every ~1 ms when available (the timed
     region of the default run is only tens of milliseconds), else `nvidia-smi` every 0.2 s."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -66,6 +66,7 @@ class ClockSampler:
         self._t = None
         self._nvml = None
         self._h = None
+        self._max = None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -81,7 +82,9 @@ class ClockSampler:
     def _sample_nvml(self):
         n = self._nvml
         sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
-        mx = float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM))
+        if self._max is None:                      # constant: asked once, so that a sample is two NVML calls (the timed region is ~10 ms)
+            self._max = float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM))
+        mx = self._max
         try:
             bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
         except Exception:
@@ -106,7 +109,7 @@ class ClockSampler:
                 if self._nvml is not None:          # NVML hiccup: fall back to nvidia-smi for the rest of the run
                     self._nvml = None
                     self.source = "nvidia-smi"
-            self._stop.wait(0.002 if self._nvml is not None else 0.2)
+            self._stop.wait(0.001 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -312,34 +315,38 @@ def run_native(args):
     persistent = kinfo["persistent"]
     iter_ms, kern, kbytes, iter_bytes = kinfo["iter_ms"], kinfo["kernel_ms"], kinfo["kernel_bytes"], kinfo["iter_bytes"]
     l2_resident = kinfo["working_set"] < 100e6
+    traffic, traffic_src, ipl = None, None, min(args.iters, 256)
+    key = None
+    try:                                              # dram bytes per launch from the committed ncu --set full capture of this command
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        dom_key = ("persistent_sr" if persistent and kinfo["sr"] else "persistent" if persistent else max(kern, key=kern.get).split()[0])
+        key = args.scene + ":" + args.active_set + ":" + dom_key
+        traffic = tj.get(key)
+        traffic_src = tj.get("_source", {}).get(key) if isinstance(tj.get("_source"), dict) else None
+        ipl = int(tj.get("_iterations_per_launch", {}).get(key, ipl)) if isinstance(tj.get("_iterations_per_launch"), dict) else ipl
+    except Exception:
+        pass
     if persistent:
         # the iteration runs as ONE persistent kernel (its phases are the kernels above): that kernel is the dominant one of the step
         dom = kinfo["persistent_name"]
         achieved = iter_bytes / (iter_ms * 1e-3) / 1e9
         dom_share = iter_ms * args.iters / ms_step
-        per_launch = {"iterations_per_launch": 64, "algorithmic_bytes_per_launch": 64 * iter_bytes,
-                      "note": "achieved = active-set bytes / duration, both per launch of 64 iterations; traffic = dram bytes of one such launch (ncu)"}
+        per_launch = {"iterations_per_launch": ipl, "algorithmic_bytes_per_launch": ipl * iter_bytes,
+                      "note": f"achieved = active-set bytes / duration, both per launch of {ipl} iterations (one launch runs the whole {args.iters}-iteration "
+                              "window plus the closing evaluation of r.r); traffic = dram bytes of one such launch (ncu)"}
     else:
         dom = max(kern, key=kern.get)
         achieved = kbytes[dom] / (kern[dom] * 1e-3) / 1e9
         dom_share = kern[dom] * args.iters / ms_step
         per_launch = {"iterations_per_launch": 1, "algorithmic_bytes_per_launch": kbytes[dom]}
-    traffic, traffic_src = None, None
-    try:                                              # dram bytes per launch from the committed ncu --set full capture of this command
-        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
-            tj = json.load(f)
-        key = args.scene + ":" + args.active_set + ":" + ("persistent_sr" if persistent and kinfo["sr"] else "persistent" if persistent else dom.split()[0])
-        traffic = tj.get(key)
-        traffic_src = tj.get("_source", {}).get(key) if isinstance(tj.get("_source"), dict) else None
-    except Exception:
-        pass
     iter_gbs = words_iter * esz * value / 1e9
     if l2_resident:
         # The active set of this scene (0.45 % of the face rows) is an L2-resident problem: the kernel is bound by grid-barrier
         # and L2 latency, not by HBM.  `achieved` is the rate at which it walks its (L2-resident) working set and is NOT
         # compared with the HBM peak; the DRAM-side figure is traffic / duration.  The HBM-bound regimes of the SAME kernels
         # are measured below (hbm_leg), against the HBM roofline.
-        dram_gbs = (traffic / (64 * iter_ms * 1e-3) / 1e9) if (traffic and persistent) else None
+        dram_gbs = (traffic / (ipl * iter_ms * 1e-3) / 1e9) if (traffic and persistent) else None
         roofline = {"bound": "l2-latency", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": None,
                     "achieved_is": "active-set bytes per second served from L2 (not DRAM); no HBM fraction is claimed for this leg",
                     "dram_GBps": dram_gbs, "dram_frac_of_peak": (dram_gbs / peak) if dram_gbs else None}
@@ -446,7 +453,7 @@ def kernel_study(solver, lib, N, torch, scale, args, esz, win=None):
     return {"iter_ms": iter_ms, "kernel_ms": kern, "kernel_bytes": kbytes, "iter_bytes": sum(kbytes.values()), "working_set": pts * (22 * esz + 1),
             "persistent": persistent, "sr": sr, "mode": modes[mode],
             "persistent_name": ("visc3d_cg_sr_resident2_kernel (phases A: apply + both dots, B: fused update; point-private data, r and segment ids resident in "
-                                "shared memory; one cooperative launch per 64 iterations)" if sr else
+                                "shared memory; one cooperative launch per up to 256 iterations)" if sr else
                                 "visc3d_cg_persistent_kernel (K1+K2+K3 phases of one cooperative launch per 64 iterations)"),
             "active": {"mode": "fluid" if solver._e.active_mode_name == "fluid" else "nonzero", "segments": segs, "segments_total": segs_total,
                        "computed_rows": rows, "cg_working_set_MB": pts * (22 * esz + 1) / 1e6}}

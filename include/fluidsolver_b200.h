@@ -102,6 +102,8 @@ int64_t fs_launch_count(void);
  *                     (0 = interleaved); applies to HBM-sized active sets, 1000 + n to every size
  *   "k1_tile"       : 0 / 1 = off / on: dense lattices run the stand-alone K1s as a shared-memory tiled kernel that marches
  *                     along x (2 = on every lattice, tests)
+ *   "sparse_setup"  : 0 / 1 = fs_visc3d_solve loads and extrapolates the velocities on the whole lattice / only around the
+ *                     active set (everything the solve reads is identical; the lattice vector x keeps stale values elsewhere)
  * Returns FS_OK, or FS_ERR_ARG for an unknown name. */
 int fs_set_option(const char* name, int value);
 

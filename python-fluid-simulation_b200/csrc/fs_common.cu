@@ -192,9 +192,9 @@ void CgHost::destroy() {
 }
 
 // tuning switches: explicit setting (fs_set_option) > environment variable > built-in default (-1)
-static int g_opt[OPT_COUNT] = {-2, -2, -2};
-static const char* const kOptEnv[OPT_COUNT] = {"FLUIDSOLVER_B200_RESIDENT", "FLUIDSOLVER_B200_K1BLOCK", "FLUIDSOLVER_B200_K1TILE"};
-static const char* const kOptName[OPT_COUNT] = {"resident_form", "k1_block", "k1_tile"};
+static int g_opt[OPT_COUNT] = {-2, -2, -2, -2};
+static const char* const kOptEnv[OPT_COUNT] = {"FLUIDSOLVER_B200_RESIDENT", "FLUIDSOLVER_B200_K1BLOCK", "FLUIDSOLVER_B200_K1TILE", "FLUIDSOLVER_B200_SPARSE_SETUP"};
+static const char* const kOptName[OPT_COUNT] = {"resident_form", "k1_block", "k1_tile", "sparse_setup"};
 
 static int g_opt_epoch = 0;
 int tuning_epoch() { return g_opt_epoch; }

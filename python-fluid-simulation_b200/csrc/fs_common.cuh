@@ -54,7 +54,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int coop_max_blocks(const void* fn, int threads, size_t dyn_smem = 0);
 
 // tuning switches (fs_set_option / FLUIDSOLVER_B200_* environment variables): -1 = not set, use the built-in default
-enum { OPT_RESIDENT_FORM = 0, OPT_K1BLOCK = 1, OPT_K1TILE = 2, OPT_COUNT = 3 };
+enum { OPT_RESIDENT_FORM = 0, OPT_K1BLOCK = 1, OPT_K1TILE = 2, OPT_SPARSE_SETUP = 3, OPT_COUNT = 4 };
 int tuning(int which);
 int tuning_epoch();      // bumped by every fs_set_option call: captured iteration graphs are keyed on it
 
@@ -1153,6 +1153,7 @@ struct IterGraph {
 
 constexpr int kCgBatch = 16;
 constexpr int kCgBatchPersistent = 64;   // iterations per launch of a persistent whole-iteration kernel (it stops early when done)
+constexpr int kCgBatchResident = 256;    // ... of the shared-memory resident kernels: every launch first loads / finally stores the resident state
 
 // Enqueue `n` iterations: whole batches of kCgBatch through the graph, the remainder launch by launch.
 template <class EnqueueOne>

@@ -228,6 +228,63 @@ __global__ void __launch_bounds__(512) visc3d_load_kernel(Lat3 L, const S* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sparse set-up (fs_visc3d_solve on a single GPU).  The CG reads the start vector only on the active rows and their
+// stencil neighbours; after three extrapolation sweeps those values depend on nothing farther than 4 lattice points
+// (Chebyshev) from an active row.  So instead of loading and sweeping the whole lattice, the solve marks the segments
+// within 5 rows / planes and 8 points of an active segment (a superset of that neighbourhood, one spare layer),
+// loads the caller's velocities there only, and runs sweep 1 over those segments only (sweeps 2 and 3 follow the work
+// lists as before).  The validity bytes are still initialised everywhere, so every sweep takes exactly the decisions of
+// the dense pass wherever its inputs are complete: by induction the state after sweep k equals the dense one within
+// 5 - k layers of the active rows — in particular on everything the solve reads.  Outside the marked region the lattice
+// vector x keeps whatever an earlier solve left there (nothing reads it; apply_viscosity only writes active rows back).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSparseSetupDefault = 1;    // fs_visc3d_solve loads / extrapolates around the active set only unless "sparse_setup" / FLUIDSOLVER_B200_SPARSE_SETUP = 0
+constexpr int kRegionLayers = 5;          // rows / planes around an active segment (4 are needed)
+constexpr int kRegionPoints = 8;          // points along z (4 are needed)
+
+__global__ void __launch_bounds__(256) visc3d_mark_region_kernel(Lat3 L, const int* __restrict__ seg, const int* __restrict__ nseg_p, long long nseg_total,
+                                                                 uint8_t* __restrict__ flags) {
+    constexpr int side = 2 * kRegionLayers + 1;
+    const long long n = (long long)*nseg_p * side * side;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long k = e / (side * side);
+        const int o = (int)(e - k * (side * side));
+        const int dx = o / side - kRegionLayers, dy = o % side - kRegionLayers;
+        const long long base = (long long)__ldg(seg + k) * kSegPts + dx * L.sx + dy * L.sy;
+        long long lo = base - kRegionPoints, hi = base + kSegPts - 1 + kRegionPoints;
+        if (hi < 0 || lo >= L.NL) continue;         // (rows that fall off a plane wrap into its neighbour: a harmless superset)
+        if (lo < 0) lo = 0;
+        if (hi >= L.NL) hi = L.NL - 1;
+        for (long long t = lo / kSegPts; t <= hi / kSegPts && t < nseg_total; ++t) flags[t] = 1;
+    }
+}
+
+// load (visc3d_load_kernel) on a list of segments: a warp per segment
+template <typename T, typename S>
+__global__ void __launch_bounds__(kThreads) visc3d_load_region_kernel(Lat3 L, const S* __restrict__ a0, const S* __restrict__ a1, const S* __restrict__ a2,
+                                                                      T* __restrict__ vec /*[3][NL]*/, const int* __restrict__ seg, const int* __restrict__ nseg_p) {
+    const int nseg = *nseg_p;
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const S* src[3] = {a0, a1, a2};
+    for (long long k = w0; k < nseg; k += nw) {
+        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
+        if (i >= L.NL) continue;
+        int x, y, z;
+        lat_decode(L, i, x, y, z);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int s0, s1, s2;
+            comp_shape(L, c, s0, s1, s2);
+            T v = T(0);
+            if (x < s0 && y < s1 && z < s2) v = (T)src[c][((long long)x * s1 + y) * s2 + z];
+            vec[c * L.NL + i] = v;
+        }
+    }
+}
+
 template <typename T, typename S>
 __global__ void __launch_bounds__(kThreads) visc3d_store_kernel(Lat3 L, const T* __restrict__ vec, const uint8_t* __restrict__ mask,
                                                                 S* __restrict__ a0, S* __restrict__ a1, S* __restrict__ a2, int mode) {
@@ -313,88 +370,108 @@ __device__ __forceinline__ bool extrap_try_fill(const Lat3& L, T* v_all, uint8_t
 // whose twelve bytes are all valid (fluid regions) exits after three loads, and the index decode and the neighbour
 // words are only touched where something may have to be filled.  Grid-stride, so the same kernel serves as the
 // fall-back of the list-driven sweeps (`only_if_overflow`).
+// one 4-point group of a sweep (see the kernels below)
+template <typename T>
+__device__ __forceinline__ void extrap_group(const Lat3& L, T* v_all, uint8_t* valid_all, int sweep, const ExtrapWork& W, int push_to,
+                                             const uint8_t* __restrict__ rowflag, long long g) {
+    const int nrows = L.X * L.Y;
+    const unsigned int sw = (unsigned int)sweep;
+    const uint32_t swv = sw * 0x01010101u;           // (sweep <= 250: fits a byte)
+    const long long i4 = g * 4;
+    if (rowflag) {
+        // sweep 1 can only fill next to an originally valid face: a group whose lattice row and the four rows around it
+        // (y+-1, x+-1) hold no fluid face at all (deep inside the solid, outside the container) is skipped on five bytes
+        const int row = (int)(L.NL < 0x7fffffffLL ? (unsigned int)i4 / (unsigned int)L.Zp : i4 / L.Zp);
+        const int ra = row > 0 ? row - 1 : row, rb = row + 1 < nrows ? row + 1 : row;
+        const int rc = row >= L.Y ? row - L.Y : row, rd = row + L.Y < nrows ? row + L.Y : row;
+        if (!(__ldg(rowflag + row) | __ldg(rowflag + ra) | __ldg(rowflag + rb) | __ldg(rowflag + rc) | __ldg(rowflag + rd))) return;
+    }
+    uint32_t own[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) own[c] = *reinterpret_cast<const uint32_t*>(valid_all + c * L.NL + i4);
+    if (bytes_all_nonzero(own[0]) && bytes_all_nonzero(own[1]) && bytes_all_nonzero(own[2])) return;
+    int x, y, z0;
+    lat_decode(L, i4, x, y, z0);
+    // the generation words of the four x/y neighbour groups and the two z-adjacent bytes, requested for all three
+    // components before any of them is looked at (one memory latency instead of three)
+    uint32_t nb[3][4];
+    unsigned int zl[3], zr[3];
+    bool need[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int s0, s1, s2;
+        comp_shape(L, c, s0, s1, s2);
+        need[c] = !bytes_all_nonzero(own[c]) && x >= 1 && x <= s0 - 2 && y >= 1 && y <= s1 - 2;
+        const uint8_t* va = valid_all + c * L.NL + i4;
+        nb[c][0] = need[c] ? *reinterpret_cast<const uint32_t*>(va + L.sx) : 0u;
+        nb[c][1] = need[c] ? *reinterpret_cast<const uint32_t*>(va - L.sx) : 0u;
+        nb[c][2] = need[c] ? *reinterpret_cast<const uint32_t*>(va + L.sy) : 0u;
+        nb[c][3] = need[c] ? *reinterpret_cast<const uint32_t*>(va - L.sy) : 0u;
+        zl[c] = (need[c] && z0 > 0) ? va[-1] : 0u;
+        zr[c] = (need[c] && z0 + 4 < L.Zp) ? va[4] : 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (!need[c]) continue;
+        // deep inside the solid every neighbour generation is 0: nothing can be filled (most groups that get here)
+        if ((nb[c][0] | nb[c][1] | nb[c][2] | nb[c][3] | own[c] | zl[c] | zr[c]) == 0u) continue;
+        int s0, s1, s2;
+        comp_shape(L, c, s0, s1, s2);
+        T* v = v_all + c * L.NL;
+        uint8_t* va = valid_all + c * L.NL;
+        // Which of the four faces can be filled is decided on whole words (byte-wise SIMD compares: 0xff where the
+        // generation g satisfies 1 <= g <= sweep), so a warp that only grazes the fluid/solid interface — nearly every warp
+        // that gets here — pays one short loop trip per candidate instead of the fully unrolled 4-face body.
+        auto okw = [&](uint32_t w) { return __vcmpgeu4(w, 0x01010101u) & __vcmpleu4(w, swv); };
+        auto okb = [&](unsigned int gg) { return gg >= 1u && gg <= sw; };
+        const uint32_t oxp = okw(nb[c][0]), oxm = okw(nb[c][1]), oyp = okw(nb[c][2]), oym = okw(nb[c][3]);
+        const uint32_t oown = okw(own[c]);
+        const uint32_t ozp = (oown >> 8) | (okb(zr[c]) ? 0xff000000u : 0u);       // byte k: face k+1 of the group, or the next group's first
+        const uint32_t ozm = (oown << 8) | (okb(zl[c]) ? 0x000000ffu : 0u);       // byte k: face k-1, or the previous group's last
+        uint32_t cand = __vcmpeq4(own[c], 0u) & (oxp | oxm | oyp | oym | ozp | ozm);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (!(z0 + k >= 1 && z0 + k <= s2 - 2)) cand &= ~(0xffu << (8 * k));
+        while (cand) {
+            const int sh = (__ffs((int)cand) - 1) & ~7;
+            cand &= ~(0xffu << sh);
+            const long long i = i4 + (sh >> 3);
+            T val = T(0);
+            int count = 0;                                // +x,-x,+y,-y,+z,-z  (:19-36)
+            if ((oxp >> sh) & 1u) { val += v[i + L.sx]; ++count; }
+            if ((oxm >> sh) & 1u) { val += v[i - L.sx]; ++count; }
+            if ((oyp >> sh) & 1u) { val += v[i + L.sy]; ++count; }
+            if ((oym >> sh) & 1u) { val += v[i - L.sy]; ++count; }
+            if ((ozp >> sh) & 1u) { val += v[i + 1]; ++count; }
+            if ((ozm >> sh) & 1u) { val += v[i - 1]; ++count; }
+            v[i] = val / (T)count;
+            va[i] = (uint8_t)(sweep + 1);
+            if (push_to >= 0) extrap_push(W, push_to, (unsigned int)(c * L.NL + i));
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, T* v_all, uint8_t* valid_all, int sweep /*1-based*/, ExtrapWork W,
                                                                       int push_to /*list to record fills in, -1 = none*/, int only_if_overflow,
                                                                       const uint8_t* __restrict__ rowflag /*sweep 1 only, or null*/,
                                                                       long long g_begin, long long g_end /*4-point groups of the swept x-planes*/) {
     if (only_if_overflow && (W.cap == 0u || W.count[2] == 0u)) return;
-    const int nrows = L.X * L.Y;
-    const unsigned int sw = (unsigned int)sweep;
-    const uint32_t swv = sw * 0x01010101u;           // (sweep <= 250: fits a byte)
-    for (long long g = g_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < g_end; g += (long long)gridDim.x * blockDim.x) {
-        const long long i4 = g * 4;
-        if (rowflag) {
-            // sweep 1 can only fill next to an originally valid face: a group whose lattice row and the four rows around it
-            // (y+-1, x+-1) hold no fluid face at all (deep inside the solid, outside the container) is skipped on five bytes
-            const int row = (int)(L.NL < 0x7fffffffLL ? (unsigned int)i4 / (unsigned int)L.Zp : i4 / L.Zp);
-            const int ra = row > 0 ? row - 1 : row, rb = row + 1 < nrows ? row + 1 : row;
-            const int rc = row >= L.Y ? row - L.Y : row, rd = row + L.Y < nrows ? row + L.Y : row;
-            if (!(__ldg(rowflag + row) | __ldg(rowflag + ra) | __ldg(rowflag + rb) | __ldg(rowflag + rc) | __ldg(rowflag + rd))) continue;
-        }
-        uint32_t own[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) own[c] = *reinterpret_cast<const uint32_t*>(valid_all + c * L.NL + i4);
-        if (bytes_all_nonzero(own[0]) && bytes_all_nonzero(own[1]) && bytes_all_nonzero(own[2])) continue;
-        int x, y, z0;
-        lat_decode(L, i4, x, y, z0);
-        // the generation words of the four x/y neighbour groups and the two z-adjacent bytes, requested for all three
-        // components before any of them is looked at (one memory latency instead of three)
-        uint32_t nb[3][4];
-        unsigned int zl[3], zr[3];
-        bool need[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            int s0, s1, s2;
-            comp_shape(L, c, s0, s1, s2);
-            need[c] = !bytes_all_nonzero(own[c]) && x >= 1 && x <= s0 - 2 && y >= 1 && y <= s1 - 2;
-            const uint8_t* va = valid_all + c * L.NL + i4;
-            nb[c][0] = need[c] ? *reinterpret_cast<const uint32_t*>(va + L.sx) : 0u;
-            nb[c][1] = need[c] ? *reinterpret_cast<const uint32_t*>(va - L.sx) : 0u;
-            nb[c][2] = need[c] ? *reinterpret_cast<const uint32_t*>(va + L.sy) : 0u;
-            nb[c][3] = need[c] ? *reinterpret_cast<const uint32_t*>(va - L.sy) : 0u;
-            zl[c] = (need[c] && z0 > 0) ? va[-1] : 0u;
-            zr[c] = (need[c] && z0 + 4 < L.Zp) ? va[4] : 0u;
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (!need[c]) continue;
-            // deep inside the solid every neighbour generation is 0: nothing can be filled (most groups that get here)
-            if ((nb[c][0] | nb[c][1] | nb[c][2] | nb[c][3] | own[c] | zl[c] | zr[c]) == 0u) continue;
-            int s0, s1, s2;
-            comp_shape(L, c, s0, s1, s2);
-            T* v = v_all + c * L.NL;
-            uint8_t* va = valid_all + c * L.NL;
-            // Which of the four faces can be filled is decided on whole words (byte-wise SIMD compares: 0xff where the
-            // generation g satisfies 1 <= g <= sweep), so a warp that only grazes the fluid/solid interface — nearly every warp
-            // that gets here — pays one short loop trip per candidate instead of the fully unrolled 4-face body.
-            auto okw = [&](uint32_t w) { return __vcmpgeu4(w, 0x01010101u) & __vcmpleu4(w, swv); };
-            auto okb = [&](unsigned int gg) { return gg >= 1u && gg <= sw; };
-            const uint32_t oxp = okw(nb[c][0]), oxm = okw(nb[c][1]), oyp = okw(nb[c][2]), oym = okw(nb[c][3]);
-            const uint32_t oown = okw(own[c]);
-            const uint32_t ozp = (oown >> 8) | (okb(zr[c]) ? 0xff000000u : 0u);       // byte k: face k+1 of the group, or the next group's first
-            const uint32_t ozm = (oown << 8) | (okb(zl[c]) ? 0x000000ffu : 0u);       // byte k: face k-1, or the previous group's last
-            uint32_t cand = __vcmpeq4(own[c], 0u) & (oxp | oxm | oyp | oym | ozp | ozm);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (!(z0 + k >= 1 && z0 + k <= s2 - 2)) cand &= ~(0xffu << (8 * k));
-            while (cand) {
-                const int sh = (__ffs((int)cand) - 1) & ~7;
-                cand &= ~(0xffu << sh);
-                const long long i = i4 + (sh >> 3);
-                T val = T(0);
-                int count = 0;                                // +x,-x,+y,-y,+z,-z  (:19-36)
-                if ((oxp >> sh) & 1u) { val += v[i + L.sx]; ++count; }
-                if ((oxm >> sh) & 1u) { val += v[i - L.sx]; ++count; }
-                if ((oyp >> sh) & 1u) { val += v[i + L.sy]; ++count; }
-                if ((oym >> sh) & 1u) { val += v[i - L.sy]; ++count; }
-                if ((ozp >> sh) & 1u) { val += v[i + 1]; ++count; }
-                if ((ozm >> sh) & 1u) { val += v[i - 1]; ++count; }
-                v[i] = val / (T)count;
-                va[i] = (uint8_t)(sweep + 1);
-                if (push_to >= 0) extrap_push(W, push_to, (unsigned int)(c * L.NL + i));
-            }
-        }
+    for (long long g = g_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < g_end; g += (long long)gridDim.x * blockDim.x)
+        extrap_group<T>(L, v_all, valid_all, sweep, W, push_to, rowflag, g);
+}
+
+// The same pass restricted to the 4-point groups of a list of 32-point segments (sparse set-up: the neighbourhood of the
+// active set, see visc3d_mark_region_kernel).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) visc3d_extrapolate_region_kernel(Lat3 L, T* v_all, uint8_t* valid_all, int sweep, ExtrapWork W, int push_to,
+                                                                             const uint8_t* __restrict__ rowflag, const int* __restrict__ seg,
+                                                                             const int* __restrict__ nseg_p) {
+    const long long n8 = (long long)*nseg_p * (kSegPts / 4);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += (long long)gridDim.x * blockDim.x) {
+        const long long g = (long long)__ldg(seg + (e >> 3)) * (kSegPts / 4) + (e & 7);
+        if (g * 4 >= L.NL) continue;
+        extrap_group<T>(L, v_all, valid_all, sweep, W, push_to, rowflag, g);
     }
 }
 
@@ -1920,7 +1997,7 @@ int fs_visc3d_store(fs_visc3d* h, int vec, void* vx, void* vy, void* vz, int dst
     return FS_OK;
 }
 
-int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
+static int visc3d_extrapolate_impl(fs_visc3d* h, int vec, int sweeps, void* stream, const SegList* region /*sweep 1 only looks at these segments, or null*/) {
     if (!h) return fail(FS_ERR_ARG, "null handle");
     if (!h->packed) return fail(FS_ERR_STATE, "fs_visc3d_extrapolate: call fs_visc3d_pack first");
     if (vec < 0 || vec >= FS_NUM_VECS) return fail(FS_ERR_ARG, "fs_visc3d_extrapolate: bad vector id");
@@ -1946,7 +2023,11 @@ int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
     const int full_grid = (int)((g_end - g_begin + kThreads - 1) / kThreads);
     for (int k = 1; k <= sweeps; ++k) {
         const int push_to = (W.cap && k < sweeps) ? ((k - 1) & 1) : -1;
-        if (k == 1 || !W.cap) {
+        if (k == 1 && region && W.cap) {
+            FS_DISPATCH(h, visc3d_extrapolate_region_kernel<T><<<kSMs * 16, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, push_to, h->rowflag,
+                                                                                             region->list, region->nseg_dev));
+            FS_LAUNCH_CHECK();
+        } else if (k == 1 || !W.cap) {
             FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<full_grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, push_to, 0,
                                                                                        k == 1 ? h->rowflag : nullptr, g_begin, g_end));
             FS_LAUNCH_CHECK();
@@ -1964,6 +2045,10 @@ int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
         }
     }
     return FS_OK;
+}
+
+int fs_visc3d_extrapolate(fs_visc3d* h, int vec, int sweeps, void* stream) {
+    return visc3d_extrapolate_impl(h, vec, sweeps, stream, nullptr);
 }
 
 static int visc3d_general(fs_visc3d* h, double scale, double mu, int src, int dst, int mode, cudaStream_t s) {
@@ -2290,6 +2375,16 @@ static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t 
     return FS_OK;
 }
 
+// iterations per enqueue of cg_drive: stand-alone kernels go out in small batches (the host checks the convergence flag in
+// between); a persistent kernel stops by itself when the state says done, so its launches are long — and longer still for
+// the resident kernels, whose every launch first loads and finally stores the shared-memory resident state
+static int visc3d_batch(const fs_visc3d* h) {
+    if (!visc3d_use_persistent(h)) return kCgBatch;
+    const int form = tuning(OPT_RESIDENT_FORM);
+    const bool resident = visc3d_use_sr(h) && !h->peers && !h->resident_failed && (form < 0 ? kResidentFormDefault : form) != 0;
+    return resident ? kCgBatchResident : kCgBatchPersistent;
+}
+
 static int visc3d_iterations(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
     if (visc3d_use_persistent(h)) {
         const int st = visc3d_persistent(h, sm, n, s);
@@ -2382,7 +2477,7 @@ int fs_visc3d_cg(fs_visc3d* h, double scale, double mu, double tol, int64_t max_
     const double sm = scale * mu;
     // single-reduction CG: one extra slot whose apply evaluates r.r of the last iterate (and sets the final status)
     return cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter + (visc3d_use_sr(h) ? 1 : 0), stats, s,
-                    visc3d_use_persistent(h) ? kCgBatchPersistent : kCgBatch);
+                    visc3d_batch(h));
 }
 
 int fs_visc3d_cg_enqueue(fs_visc3d* h, double scale, double mu, int64_t n, void* stream) {
@@ -2508,7 +2603,7 @@ int fs_visc3d_solve_packed(fs_visc3d* h, double dt, double mu, double rho, doubl
     const double sm = scale * mu;
     FS_TRY(visc3d_cg_begin_sparse(h, scale, mu, tol, max_iter, s));
     int status = cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter + (visc3d_use_sr(h) ? 1 : 0), stats, s,
-                          visc3d_use_persistent(h) ? kCgBatchPersistent : kCgBatch);
+                          visc3d_batch(h));
     if (status != FS_OK) return status;
     const int grid = seg_grid(h->seg.nseg, kThreads / 32, kSMs * 4);
     if (vel_dtype == FS_F32) {
@@ -2531,12 +2626,29 @@ int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_
     const double scale = dt / cell_vol / rho;                                   // :567
     const double sm = scale * mu;
     FS_TRY(fs_visc3d_pack(h, sphi, lvol, cell_vol * 0.125, stream));            // :568 (+ active segment list)
-    FS_TRY(fs_visc3d_load(h, FS_VEC_X, vx, vy, vz, vel_dtype, stream));         // :569-571
-    FS_TRY(fs_visc3d_extrapolate(h, FS_VEC_X, 3, stream));                      // :573
+    const int sp = tuning(OPT_SPARSE_SETUP);
+    if ((sp < 0 ? kSparseSetupDefault : sp) != 0 && !h->comm && !h->windowed && h->work.cap != 0u) {
+        // :569-573 where the solve looks: velocities loaded and extrapolated around the active set only (see visc3d_mark_region_kernel)
+        FS_TRY(h->xseg.finish());
+        FS_CUDA(cudaMemsetAsync(h->xflags, 0, (size_t)h->xseg.nseg_total, s));
+        visc3d_mark_region_kernel<<<kSMs * 8, 256, 0, s>>>(h->L, h->seg.list, h->seg.nseg_dev, h->xseg.nseg_total, h->xflags);
+        FS_LAUNCH_CHECK();
+        FS_TRY(h->xseg.enqueue(h->xflags, s, 1));
+        if (vel_dtype == FS_F32) {
+            FS_DISPATCH(h, visc3d_load_region_kernel<T, float><<<kSMs * 8, kThreads, 0, s>>>(h->L, (const float*)vx, (const float*)vy, (const float*)vz, vec_ptr<T>(h, FS_VEC_X), h->xseg.list, h->xseg.nseg_dev));
+        } else {
+            FS_DISPATCH(h, visc3d_load_region_kernel<T, double><<<kSMs * 8, kThreads, 0, s>>>(h->L, (const double*)vx, (const double*)vy, (const double*)vz, vec_ptr<T>(h, FS_VEC_X), h->xseg.list, h->xseg.nseg_dev));
+        }
+        FS_LAUNCH_CHECK();
+        FS_TRY(visc3d_extrapolate_impl(h, FS_VEC_X, 3, stream, &h->xseg));
+    } else {
+        FS_TRY(fs_visc3d_load(h, FS_VEC_X, vx, vy, vz, vel_dtype, stream));     // :569-571
+        FS_TRY(fs_visc3d_extrapolate(h, FS_VEC_X, 3, stream));                  // :573
+    }
     FS_TRY(visc3d_cg_begin_sparse(h, scale, mu, tol, max_iter, s));             // :574-587 on the active set
     // :588-612 (single-reduction CG: one extra slot whose apply evaluates r.r of the last iterate and sets the final status)
     int status = cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter + (visc3d_use_sr(h) ? 1 : 0), stats, s,
-                          visc3d_use_persistent(h) ? kCgBatchPersistent : kCgBatch);
+                          visc3d_batch(h));
     if (status != FS_OK) return status;                                         // the reference raises before write-back
     {
         // :613 — only rows of the active set can differ from what was loaded from these very arrays; every other fluid face
@@ -2550,6 +2662,7 @@ int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_
         FS_LAUNCH_CHECK();
     }
     FS_CUDA(cudaStreamSynchronize(s));
+    FS_TRY(h->xseg.finish());                                                   // (region list of a sparse set-up: its count has arrived long ago)
     return FS_OK;
 }
 

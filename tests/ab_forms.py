@@ -91,6 +91,20 @@ for form in (1, 2, 0, 1, 2):
     except Exception as e:                                      # keep going: the other forms are still worth their numbers
         emit(scene=f"buckling-{n}", resident_form=form, error=repr(e))
 N.set_option("resident_form", -1)
+for sp in (0, 1, 0, 1):                                  # dense / sparse set-up of solve() on the default forms
+    try:
+        N.set_option("sparse_setup", sp)
+        v = fixed_solve(s, sc, 200)
+        d200 = float(s.delta)
+        r = [a.clone() for a in (s.r_x, s.r_y, s.r_z)]
+        if sp == 0:
+            ref_r, ref_d = r, d200
+        ms_step = timed(lambda: fixed_solve(s, sc, 200), 10)
+        emit(scene=f"buckling-{n}", sparse_setup=sp, delta=d200, delta_equal_dense=(d200 == ref_d),
+             r_equal_dense=all(bool(torch.equal(a, b)) for a, b in zip(r, ref_r)), ms_per_step=ms_step, iters_per_s=200 / (ms_step * 1e-3))
+    except Exception as e:
+        emit(scene=f"buckling-{n}", sparse_setup=sp, error=repr(e))
+N.set_option("sparse_setup", -1)
 del s, sc
 torch.cuda.empty_cache()
 

@@ -17,7 +17,7 @@ FORMS = [0, 1, 2]          # resident_form: global-memory kernel, first / second
 def _restore_options():
     from solver import _native as N
     yield
-    for k in ("resident_form", "k1_block", "k1_tile"):
+    for k in ("resident_form", "k1_block", "k1_tile", "sparse_setup"):
         N.set_option(k, -1)
 
 
@@ -149,3 +149,42 @@ def test_k1_tiled_kernel_agrees_with_list_kernel(gres, rows, planes, dtype):
     assert abs(d - d0) <= tol_d * abs(d0), (d, d0)
     for a, b in zip(x, x0):
         assert rel_l2(a, b) < tol_x
+
+
+@pytest.mark.parametrize("gres", [(24, 24, 24), (36, 40, 44)])
+@pytest.mark.parametrize("cap", [None, "7"])
+def test_sparse_setup_equals_dense_setup(gres, cap, monkeypatch):
+    """fs_visc3d_solve with the sparse set-up (velocities loaded / extrapolated around the active set only) against the
+    dense set-up: RHS, first residual, iteration count, delta and the written-back velocities are IDENTICAL BITS — on
+    a sequence of solves with changing liquid regions on the same object (the lattice vector keeps stale values outside
+    the region of each solve), with work lists large enough and overflowing (cap=7: sweeps 2 and 3 fall back to full
+    passes)."""
+    import scenes
+    from solver import _native as N
+    from solver.ViscosityCGSolver3D import ViscosityCGSolver3D
+    if cap is not None:
+        monkeypatch.setenv("FLUIDSOLVER_B200_EXTRAP_CAP", cap)
+    sc = scenes.buckling(gres[0], device="cuda", mu=10.0, gres=gres)
+    lv2 = sc["lvol"].clone()
+    lv2[:, : lv2.shape[1] // 3] = 0                      # drain the pool
+    lv3 = sc["lvol"].clone()
+    lv3[: lv3.shape[0] // 2] = 0                         # keep the liquid of one half only
+    N.set_option("sparse_setup", 1)
+    sparse = ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
+    torch.manual_seed(5)
+    for lvol in (sc["lvol"], lv2, lv3, sc["lvol"]):
+        vin = [sc[k] + 0.05 * torch.randn_like(sc[k]) for k in ("vx", "vy", "vz")]      # new velocities every step
+        N.set_option("sparse_setup", 0)
+        dense = ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
+        vd = [a.clone() for a in vin]
+        dense.solve(sc["dt"], 10.0, sc["rho"], *vd, sc["sphi"], None, None, lvol)
+        N.set_option("sparse_setup", 1)
+        vs = [a.clone() for a in vin]
+        sparse.solve(sc["dt"], 10.0, sc["rho"], *vs, sc["sphi"], None, None, lvol)
+        assert sparse.iterations == dense.iterations and sparse.delta == dense.delta
+        for nm in ("b", "r"):
+            for c in "xyz":
+                assert torch.equal(getattr(sparse, f"{nm}_{c}"), getattr(dense, f"{nm}_{c}")), (nm, c)
+        for a, b in zip(vs, vd):
+            assert torch.equal(a, b)
+        assert any(not torch.equal(a, b) for a, b in zip(vs, vin))          # (the solve did change something)
