@@ -97,7 +97,7 @@ const char* fs_last_error(void);
 int64_t fs_launch_count(void);
 /* Tuning switches of the kernels (the programmatic form of the FLUIDSOLVER_B200_* environment variables; they select between
  * result-equivalent implementations and never change what is computed).  value < 0 restores the default.
- *   "resident_form" : 0 = persistent CG through global memory, 1 / 2 = first / second shared-memory resident kernel
+ *   "resident_form" : 0 = persistent CG through global memory, non-zero = shared-memory resident kernel
  *   "k1_block"      : n = trips of consecutive segments a CTA of the stand-alone K1s takes before it jumps ahead by the grid
  *                     (0 = interleaved); applies to HBM-sized active sets, 1000 + n to every size
  *   "k1_tile"       : 0 / 1 = off / on: dense lattices run the stand-alone K1s as a shared-memory tiled kernel that marches

@@ -253,9 +253,10 @@ __global__ void __launch_bounds__(256) visc3d_mark_region_kernel(Lat3 L, const i
         const int dx = o / side - kRegionLayers, dy = o % side - kRegionLayers;
         const long long base = (long long)__ldg(seg + k) * kSegPts + dx * L.sx + dy * L.sy;
         long long lo = base - kRegionPoints, hi = base + kSegPts - 1 + kRegionPoints;
-        if (hi < 0 || lo >= L.NL) continue;         // (rows that fall off a plane wrap into its neighbour: a harmless superset)
-        if (lo < 0) lo = 0;
-        if (hi >= L.NL) hi = L.NL - 1;
+        const long long w_lo = (long long)L.wlo * L.sx, w_hi = (long long)(L.whi + 1) * L.sx - 1;     // the planes this handle loads (whole lattice: 0 .. NL-1)
+        if (hi < w_lo || lo > w_hi) continue;       // (rows that fall off a plane wrap into its neighbour: a harmless superset)
+        if (lo < w_lo) lo = w_lo;
+        if (hi > w_hi) hi = w_hi;
         for (long long t = lo / kSegPts; t <= hi / kSegPts && t < nseg_total; ++t) flags[t] = 1;
     }
 }
@@ -274,12 +275,14 @@ __global__ void __launch_bounds__(kThreads) visc3d_load_region_kernel(Lat3 L, co
         if (i >= L.NL) continue;
         int x, y, z;
         lat_decode(L, i, x, y, z);
+        if (x < L.wlo || x > L.whi) continue;       // (a segment that straddles the first / last plane of an x-window)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             int s0, s1, s2;
             comp_shape(L, c, s0, s1, s2);
+            const int xs = c == 0 ? L.whi + 1 : L.wcells;          // planes present in the caller's (windowed) array: [wlo, xs)
             T v = T(0);
-            if (x < s0 && y < s1 && z < s2) v = (T)src[c][((long long)x * s1 + y) * s2 + z];
+            if (x < xs && y < s1 && z < s2) v = (T)src[c][((long long)(x - L.wlo) * s1 + y) * s2 + z];
             vec[c * L.NL + i] = v;
         }
     }
@@ -466,11 +469,11 @@ __global__ void __launch_bounds__(kThreads) visc3d_extrapolate_kernel(Lat3 L, T*
 template <typename T>
 __global__ void __launch_bounds__(kThreads) visc3d_extrapolate_region_kernel(Lat3 L, T* v_all, uint8_t* valid_all, int sweep, ExtrapWork W, int push_to,
                                                                              const uint8_t* __restrict__ rowflag, const int* __restrict__ seg,
-                                                                             const int* __restrict__ nseg_p) {
+                                                                             const int* __restrict__ nseg_p, long long g_begin, long long g_end) {
     const long long n8 = (long long)*nseg_p * (kSegPts / 4);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += (long long)gridDim.x * blockDim.x) {
         const long long g = (long long)__ldg(seg + (e >> 3)) * (kSegPts / 4) + (e & 7);
-        if (g * 4 >= L.NL) continue;
+        if (g < g_begin || g >= g_end) continue;    // (the swept x-planes: the whole lattice, or an x-window minus its edge planes)
         extrap_group<T>(L, v_all, valid_all, sweep, W, push_to, rowflag, g);
     }
 }
@@ -1116,201 +1119,20 @@ __global__ void __launch_bounds__(kPersistThreads, 1) visc3d_cg_sr_persistent_ke
 // ---------------------------------------------------------------------------------------------
 // Single-reduction CG with the POINT-PRIVATE data resident in shared memory.  In this recurrence only r is ever read by
 // another thread (the stencil of the apply); p, s, w, x and the 16 pre-scaled coefficient values of a point are touched by
-// the lane that owns the point and by nobody else.  The warp -> segment assignment is static (warp g takes segments g,
-// g + nwarps, ...), so the first kResTrips-th trips of every warp keep all of that in shared memory for the whole launch:
-// 28 values per point (16 coefficients, p, s, w, x) + the activity byte = 7200 B per fp64 segment, 32 segments per CTA in
-// the 227 KB of a B200 SM = 4 736 segments on the chip (the 256^3 benchmark scene has 4 253).  Per iteration the L2 then
-// sees the r neighbourhood reads of phase A and one read + one write of r in phase B (about 27 MB instead of 62 MB on that
-// scene, whose iteration is L2-bandwidth-bound between its two grid barriers).  Segments beyond the resident trips run
+// the lane that owns the point and by nobody else.  Every CTA owns a contiguous run of the (lattice-ordered) active list —
+// the y / z neighbours of its segments are mostly its own segments and hit in L1 during phase A — and position li of the
+// run belongs to warp li % 16, so all of that stays in shared memory for the whole launch, together with the residual of
+// the own points and the segment ids: 31 values per point (16 coefficients, p, s, w, x, r) + the activity byte + the id =
+// 7 972 B per fp64 segment.  Slots are addressed by the position of a segment in the CTA's run, so exactly `chunk` slots are
+// needed: 29 for the 4 253 segments of the 256^3 benchmark scene = 231 KB of the 227 KiB an SM offers.  Phase A reads the r
+// neighbourhood from L2 / L1; phase B touches global memory only to STORE the new r for the neighbours' stencils — no
+// dependent L2 read in it (a first form of this kernel kept r and the segment ids in global memory and spent two sequential
+// round trips there per trip: 8.1 instead of 7.6 us per iteration).  Positions beyond `res_slots` (longer lists) run
 // through global memory exactly like visc3d_cg_sr_persistent_kernel.  p, s, x are loaded at kernel entry and written back
-// at exit (once per launch of up to 64 iterations), so the global state between launches is unchanged.
-// ---------------------------------------------------------------------------------------------
-constexpr int kResVals = 28;      // per point: 16 coefficients, p[3], s[3], w[3], x[3]
-template <typename T> __host__ __device__ constexpr size_t res_slot_bytes() { return (size_t)kResVals * 32 * sizeof(T) + 32; }
-
-template <typename T, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) visc3d_cg_sr_resident_kernel(Visc3Dev<T> P, T* x, T* r, T* p, T* sv, T* w,
-                                                                                   const int* __restrict__ seg, const int* __restrict__ nseg_p,
-                                                                                   CgState* st, double* partials, GridBar* bar, int n_slots, int res_trips,
-                                                                                   unsigned long long* prof) {
-    extern __shared__ __align__(16) unsigned char res_smem[];
-    constexpr int kWarps = THREADS / 32;
-    T* const svals = reinterpret_cast<T*>(res_smem);                                           // [res_trips*kWarps][kResVals][32]
-    uint8_t* const sact = res_smem + (size_t)res_trips * kWarps * kResVals * 32 * sizeof(T);    // [res_trips*kWarps][32]
-    const Lat3& L = P.L;
-    const long long NL = L.NL;
-    const long long stv[3] = {L.sx, L.sy, 1};
-    const int nseg = *nseg_p;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // Every CTA owns a CONTIGUOUS run of the (lattice-ordered) active list, so the y / z neighbours of its segments are
-    // mostly its own segments and hit in L1 during phase A; warp `warp` takes entries warp, warp + 16, ... of the run.
-    const long long chunk = ((long long)nseg + gridDim.x - 1) / gridDim.x;
-    const long long c_lo = (long long)blockIdx.x * chunk;
-    const long long c_hi = c_lo + chunk < nseg ? c_lo + chunk : nseg;
-    const long long gw = c_lo + warp, nw = kWarps;
-
-    // ---- prologue: point-private data of the resident trips -> shared memory
-    for (int j = 0; j < res_trips; ++j) {
-        const long long k = gw + (long long)j * nw;
-        if (k >= c_hi) break;
-        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
-        const bool in = i < NL;
-        const long long jj = in ? i : (NL - 1);
-        T* S = svals + ((size_t)(j * kWarps + warp) * kResVals) * 32 + lane;
-        S[0 * 32] = __ldg(P.cs[0] + jj); S[1 * 32] = __ldg(P.cs[1] + jj); S[2 * 32] = __ldg(P.cs[2] + jj);
-        S[3 * 32] = __ldg(P.cs[3] + jj);
-        S[4 * 32] = __ldg(P.cs[3] + jj - stv[0]); S[5 * 32] = __ldg(P.cs[3] + jj - stv[1]); S[6 * 32] = __ldg(P.cs[3] + jj - stv[2]);
-        S[7 * 32] = __ldg(P.cs[4] + jj); S[8 * 32] = __ldg(P.cs[4] + jj + stv[1]); S[9 * 32] = __ldg(P.cs[4] + jj + stv[0]);
-        S[10 * 32] = __ldg(P.cs[5] + jj); S[11 * 32] = __ldg(P.cs[5] + jj + stv[2]); S[12 * 32] = __ldg(P.cs[5] + jj + stv[0]);
-        S[13 * 32] = __ldg(P.cs[6] + jj); S[14 * 32] = __ldg(P.cs[6] + jj + stv[2]); S[15 * 32] = __ldg(P.cs[6] + jj + stv[1]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            S[(16 + c) * 32] = in ? p[c * NL + i] : T(0);
-            S[(19 + c) * 32] = in ? sv[c * NL + i] : T(0);
-            S[(22 + c) * 32] = T(0);
-            S[(25 + c) * 32] = in ? x[c * NL + i] : T(0);
-        }
-        sact[(size_t)(j * kWarps + warp) * 32 + lane] = in ? (uint8_t)((unsigned int)__ldg(P.act + i) & kActCompute) : (uint8_t)0;
-    }
-    __syncwarp();
-
-    double delta = st->delta, gamma_old = st->delta_old, dl = st->dq, alpha_d = st->alpha, beta_d = st->beta;
-    bool first = st->sr_first != 0;
-    const double tol2 = st->tol2;
-    long long iter = st->iter;
-    const long long max_iter = st->max_iter;
-    int done = st->done;
-    GridSync gs{bar, 0u};
-    const bool stamp = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-    int np = 0;
-    auto tick = [&]() {
-        if (stamp && np < 1024) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); prof[np++] = t; }
-    };
-    auto nb = [&](int comp, long long j) -> T { return r[comp * NL + j]; };      // coherent: other CTAs rewrote r before the last barrier
-    const PeerHot nohot = {};
-    for (int it = 0; it < n_slots && !done; ++it) {
-        tick();
-        // ---- phase A: w = A r, (r.r, w.r)
-        double rr = 0.0, wr = 0.0;
-        {
-            int j = 0;
-            for (long long k = gw; k < c_hi; k += nw, ++j) {
-                const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
-                const bool in = i < NL;
-                const long long jj = in ? i : (NL - 1);
-                const T du = nb(0, jj), dv = nb(1, jj), dw = nb(2, jj);
-                T ru, rv, rw;
-                unsigned int a;
-                if (j < res_trips) {
-                    T* S = svals + ((size_t)(j * kWarps + warp) * kResVals) * 32 + lane;
-                    a = sact[(size_t)(j * kWarps + warp) * 32 + lane];
-                    auto cf = [&](int plane, int axis, int sign) -> T { return S[visc3_cslot(plane, axis, sign) * 32]; };
-                    ru = visc_row_scaled_cf<T, 3, 0>(jj, stv, S[0 * 32], du, cf, nb);
-                    rv = visc_row_scaled_cf<T, 3, 1>(jj, stv, S[1 * 32], dv, cf, nb);
-                    rw = visc_row_scaled_cf<T, 3, 2>(jj, stv, S[2 * 32], dw, cf, nb);
-                    S[22 * 32] = (a & 1u) ? ru : T(0);          // w stays in shared memory (zero on rows that are not computed)
-                    S[23 * 32] = (a & 2u) ? rv : T(0);
-                    S[24 * 32] = (a & 4u) ? rw : T(0);
-                } else {
-                    a = in ? ((unsigned int)__ldg(P.act + i) & kActCompute) : 0u;
-                    ru = visc_row_scaled<T, 3, 0>(P.cs, jj, stv, __ldg(P.cs[0] + jj), du, nb);
-                    rv = visc_row_scaled<T, 3, 1>(P.cs, jj, stv, __ldg(P.cs[1] + jj), dv, nb);
-                    rw = visc_row_scaled<T, 3, 2>(P.cs, jj, stv, __ldg(P.cs[2] + jj), dw, nb);
-                    if (a & 1u) w[i] = ru;
-                    if (a & 2u) w[NL + i] = rv;
-                    if (a & 4u) w[2 * NL + i] = rw;
-                }
-                if (a & 1u) { wr += (double)du * (double)ru; rr += (double)du * (double)du; }
-                if (a & 2u) { wr += (double)dv * (double)rv; rr += (double)dv * (double)dv; }
-                if (a & 4u) { wr += (double)dw * (double)rw; rr += (double)dw * (double)dw; }
-            }
-        }
-        tick();
-        grid_allreduce2(rr, wr, partials, gs);
-        tick();
-        delta = rr;
-        if (rr < tol2) done = 1;
-        else if (iter >= max_iter || !(rr == rr)) done = 2;
-        if (done) break;
-        dl = wr;
-        {
-            double a, b;
-            cg_sr_scalars(rr, wr, gamma_old, alpha_d, first, a, b);
-            alpha_d = a; beta_d = b;
-        }
-        gamma_old = rr;
-        first = false;
-        // ---- phase B: p = r + beta p, s = w + beta s, x += alpha p, r -= alpha s
-        {
-            const T alpha = (T)alpha_d, beta = (T)beta_d;
-            int j = 0;
-            for (long long k = gw; k < c_hi; k += nw, ++j) {
-                const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
-                if (i >= NL) continue;
-                T rv[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) rv[c] = r[c * NL + i];
-                if (j < res_trips) {
-                    T* S = svals + ((size_t)(j * kWarps + warp) * kResVals) * 32 + lane;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const T pn = rv[c] + beta * S[(16 + c) * 32];
-                        const T sn = S[(22 + c) * 32] + beta * S[(19 + c) * 32];
-                        S[(16 + c) * 32] = pn;
-                        S[(19 + c) * 32] = sn;
-                        S[(25 + c) * 32] += alpha * pn;
-                        r[c * NL + i] = rv[c] - alpha * sn;
-                    }
-                } else {                               // beyond the resident trips: through global memory
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const long long e = c * NL + i;
-                        const T pn = rv[c] + beta * p[e];
-                        const T sn = w[e] + beta * sv[e];
-                        p[e] = pn;
-                        sv[e] = sn;
-                        x[e] += alpha * pn;
-                        r[e] = rv[c] - alpha * sn;
-                    }
-                }
-            }
-        }
-        iter += 1;
-        tick();
-        gs.sync();
-        tick();
-    }
-    // ---- epilogue: the resident p, s, x go back to global memory (w is scratch)
-    for (int j = 0; j < res_trips; ++j) {
-        const long long k = gw + (long long)j * nw;
-        if (k >= c_hi) break;
-        const long long i = (long long)__ldg(seg + k) * kSegPts + lane;
-        if (i >= NL) continue;
-        const T* S = svals + ((size_t)(j * kWarps + warp) * kResVals) * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            p[c * NL + i] = S[(16 + c) * 32];
-            sv[c * NL + i] = S[(19 + c) * 32];
-            x[c * NL + i] = S[(25 + c) * 32];
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        st->delta = delta; st->delta_old = gamma_old; st->dq = dl; st->alpha = alpha_d; st->beta = beta_d;
-        st->iter = iter; st->done = done; st->sr_first = first ? 1 : 0;
-    }
-    (void)nohot;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Second form of the resident kernel: the residual of the CTA's own points is kept in shared memory as well (31 values per
-// point), and so are the segment ids, so phase B touches global memory only to STORE the new r for the neighbours' stencils —
-// no dependent L2 read in it any more (the first form spends two sequential round trips there: segment id, then r, per
-// trip).  Slots are addressed by the position of a segment in the CTA's run, so exactly `chunk` slots are needed: 29 of
-// 7 972 B for the 4 253 segments of the 256^3 benchmark scene = 231 KB of the 227 KiB an SM offers.  Positions beyond
-// `res_slots` (longer lists) run through global memory as before.
+// at exit (once per launch of up to 256 iterations), so the global state between launches is unchanged.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRes2Vals = 31;     // per point: 16 coefficients, p[3], s[3], w[3], x[3], r[3]
-constexpr int kResidentFormDefault = 2;   // which resident kernel runs when "resident_form" / FLUIDSOLVER_B200_RESIDENT is not set
+constexpr int kResidentFormDefault = 2;   // 0 = persistent CG through global memory, non-zero = shared-memory resident kernel ("resident_form" / FLUIDSOLVER_B200_RESIDENT)
 constexpr int kRes2Threads = 512;
 template <typename T> __host__ __device__ constexpr size_t res2_slot_bytes() { return (size_t)kRes2Vals * 32 * sizeof(T) + 32 + sizeof(int); }
 
@@ -2025,7 +1847,7 @@ static int visc3d_extrapolate_impl(fs_visc3d* h, int vec, int sweeps, void* stre
         const int push_to = (W.cap && k < sweeps) ? ((k - 1) & 1) : -1;
         if (k == 1 && region && W.cap) {
             FS_DISPATCH(h, visc3d_extrapolate_region_kernel<T><<<kSMs * 16, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, push_to, h->rowflag,
-                                                                                             region->list, region->nseg_dev));
+                                                                                             region->list, region->nseg_dev, g_begin, g_end));
             FS_LAUNCH_CHECK();
         } else if (k == 1 || !W.cap) {
             FS_DISPATCH(h, visc3d_extrapolate_kernel<T><<<full_grid, kThreads, 0, s>>>(h->L, vec_ptr<T>(h, vec), h->valid, k, W, push_to, 0,
@@ -2227,60 +2049,9 @@ static bool visc3d_use_persistent(const fs_visc3d* h) {
 }
 
 // `n` = iteration slots (classic: iterations; single-reduction: an extra closing slot evaluates r.r of the last iterate)
-// Shared-memory resident form of the single-reduction persistent kernel (single GPU / gathered solve; FLUIDSOLVER_B200_RESIDENT=0
-// switches it off).  Returns 1 if it cannot run here (nothing enqueued), so that the caller falls back.
-static int visc3d_persistent_resident(fs_visc3d* h, double sm, long long n, cudaStream_t s) {
-    int dev = 0, smem_max = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 1;
-    const void* fn = nullptr;
-    size_t slot = 0;
-    static int threads_env = -1;
-    if (threads_env < 0) { const char* e = getenv("FLUIDSOLVER_B200_RESIDENT_THREADS"); threads_env = e ? atoi(e) : 0; }
-    const int kThreadsRes = threads_env == 1024 ? 1024 : 512;      // 1024 threads (64 registers) spill in the apply: 11.9 vs 8.1 us per iteration
-    FS_DISPATCH(h, { fn = kThreadsRes == 512 ? (const void*)visc3d_cg_sr_resident_kernel<T, 512> : (const void*)visc3d_cg_sr_resident_kernel<T, 1024>; slot = res_slot_bytes<T>(); });
-    const int kWarps = kThreadsRes / 32;
-    const int max_trips = (int)(((size_t)smem_max - 1024) / (kWarps * slot));       // 1 KB left for the static reduction scratch
-    if (max_trips < 1) return 1;
-    // grid first (it fixes the warp -> segment map), then as many resident trips as fit
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_trips * kWarps * slot)) != cudaSuccess) { cudaGetLastError(); return 1; }
-    const int cap = coop_max_blocks(fn, kThreadsRes, max_trips * kWarps * slot);
-    if (cap < 1) return 1;
-    int grid = seg_grid(h->seg.nseg, kWarps, cap < kSMs ? cap : kSMs);
-    if (const char* e = getenv("FLUIDSOLVER_B200_PERSIST_GRID")) { const int g = atoi(e); if (g >= 1 && g <= cap) grid = g; }
-    const long long chunk = ((long long)h->seg.nseg + grid - 1) / grid;        // segments per CTA (contiguous run of the list)
-    int trips = (int)((chunk + kWarps - 1) / kWarps);
-    if (trips < 1) trips = 1;
-    int res_trips = trips < max_trips ? trips : max_trips;
-    const size_t smem = (size_t)res_trips * kWarps * slot;
-    unsigned long long* prof = getenv("FLUIDSOLVER_B200_PROFILE") ? reinterpret_cast<unsigned long long*>(h->valid) : nullptr;
-    while (n > 0) {
-        int ni = (int)(n < (1 << 20) ? n : (1 << 20));
-        cudaError_t e = cudaMemsetAsync(h->bar, 0, sizeof(GridBar), s);
-        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-        FS_DISPATCH(h, {
-            Visc3Dev<T> P = dev_view<T>(h);
-            T* x = vec_ptr<T>(h, FS_VEC_X); T* r = vec_ptr<T>(h, FS_VEC_R); T* d = vec_ptr<T>(h, FS_VEC_D); T* q = vec_ptr<T>(h, FS_VEC_Q);
-            T* w = reinterpret_cast<T*>(h->d2);
-            const int* seg = h->seg.list; const int* nsegp = h->seg.nseg_dev;
-            CgState* st = h->st; double* partials = h->partials; GridBar* bar = h->bar;
-            void* args[] = {&P, &x, &r, &d, &q, &w, &seg, &nsegp, &st, &partials, &bar, &ni, &res_trips, &prof};
-            e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreadsRes), args, smem, s);
-        });
-        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported || e == cudaErrorInvalidValue) {
-            cudaGetLastError();
-            return 1;
-        }
-        if (e != cudaSuccess) return fail(FS_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
-        FS_LAUNCH_CHECK();
-        n -= ni;
-    }
-    (void)sm;
-    return FS_OK;
-}
-
-// Second resident form (visc3d_cg_sr_resident2_kernel: r resident as well, slots by run position); "resident_form" /
-// FLUIDSOLVER_B200_RESIDENT = 1 selects the first form, 0 the global-memory kernel.  Returns 1 if it cannot run here
-// (nothing enqueued).
+// Shared-memory resident form of the single-reduction persistent kernel (single GPU / gathered solve); "resident_form" /
+// FLUIDSOLVER_B200_RESIDENT = 0 selects the global-memory kernel.  Returns 1 if it cannot run here (nothing enqueued), so
+// that the caller falls back.
 static int resident_form() {
     const int v = tuning(OPT_RESIDENT_FORM);
     return v < 0 ? kResidentFormDefault : v;
@@ -2333,9 +2104,7 @@ static int visc3d_persistent(fs_visc3d* h, double sm, long long n, cudaStream_t 
     const bool sr = visc3d_use_sr(h);
     if (sr && !h->peers && !h->resident_failed) {
         const int form = resident_form();
-        int st = 1;
-        if (form == 2) st = visc3d_persistent_resident2(h, n, s);
-        if (st == 1 && form != 0) st = visc3d_persistent_resident(h, sm, n, s);
+        const int st = form != 0 ? visc3d_persistent_resident2(h, n, s) : 1;
         if (st != 1) return st;
         if (form != 0) h->resident_failed = true;   // not possible on this context: the global-memory form below takes over
     }
@@ -2530,6 +2299,30 @@ int fs_visc3d_set_window(fs_visc3d* h, int cell_lo, int cell_hi) {
     return FS_OK;
 }
 
+// :569-573 — the caller's velocities into the lattice vector x and the three extrapolation sweeps: around the active set
+// only (see visc3d_mark_region_kernel; "sparse_setup" / FLUIDSOLVER_B200_SPARSE_SETUP = 0 switches back), else on the whole
+// lattice / x-window.  Needs the pack of this solve (its activity map and segment list) enqueued on the same stream.  The
+// region list lives in `xseg` until the gathered solve reuses that list for its publish flags (stream order keeps the two apart).
+static int visc3d_load_extrapolate(fs_visc3d* h, const void* vx, const void* vy, const void* vz, int vel_dtype, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int sp = tuning(OPT_SPARSE_SETUP);
+    if ((sp < 0 ? kSparseSetupDefault : sp) != 0 && !h->comm && h->work.cap != 0u) {
+        FS_CUDA(cudaMemsetAsync(h->xflags, 0, (size_t)h->xseg.nseg_total, s));
+        visc3d_mark_region_kernel<<<kSMs * 8, 256, 0, s>>>(h->L, h->seg.list, h->seg.nseg_dev, h->xseg.nseg_total, h->xflags);
+        FS_LAUNCH_CHECK();
+        FS_TRY(h->xseg.enqueue(h->xflags, s, 1));
+        if (vel_dtype == FS_F32) {
+            FS_DISPATCH(h, visc3d_load_region_kernel<T, float><<<kSMs * 8, kThreads, 0, s>>>(h->L, (const float*)vx, (const float*)vy, (const float*)vz, vec_ptr<T>(h, FS_VEC_X), h->xseg.list, h->xseg.nseg_dev));
+        } else {
+            FS_DISPATCH(h, visc3d_load_region_kernel<T, double><<<kSMs * 8, kThreads, 0, s>>>(h->L, (const double*)vx, (const double*)vy, (const double*)vz, vec_ptr<T>(h, FS_VEC_X), h->xseg.list, h->xseg.nseg_dev));
+        }
+        FS_LAUNCH_CHECK();
+        return visc3d_extrapolate_impl(h, FS_VEC_X, 3, stream, &h->xseg);
+    }
+    FS_TRY(fs_visc3d_load(h, FS_VEC_X, vx, vy, vz, vel_dtype, stream));
+    return fs_visc3d_extrapolate(h, FS_VEC_X, 3, stream);
+}
+
 size_t fs_visc3d_gather_record_bytes(const fs_visc3d* h) { return h ? gather_record_bytes(h->esz) : 0; }
 int fs_visc3d_gather_reexport(fs_visc3d* h, void* records, int64_t cap, void* stream);
 
@@ -2544,8 +2337,7 @@ int fs_visc3d_gather_export(fs_visc3d* h, const void* vx, const void* vy, const 
         return fail(FS_ERR_ARG, "fs_visc3d_gather_export: the window must extend 4 cells beyond the owned planes");
     cudaStream_t s = (cudaStream_t)stream;
     FS_TRY(fs_visc3d_pack(h, sphi, lvol, vol_norm, stream));                    // window planes only (+ wipes the previous solve's segments)
-    FS_TRY(fs_visc3d_load(h, FS_VEC_X, vx, vy, vz, vel_dtype, stream));
-    FS_TRY(fs_visc3d_extrapolate(h, FS_VEC_X, 3, stream));
+    FS_TRY(visc3d_load_extrapolate(h, vx, vy, vz, vel_dtype, stream));          // (around the window's active rows only, unless switched off)
     FS_TRY(h->seg.finish());                                                    // (the list pack enqueued is not used: the global one follows the import)
     const long long nseg_total = h->xseg.nseg_total;
     FS_CUDA(cudaMemsetAsync(h->xflags, 0, (size_t)nseg_total, s));
@@ -2626,25 +2418,7 @@ int fs_visc3d_solve(fs_visc3d* h, double dt, double mu, double rho, double cell_
     const double scale = dt / cell_vol / rho;                                   // :567
     const double sm = scale * mu;
     FS_TRY(fs_visc3d_pack(h, sphi, lvol, cell_vol * 0.125, stream));            // :568 (+ active segment list)
-    const int sp = tuning(OPT_SPARSE_SETUP);
-    if ((sp < 0 ? kSparseSetupDefault : sp) != 0 && !h->comm && !h->windowed && h->work.cap != 0u) {
-        // :569-573 where the solve looks: velocities loaded and extrapolated around the active set only (see visc3d_mark_region_kernel)
-        FS_TRY(h->xseg.finish());
-        FS_CUDA(cudaMemsetAsync(h->xflags, 0, (size_t)h->xseg.nseg_total, s));
-        visc3d_mark_region_kernel<<<kSMs * 8, 256, 0, s>>>(h->L, h->seg.list, h->seg.nseg_dev, h->xseg.nseg_total, h->xflags);
-        FS_LAUNCH_CHECK();
-        FS_TRY(h->xseg.enqueue(h->xflags, s, 1));
-        if (vel_dtype == FS_F32) {
-            FS_DISPATCH(h, visc3d_load_region_kernel<T, float><<<kSMs * 8, kThreads, 0, s>>>(h->L, (const float*)vx, (const float*)vy, (const float*)vz, vec_ptr<T>(h, FS_VEC_X), h->xseg.list, h->xseg.nseg_dev));
-        } else {
-            FS_DISPATCH(h, visc3d_load_region_kernel<T, double><<<kSMs * 8, kThreads, 0, s>>>(h->L, (const double*)vx, (const double*)vy, (const double*)vz, vec_ptr<T>(h, FS_VEC_X), h->xseg.list, h->xseg.nseg_dev));
-        }
-        FS_LAUNCH_CHECK();
-        FS_TRY(visc3d_extrapolate_impl(h, FS_VEC_X, 3, stream, &h->xseg));
-    } else {
-        FS_TRY(fs_visc3d_load(h, FS_VEC_X, vx, vy, vz, vel_dtype, stream));     // :569-571
-        FS_TRY(fs_visc3d_extrapolate(h, FS_VEC_X, 3, stream));                  // :573
-    }
+    FS_TRY(visc3d_load_extrapolate(h, vx, vy, vz, vel_dtype, stream));          // :569-573 (where the solve looks)
     FS_TRY(visc3d_cg_begin_sparse(h, scale, mu, tol, max_iter, s));             // :574-587 on the active set
     // :588-612 (single-reduction CG: one extra slot whose apply evaluates r.r of the last iterate and sets the final status)
     int status = cg_drive(h->cg, [&](cudaStream_t ss, long long nb) { return visc3d_iterations(h, sm, nb, ss); }, (long long)max_iter + (visc3d_use_sr(h) ? 1 : 0), stats, s,
