@@ -198,13 +198,55 @@ void port_visc3d_extrapolate(int nx, int ny, int nz, int num_iter, double* vx, d
     }
 }
 
+/* Sum of a[i]*b[i] in the order of NumPy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum:
+ * below 8 elements sequential, up to 128 elements eight interleaved partial sums combined as a balanced tree, above that two
+ * halves with the split rounded down to a multiple of 8) — what `cp.sum(d * q)` (ViscosityCGSolver3D.py:585, :590, :600)
+ * evaluates to under the NumPy-backed cupy shim the golden fixtures were generated with.  The order depends on n only, never on
+ * the thread count or on scheduling, so the CG trajectory of this port is reproducible run to run (an OpenMP `reduction(+)`
+ * combines the threads' partial sums in arrival order: on the stiff 6x8x6 fixture that moved the iteration count between 95
+ * and 98 from one run to the next). */
+static double pw_sum(const double* a, const double* b, ptrdiff_t n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (ptrdiff_t i = 0; i < n; ++i) res += a[i] * b[i];
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j] * b[j];
+        ptrdiff_t i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j] * b[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i] * b[i];
+        return res;
+    }
+    ptrdiff_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return pw_sum(a, b, n2) + pw_sum(a + n2, b + n2, n - n2);
+}
+
+/* the same tree, its upper levels as OpenMP tasks (the split points depend on n only) */
+static double pw_sum_tasks(const double* a, const double* b, ptrdiff_t n) {
+    if (n <= (ptrdiff_t)1 << 17) return pw_sum(a, b, n);
+    ptrdiff_t n2 = n / 2;
+    n2 -= n2 % 8;
+    double s1 = 0.0, s2 = 0.0;
+#pragma omp task shared(s1)
+    s1 = pw_sum_tasks(a, b, n2);
+    s2 = pw_sum_tasks(a + n2, b + n2, n - n2);
+#pragma omp taskwait
+    return s1 + s2;
+}
+
 static double dot3(const geom_t* g, double* const* a, double* const* b) {
     double tot = 0.0;
     for (int A = 0; A < 3; ++A) {
         const ptrdiff_t n = (ptrdiff_t)g->sh[A][0] * g->sh[A][1] * g->sh[A][2];
         double s = 0.0;
-#pragma omp parallel for reduction(+ : s) schedule(static)
-        for (ptrdiff_t i = 0; i < n; ++i) s += a[A][i] * b[A][i];
+#pragma omp parallel
+#pragma omp single
+        s = pw_sum_tasks(a[A], b[A], n);
         tot += s;
     }
     return tot;

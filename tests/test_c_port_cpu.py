@@ -1,5 +1,6 @@
 """CPU: the C/OpenMP restatement (oracle/c_port) against the NumPy oracle and the reference's golden vectors."""
 import numpy as np
+import pytest
 
 from conftest import load_golden, rel_l2
 from oracle import c_port
@@ -59,16 +60,26 @@ def test_c_port_thread_control():
     assert n >= 1 and n == c_port.num_threads()
 
 
-def test_c_port_solve_vs_reference():
-    for tag in ("visc3d_solve_8x10x8", "visc3d_solve_stiff_6x8x6"):
-        f = load_golden(tag)
-        s = c_port.ViscosityCGSolver3D(f["gres"], f["bound_size"])
-        v = [f["vx"].copy(), f["vy"].copy(), f["vz"].copy()]
-        s.solve(float(f["dt"]), float(f["mu"]), float(f["rho"]), *v, f["sphi"], None, f["lphi"], f["lvol"], tol=float(f["tol"]))
-        it_ref = int(f["iterations"])
-        assert abs(s.iterations - it_ref) <= max(1, round(0.02 * it_ref)), (s.iterations, it_ref)
-        for a, n in zip(v, "xyz"):
-            assert rel_l2(a, f[f"v{n}_new"]) < 1e-4
+@pytest.mark.parametrize("threads", [1, 3, None])
+def test_c_port_solve_vs_reference(threads):
+    """The port's dot products follow NumPy's pairwise summation order (what the fixtures' cp.sum evaluated to), whatever the
+    OpenMP team: the reference's iteration counts are reproduced EXACTLY and run to run, also on the stiff fixture whose
+    count moves by three with the summation order."""
+    if threads is None:
+        c_port.use_all_cores()
+    else:
+        c_port.load().port_set_num_threads(threads)
+    try:
+        for tag in ("visc3d_solve_8x10x8", "visc3d_solve_stiff_6x8x6"):
+            f = load_golden(tag)
+            s = c_port.ViscosityCGSolver3D(f["gres"], f["bound_size"])
+            v = [f["vx"].copy(), f["vy"].copy(), f["vz"].copy()]
+            s.solve(float(f["dt"]), float(f["mu"]), float(f["rho"]), *v, f["sphi"], None, f["lphi"], f["lvol"], tol=float(f["tol"]))
+            assert s.iterations == int(f["iterations"]), (s.iterations, int(f["iterations"]))
+            for a, n in zip(v, "xyz"):
+                assert rel_l2(a, f[f"v{n}_new"]) < 1e-4
+    finally:
+        c_port.use_all_cores()
 
 
 def test_c_port_vs_numpy_oracle_scene():
@@ -81,6 +92,7 @@ def test_c_port_vs_numpy_oracle_scene():
     b = c_port.ViscosityCGSolver3D(sc["gres"], sc["bound_size"])
     vb = [sc[k].numpy().copy() for k in ("vx", "vy", "vz")]
     b.solve(*args, *vb, sc["sphi"].numpy(), None, None, sc["lvol"].numpy())
-    assert abs(a.trace.iterations - b.iterations) <= max(1, round(0.02 * a.trace.iterations))
+    # same kernels bit for bit, same summation order: the two oracles agree in every bit of the solution
+    assert a.trace.iterations == b.iterations
     for x, y in zip(va, vb):
-        assert rel_l2(x, y) < 1e-4
+        assert np.array_equal(x, y)
