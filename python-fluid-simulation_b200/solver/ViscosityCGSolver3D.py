@@ -11,7 +11,12 @@ Differences a caller can observe (all documented in DESIGN.md):
   * ``dtype=torch.float32`` selects fp32 vector/coefficient storage with fp64 dot products (the
     reference is fp64 throughout; fp64 is the default here);
   * a NaN residual aborts with the same ``ValueError("Failed to converge!")`` instead of spinning
-    for ``prod(gres)`` iterations.
+    for ``prod(gres)`` iterations;
+  * ``solve()`` loads and extrapolates the velocities only where it reads them (within five lattice layers
+    of a row the CG computes): ``vx, vy, vz``, ``b_*``, ``r_*``, ``delta`` and ``iterations`` are bit-identical to the
+    whole-lattice set-up, but ``x_*`` keeps stale values far from the liquid
+    (``solver._native.set_option("sparse_setup", 0)`` restores the reference's behaviour for ``x_*``; the module-level
+    ``extrapolate`` is always dense).
 """
 import ctypes
 
