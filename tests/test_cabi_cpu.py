@@ -106,3 +106,17 @@ int main(void) {
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     v, p, p2, _ = r.stdout.split()
     assert int(v) == N.load().fs_visc3d_workspace_bytes(32, 32, 32, N.FS_F64)
+
+
+def test_set_option_accepts_known_switches_only():
+    """fs_set_option: the tuning switches between result-equivalent kernel forms (no GPU needed to set them)."""
+    from solver import _native as N
+    lib = N.load()
+    for name in ("resident_form", "k1_block", "k1_tile", "sparse_setup"):
+        assert lib.fs_set_option(name.encode(), 1) == 0
+        assert lib.fs_set_option(name.encode(), -1) == 0          # back to the default
+    assert lib.fs_set_option(b"no_such_switch", 1) < 0
+    assert b"no_such_switch" in lib.fs_last_error()
+    assert lib.fs_set_option(None, 1) < 0
+    with pytest.raises(N.NativeError):
+        N.set_option("llred", 1)                                   # (an experiment that was measured and removed)
